@@ -1,0 +1,18 @@
+"""flowreg3d_b200 -- B200-native (sm_100a) drop-in for flowreg3D's dense 3-D optical-flow
+registration path.  Python host code + hand-written CUDA kernels behind a C ABI (libfr3d.so).
+
+Reference-facing surface (same names and argument meaning as FlowRegSuite/flowreg3D):
+    get_displacement, imregister_wrapper      core/optical_flow_3d.py
+    OFOptions                                 motion_correction/OF_options_3D.py
+    compensate_arr_3D                         motion_correction/compensate_arr_3D.py
+    B200Executor3D (BaseExecutor3D plugin)    motion_correction/parallelization/base_3d.py
+"""
+from .core import Context, Registration, get_displacement, imregister_wrapper  # noqa: F401
+from .plan import FlowParams  # noqa: F401
+from .options import OFOptions  # noqa: F401
+from .executor import B200Executor3D  # noqa: F401
+from .compensate import SequenceCorrector, compensate_arr_3D, compensate_arr_3D_sharded  # noqa: F401
+
+__all__ = ["get_displacement", "imregister_wrapper", "OFOptions", "compensate_arr_3D",
+           "compensate_arr_3D_sharded", "B200Executor3D", "SequenceCorrector", "Registration",
+           "FlowParams", "Context"]

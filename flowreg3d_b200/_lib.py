@@ -1,0 +1,117 @@
+"""ctypes binding of libfr3d.so (the C ABI declared in include/fr3d.h).
+
+There is no CPU fallback: if the CUDA library is missing or no B200 is visible the package raises.
+(tests/emu builds a CPU emulation of the kernel logic for the not-gpu tests; it is selected only by
+the test-suite through FR3D_LIBRARY_OVERRIDE and is never shipped.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+MAX_CHANNELS = 4
+ABI_VERSION = 1
+
+F32, F64, U8, U16, I16, I32 = range(6)
+_DTYPES = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.uint8): U8,
+           np.dtype(np.uint16): U16, np.dtype(np.int16): I16, np.dtype(np.int32): I32}
+
+
+def dtype_code(dt) -> int:
+    dt = np.dtype(dt)
+    if dt not in _DTYPES:
+        raise TypeError(f"libfr3d does not take dtype {dt}; supported: {[str(k) for k in _DTYPES]}")
+    return _DTYPES[dt]
+
+
+class AxisTable(C.Structure):
+    _fields_ = [("in_len", C.c_int32), ("out_len", C.c_int32), ("P", C.c_int32),
+                ("idx", C.c_void_p), ("wt", C.c_void_p)]
+
+
+class Level(C.Structure):
+    _fields_ = [("size", C.c_int32 * 3), ("h", C.c_double * 3), ("alpha", C.c_double * 3),
+                ("median", C.c_int32), ("from_full", AxisTable * 3), ("from_prev", AxisTable * 3)]
+
+
+class Plan(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("Z", C.c_int32), ("Y", C.c_int32), ("X", C.c_int32),
+                ("C", C.c_int32), ("max_batch", C.c_int32), ("n_levels", C.c_int32),
+                ("levels", C.POINTER(Level)), ("to_full", AxisTable * 3),
+                ("iterations", C.c_int32), ("update_lag", C.c_int32),
+                ("a_data", C.c_double * MAX_CHANNELS), ("a_smooth", C.c_double),
+                ("sweep", C.c_int32), ("interp", C.c_int32),
+                ("gauss_radius", (C.c_int32 * 3) * MAX_CHANNELS),
+                ("gauss_w", (C.c_void_p * 3) * MAX_CHANNELS)]
+
+
+class Fr3dError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libfr3d error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def library_path() -> Path:
+    ov = os.environ.get("FR3D_LIBRARY_OVERRIDE")
+    return Path(ov) if ov else HERE / "libfr3d.so"
+
+
+def load():
+    """Load libfr3d.so; raise loudly when it is absent (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not path.exists():
+        raise ImportError(
+            f"{path} not found: build it with `python -m flowreg3d_b200.build` (needs nvcc). "
+            "flowreg3d_b200 has no CPU fallback.")
+    L = C.CDLL(str(path))
+    vp, ci, cd, i64 = C.c_void_p, C.c_int, C.c_double, C.c_int64
+    sig = {
+        "fr3d_abi_version": (ci, []),
+        "fr3d_create": (ci, [C.POINTER(vp), ci, C.POINTER(Plan), vp]),
+        "fr3d_destroy": (None, [vp]),
+        "fr3d_last_error": (C.c_char_p, [vp]),
+        "fr3d_synchronize": (ci, [vp]),
+        "fr3d_launch_count": (i64, [vp]),
+        "fr3d_device_bytes": (i64, [vp]),
+        "fr3d_preprocess": (ci, [vp, vp, ci, ci, vp, vp, vp]),
+        "fr3d_set_reference": (ci, [vp, vp, vp, vp]),
+        "fr3d_get_displacement": (ci, [vp, vp, vp, ci, vp, ci]),
+        "fr3d_compensate": (ci, [vp, vp, ci, vp, vp, ci, ci, vp]),
+        "fr3d_resize3d": (ci, [vp, vp, ci, ci, ci, ci, C.POINTER(AxisTable), vp]),
+        "fr3d_warp": (ci, [vp, vp, ci, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]),
+        "fr3d_motion_tensor": (ci, [vp, vp, vp, ci, ci, ci, cd, cd, cd, ci, vp]),
+        "fr3d_sor_level": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, vp, cd, cd, cd, ci, ci, vp, cd, ci, vp]),
+        "fr3d_median5": (ci, [vp, vp, ci, ci, ci, ci, vp]),
+        "fr3d_mean_frames": (ci, [vp, vp, ci, i64, vp]),
+        "fr3d_fill_resize_table": (ci, [ci, ci, vp, ci, vp, vp]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)  # AttributeError if the library does not export a declared symbol
+        f.restype = res
+        f.argtypes = args
+    if L.fr3d_abi_version() != ABI_VERSION:
+        raise ImportError(f"{path}: ABI {L.fr3d_abi_version()} != binding ABI {ABI_VERSION}")
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "fr3d_abi_version", "fr3d_create", "fr3d_destroy", "fr3d_last_error", "fr3d_synchronize",
+    "fr3d_launch_count", "fr3d_device_bytes", "fr3d_preprocess", "fr3d_set_reference",
+    "fr3d_get_displacement", "fr3d_compensate", "fr3d_resize3d", "fr3d_warp", "fr3d_motion_tensor",
+    "fr3d_sor_level", "fr3d_median5", "fr3d_mean_frames", "fr3d_fill_resize_table",
+]
+
+
+def is_emulator() -> bool:
+    return bool(os.environ.get("FR3D_LIBRARY_OVERRIDE"))

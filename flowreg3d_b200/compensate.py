@@ -1,0 +1,256 @@
+"""Sequence entry points (drop-in boundary L4 of the reference).
+
+``compensate_arr_3D(c1, c_ref, options)`` has the signature, shape canonicalisation and return
+contract of flowreg3d.motion_correction.compensate_arr_3D.compensate_arr_3D
+(compensate_arr_3D.py:13-143) and the batch semantics of BatchMotionCorrector.run
+(compensate_recording_3D.py:431-557):
+
+  * reference pre-processing (normalise against its own range, Gaussian pre-filter)   :198-254
+  * frames pre-processed against the reference's range                                :459-463
+  * first batch: w_init = mean flow of its first min(22, T) frames solved from zero   :342-393
+  * per batch: flow from w_init, compensation warp, w_init <- mean of the last <= 20 flows :476-485
+
+Unlike the reference, where the executor receives host arrays pre-processed by scipy, everything
+between the raw frames and (registered, flow) stays on the GPU: normalise + pre-filter, pyramid,
+level solves, flow up-sampling, compensation warp and the w_init averages.
+
+Multi-GPU (one process per GPU, torch.distributed/NCCL): frames of each batch are split into
+contiguous shards, the fixed volume is replicated, and the only exchange is one all-reduce of the
+partial w_init sums per batch.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import device as dev
+from .core import Registration
+from .options import OFOptions
+from .plan import FlowParams
+
+_OUT_TYPES = {"single": np.float32, "double": np.float64, "uint8": np.uint8, "uint16": np.uint16,
+              "int16": np.int16, "int32": np.int32}
+
+
+def flow_params_from_options(options) -> FlowParams:
+    """compensate_recording_3D.py:301-315."""
+    return FlowParams(alpha=tuple(float(a) for a in options.alpha), update_lag=int(options.update_lag),
+                      iterations=int(options.iterations),
+                      min_level=int(getattr(options, "effective_min_level", getattr(options, "min_level", 0))),
+                      levels=int(options.levels), eta=float(options.eta), a_smooth=float(options.a_smooth),
+                      a_data=options.a_data)
+
+
+def normalization_range(reference_raw: np.ndarray, channel_normalization) -> Tuple[np.ndarray, np.ndarray]:
+    """(lo, den) per channel such that normalised = (x - lo)/den  (util/image_processing_3D.py:12-92).
+    NB: the reference compares the enum against the string "separate"; JOINT ("joint") therefore takes
+    the global branch with eps = 1e-8 in the denominator."""
+    mode = str(getattr(channel_normalization, "value", channel_normalization))
+    Cn = reference_raw.shape[-1]
+    if mode == "separate":
+        lo = np.array([reference_raw[..., c].min() for c in range(Cn)], dtype=np.float64)
+        hi = np.array([reference_raw[..., c].max() for c in range(Cn)], dtype=np.float64)
+        rng = hi - lo
+        return lo, np.where(rng > 0, rng, 1.0)
+    lo = np.float64(reference_raw.min())
+    hi = np.float64(reference_raw.max())
+    return np.full(Cn, lo), np.full(Cn, hi - lo + 1e-8)
+
+
+def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous split of n frames over `world` ranks (first n % world ranks get one more)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class SequenceCorrector:
+    """Stateful batch processor: owns the Registration, the fixed volume and the w_init chain."""
+
+    def __init__(self, reference_raw: np.ndarray, options, max_batch: Optional[int] = None,
+                 device: Optional[torch.device] = None, group=None):
+        if bool(getattr(options, "cc_initialization", False)):
+            raise NotImplementedError("cc_initialization is not implemented on the B200 path")
+        if bool(getattr(options, "update_reference", False)):
+            raise NotImplementedError("update_reference is not implemented on the B200 path")
+        self.options = options
+        ref = np.asarray(reference_raw)
+        if ref.ndim == 3:
+            ref = ref[..., None]
+        self.reference_raw = ref.astype(np.float64)  # compensate_recording_3D.py:201-205
+        Z, Y, X, Cn = self.reference_raw.shape
+        self.shape, self.C = (Z, Y, X), Cn
+        self.group = group
+        self.world = 1
+        self.rank = 0
+        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(group)
+            self.rank = torch.distributed.get_rank(group)
+        fp = flow_params_from_options(options)
+        if fp.a_smooth != 1.0:
+            raise NotImplementedError("a_smooth != 1.0 (nonlinear smoothness term) is not implemented on the B200 path")
+        mb = int(max_batch or options.buffer_size)
+        self.reg = Registration(self.shape, Cn, fp, max_batch=mb,
+                                interpolation_method=getattr(options, "interpolation_method", "cubic"),
+                                sigma=options.sigma, device=device)
+        self.device = self.reg.device
+        # weights (compensate_recording_3D.py:211-224)
+        wvec = [options.get_weight_at(c, Cn) for c in range(Cn)]
+        if all(np.ndim(w) == 0 for w in wvec):
+            weight = np.ones((1, 1, 1, Cn)) * np.asarray(wvec, float).reshape(1, 1, 1, Cn)
+            weight = np.broadcast_to(weight, (Z, Y, X, Cn))
+        else:
+            weight = np.ones((Z, Y, X, Cn))
+            for c in range(Cn):
+                weight[..., c] = wvec[c]
+        self.lo, self.den = normalization_range(self.reference_raw,
+                                                getattr(options, "channel_normalization", "together"))
+        ref_dev = dev.to_device(self.reference_raw, self.device)
+        # the reference normalises the fixed volume against ITS OWN range (normalization_ref=None);
+        # that is the same (lo, den) as above
+        ref_proc = self.reg.preprocess(ref_dev[None], self.lo, self.den)
+        self.reg.set_reference(ref_proc[0], weight=weight, ref_raw=ref_dev)
+        self.w_init: Optional[torch.Tensor] = None  # (Z,Y,X,3) float32 on device
+
+    # -- helpers ------------------------------------------------------------------------
+    def _flows(self, proc: torch.Tensor, uvw: Optional[torch.Tensor]) -> torch.Tensor:
+        outs = []
+        for t0 in range(0, proc.shape[0], self.reg.max_batch):
+            outs.append(self.reg.get_displacement(proc[t0:t0 + self.reg.max_batch], uvw=uvw))
+        return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+
+    def _mean_of(self, flows: Optional[torch.Tensor], count: int) -> torch.Tensor:
+        """Mean over `count` frames of the GLOBAL batch, `flows` being this rank's share."""
+        Z, Y, X = self.shape
+        if self.world == 1:
+            return self.reg.mean_frames(flows)
+        part = torch.zeros((Z, Y, X, 3), dtype=torch.float32, device=self.device)
+        if flows is not None and flows.shape[0] > 0:
+            part = self.reg.mean_frames(flows) * float(flows.shape[0])
+            self.reg.sync()
+        torch.distributed.all_reduce(part, op=torch.distributed.ReduceOp.SUM, group=self.group)
+        return part / float(count)
+
+    # -- one batch ------------------------------------------------------------------------
+    def process_batch(self, raw_local, global_size: Optional[int] = None, local_offset: int = 0,
+                      compensate: bool = True):
+        """raw_local: this rank's frames (t,Z,Y,X,C) of the current batch (ndarray or device tensor);
+        global_size / local_offset place them in the global batch (defaults: single process).
+        Returns device tensors (registered float32 (t,Z,Y,X,C), flows float32 (t,Z,Y,X,3))."""
+        raw = self.reg._as_dev(raw_local, None, None)
+        t = raw.shape[0]
+        G = t if global_size is None else int(global_size)
+        proc = self.reg.preprocess(raw, self.lo, self.den) if t > 0 else None
+        if self.w_init is None:
+            # bootstrap (compensate_recording_3D.py:359-388): first min(22, G) frames from zero flow
+            n_init = min(22, G)
+            a, b = max(0, -local_offset), max(0, min(t, n_init - local_offset))
+            w0 = self._flows(proc[a:b], None) if b > a else None
+            self.w_init = self._mean_of(w0, n_init)
+        use_chain = bool(getattr(self.options, "update_initialization_w", True))
+        uvw = self.w_init if use_chain else torch.zeros_like(self.w_init)
+        flows = self._flows(proc, uvw) if t > 0 else None
+        if use_chain:
+            # (:481-485) mean of the last <= 20 flows of the global batch
+            first = G - 20 if G > 20 else 0
+            a, b = max(0, first - local_offset), t
+            self.w_init = self._mean_of(flows[a:b] if (flows is not None and b > a) else None, G - first)
+        reg = None
+        if compensate and t > 0:
+            outs = []
+            for t0 in range(0, t, self.reg.max_batch):
+                outs.append(self.reg.compensate(raw[t0:t0 + self.reg.max_batch], flows[t0:t0 + self.reg.max_batch]))
+            reg = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+        return reg, flows
+
+    def close(self):
+        self.reg.ctx.close()
+
+
+def compensate_arr_3D(c1: np.ndarray, c_ref: np.ndarray, options=None,
+                      progress_callback: Optional[Callable[[int, int], None]] = None,
+                      device: Optional[torch.device] = None):
+    """Drop-in for flowreg3d.motion_correction.compensate_arr_3D: returns (registered, flow) with
+    registered shaped like c1 and flow (T,Z,Y,X,3) float32."""
+    c1 = np.asarray(c1)
+    c_ref = np.asarray(c_ref)
+    squeezed = False
+    original_shape = c1.shape
+    if c1.size == 0:
+        raise ValueError("Input array cannot be empty")
+    if c1.ndim == 4 and c_ref.ndim == 3:
+        c1 = c1[..., None]
+        c_ref = c_ref[..., None]
+        squeezed = True
+    elif c1.ndim == 3:
+        c1 = c1[None, :, :, :, None]
+        if c_ref.ndim == 3:
+            c_ref = c_ref[..., None]
+        squeezed = True
+    options = OFOptions() if options is None else options.copy()
+    T = c1.shape[0]
+    seq = SequenceCorrector(c_ref, options, device=device)
+    registered = np.empty_like(c1)
+    w = np.empty((T,) + seq.shape + (3,), np.float32)
+    done = 0
+    try:
+        for b0 in range(0, T, int(options.buffer_size)):
+            b1 = min(T, b0 + int(options.buffer_size))
+            reg, flows = seq.process_batch(c1[b0:b1])
+            seq.reg.sync()
+            registered[b0:b1] = dev.to_host(reg)
+            w[b0:b1] = dev.to_host(flows)
+            done += b1 - b0
+            if progress_callback is not None:
+                try:
+                    progress_callback(done, T)
+                except Exception as e:  # compensate_recording_3D.py:158-162
+                    import warnings
+                    warnings.warn(f"Progress callback error: {e}")
+    finally:
+        seq.close()
+    tn = getattr(options, "output_typename", None)
+    if tn and tn in _OUT_TYPES:
+        registered = registered.astype(_OUT_TYPES[tn])
+    if squeezed:
+        if len(original_shape) == 3:
+            registered = np.squeeze(registered)
+            w = np.squeeze(w, axis=0)
+        elif len(original_shape) == 4:
+            registered = np.squeeze(registered, axis=-1)
+    return registered, w
+
+
+def compensate_arr_3D_sharded(c1: np.ndarray, c_ref: np.ndarray, options=None, group=None,
+                              device: Optional[torch.device] = None):
+    """Multi-GPU variant: every rank passes the same (T,Z,Y,X,C) array (or a memory map of it) and
+    gets back ITS shard: (registered, flow, frame_indices).  Results are identical in layout to
+    compensate_arr_3D restricted to frame_indices."""
+    c1 = np.asarray(c1)
+    c_ref = np.asarray(c_ref)
+    if c1.ndim == 4:
+        c1 = c1[..., None]
+    if c_ref.ndim == 3:
+        c_ref = c_ref[..., None]
+    options = OFOptions() if options is None else options.copy()
+    seq = SequenceCorrector(c_ref, options, device=device, group=group)
+    regs, flows, idx = [], [], []
+    T = c1.shape[0]
+    try:
+        for b0 in range(0, T, int(options.buffer_size)):
+            b1 = min(T, b0 + int(options.buffer_size))
+            lo, hi = shard_bounds(b1 - b0, seq.world, seq.rank)
+            reg, fl = seq.process_batch(c1[b0 + lo:b0 + hi], global_size=b1 - b0, local_offset=lo)
+            seq.reg.sync()
+            if hi > lo:
+                regs.append(dev.to_host(reg).copy())
+                flows.append(dev.to_host(fl).copy())
+                idx.extend(range(b0 + lo, b0 + hi))
+    finally:
+        seq.close()
+    Z, Y, X = seq.shape
+    if regs:
+        return np.concatenate(regs, 0), np.concatenate(flows, 0), np.asarray(idx)
+    return (np.empty((0, Z, Y, X, seq.C), np.float32), np.empty((0, Z, Y, X, 3), np.float32), np.asarray(idx, int))

@@ -1,0 +1,387 @@
+"""Per-pair entry points with the reference's signatures (drop-in boundary B2):
+
+    get_displacement(fixed, moving, alpha, update_lag, iterations, min_level, levels, eta, a_smooth,
+                     a_data, const_assumption, uvw, weight) -> (Z,Y,X,3) float64
+    imregister_wrapper(f2_level, u, v, w, f1_level, interpolation_method) -> float32
+
+(reference: src/flowreg3d/core/optical_flow_3d.py:319-333 and :22-74), plus the Registration
+context they are built on.  All per-voxel work happens in libfr3d's CUDA kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, device as dev
+from .plan import FlowParams, PlanHolder, SWEEP_LEXICOGRAPHIC, TableSet, make_tables
+
+
+def _check(ctx, rc):
+    if rc != 0:
+        msg = _lib.load().fr3d_last_error(ctx)
+        raise _lib.Fr3dError(rc, msg.decode() if msg else "?")
+
+
+def _stream_handle(device: torch.device) -> int:
+    if device.type != "cuda":
+        return 0
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class Context:
+    """RAII wrapper of fr3d_ctx."""
+
+    def __init__(self, plan: Optional[PlanHolder] = None, device: Optional[torch.device] = None):
+        self.lib = _lib.load()
+        self.device = device if device is not None else dev.default_device()
+        self.plan = plan
+        h = C.c_void_p()
+        idx = self.device.index if self.device.type == "cuda" else 0
+        rc = self.lib.fr3d_create(C.byref(h), idx or 0, C.byref(plan.plan) if plan is not None else None,
+                                  _stream_handle(self.device))
+        if rc != 0:
+            msg = self.lib.fr3d_last_error(None)
+            raise _lib.Fr3dError(rc, msg.decode() if msg else "?")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.fr3d_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        _check(self.h, self.lib.fr3d_synchronize(self.h))
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.fr3d_launch_count(self.h))
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self.lib.fr3d_device_bytes(self.h))
+
+
+_bare: dict = {}
+
+
+def bare_context(device: Optional[torch.device] = None) -> Context:
+    """Plan-less context serving the stage entry points (one per device)."""
+    device = device if device is not None else dev.default_device()
+    key = str(device)
+    if key not in _bare:
+        _bare[key] = Context(None, device)
+    return _bare[key]
+
+
+class Registration:
+    """B frames against one fixed volume: pre-process, flow, compensation -- device resident.
+
+    Mirrors what BatchMotionCorrector asks of an executor (compensate_recording_3D.py:285-340):
+    the fixed volume's pyramid is built once (set_reference) and reused for every frame.
+    """
+
+    def __init__(self, shape, n_channels: int, params: FlowParams, max_batch: int = 1,
+                 interpolation_method: str = "cubic", sigma=None, sweep: int = SWEEP_LEXICOGRAPHIC,
+                 device: Optional[torch.device] = None):
+        meth = str(getattr(interpolation_method, "value", interpolation_method)).lower()
+        if meth not in ("cubic", "linear"):
+            raise ValueError("Unsupported interpolation method. Use 'linear' or 'cubic'.")
+        self.shape = tuple(int(s) for s in shape)
+        self.C = int(n_channels)
+        self.max_batch = int(max_batch)
+        self.plan = PlanHolder(self.shape, self.C, params, max_batch=max_batch,
+                               interp=3 if meth == "cubic" else 1, sigma=sigma, sweep=sweep)
+        self.ctx = Context(self.plan, device)
+        self.device = self.ctx.device
+        self._ref_raw = None
+        self._keep = []
+
+    # -- reference ------------------------------------------------------------------------
+    def set_reference(self, ref_proc, weight=None, ref_raw=None):
+        """ref_proc (Z,Y,X,C) pre-processed fixed volume; weight: None (1/C), 1-D per-channel,
+        (Z,Y,X) or (Z,Y,X,C) (core/optical_flow_3d.py:351-381); ref_raw: raw fixed volume used as
+        the out-of-volume fill of the compensation warp."""
+        Z, Y, X = self.shape
+        rp = self._as_dev(ref_proc, np.float32, (Z, Y, X, self.C))
+        wdev, wconst = None, None
+        if weight is None:
+            wconst = np.full(self.C, 1.0 / self.C)
+        else:
+            w = weight.cpu().numpy() if isinstance(weight, torch.Tensor) else np.asarray(weight)
+            w = w.astype(np.float64)
+            if w.ndim == 1:
+                if len(w) < self.C:
+                    we = np.full(self.C, 1.0 / self.C)
+                    we[:len(w)] = w
+                    w = we
+                elif len(w) > self.C:
+                    w = w[:self.C]
+                wconst = w / w.sum()
+            elif w.ndim == 3:
+                w = np.ones((Z, Y, X, self.C)) * w[..., None]
+            if wconst is None:
+                flat = w.reshape(-1, self.C)
+                if np.all(flat == flat[0]):
+                    wconst = flat[0].copy()  # spatially constant: broadcast on the device instead of uploading
+                else:
+                    wdev = self._as_dev(w, np.float32, (Z, Y, X, self.C))
+        wc = None
+        if wconst is not None:
+            # the reference resizes float32(weight); FillK rounds the float64 constant to float32 the same way
+            wc = (C.c_double * _lib.MAX_CHANNELS)(*([float(v) for v in wconst] + [0.0] * (_lib.MAX_CHANNELS - self.C)))
+        _check(self.ctx.h, self.ctx.lib.fr3d_set_reference(self.ctx.h, dev.ptr(rp), dev.ptr(wdev), wc))
+        if ref_raw is not None:
+            rr = ref_raw if isinstance(ref_raw, torch.Tensor) else np.asarray(ref_raw)
+            if not isinstance(rr, torch.Tensor) and rr.dtype not in _lib._DTYPES:
+                rr = rr.astype(np.float64)
+            self._ref_raw = self._as_dev(rr, None, (Z, Y, X, self.C))
+        self.ctx.sync()  # rp / wdev may be temporaries
+
+    # -- stages ---------------------------------------------------------------------------
+    def preprocess(self, raw, lo, den, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """(raw - lo)/den then the Gaussian pre-filter; raw (B,Z,Y,X,C) any supported dtype, device
+        tensor or ndarray; returns device float32 (B,Z,Y,X,C)."""
+        raw_t = self._as_dev(raw, None, None)
+        if raw_t.dim() == 4:
+            raw_t = raw_t[None]
+        B = raw_t.shape[0]
+        if tuple(raw_t.shape[1:]) != self.shape + (self.C,):
+            raise ValueError(f"raw frames have shape {tuple(raw_t.shape)}, expected (B,{self.shape},{self.C})")
+        if out is None:
+            out = dev.empty((B,) + self.shape + (self.C,), np.float32, self.device)
+        lo = np.broadcast_to(np.asarray(lo, float), (self.C,)).copy()
+        den = np.broadcast_to(np.asarray(den, float), (self.C,)).copy()
+        _check(self.ctx.h, self.ctx.lib.fr3d_preprocess(self.ctx.h, dev.ptr(raw_t), self._code(raw_t), B,
+                                                        lo.ctypes.data, den.ctypes.data, dev.ptr(out)))
+        self._keep = [raw_t]
+        return out
+
+    def get_displacement(self, moving_proc, uvw=None, out_dtype=np.float32,
+                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """moving_proc (B,Z,Y,X,C) float32 (device tensor or ndarray); uvw (Z,Y,X,3) shared initial
+        flow or None.  Returns device (B,Z,Y,X,3)."""
+        mv = self._as_dev(moving_proc, np.float32, None)
+        if mv.dim() == 4:
+            mv = mv[None]
+        B = mv.shape[0]
+        if tuple(mv.shape[1:]) != self.shape + (self.C,):
+            raise ValueError(f"moving frames have shape {tuple(mv.shape)}, expected (B,{self.shape},{self.C})")
+        uv = None if uvw is None else self._as_dev(uvw, np.float32, self.shape + (3,))
+        if out is None:
+            out = dev.empty((B,) + self.shape + (3,), out_dtype, self.device)
+        _check(self.ctx.h, self.ctx.lib.fr3d_get_displacement(
+            self.ctx.h, dev.ptr(mv), dev.ptr(uv), B, dev.ptr(out), self._code(out)))
+        self._keep = [mv, uv]
+        return out
+
+    def compensate(self, raw, flow, ref_raw=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Warp B raw frames with their flows (float32), out-of-volume voxels from ref_raw."""
+        raw_t = self._as_dev(raw, None, None)
+        if raw_t.dim() == 4:
+            raw_t = raw_t[None]
+        B = raw_t.shape[0]
+        fl = self._as_dev(flow, np.float32, (B,) + self.shape + (3,))
+        rr = self._ref_raw if ref_raw is None else self._as_dev(ref_raw, None, self.shape + (self.C,))
+        if rr is None:
+            raise ValueError("no raw reference: pass ref_raw here or to set_reference")
+        if out is None:
+            out = dev.empty((B,) + self.shape + (self.C,), np.float32, self.device)
+        _check(self.ctx.h, self.ctx.lib.fr3d_compensate(
+            self.ctx.h, dev.ptr(raw_t), self._code(raw_t), dev.ptr(fl), dev.ptr(rr), self._code(rr), B,
+            dev.ptr(out)))
+        self._keep = [raw_t, fl, rr]
+        return out
+
+    def mean_frames(self, frames: torch.Tensor) -> torch.Tensor:
+        """numpy.mean(frames, axis=0) for float32 device frames (T, ...) -> (...)."""
+        T = frames.shape[0]
+        n = frames[0].numel()
+        out = dev.empty(tuple(frames.shape[1:]), np.float32, self.device)
+        fr = frames.contiguous()
+        _check(self.ctx.h, self.ctx.lib.fr3d_mean_frames(self.ctx.h, dev.ptr(fr), T, n, dev.ptr(out)))
+        self._keep = [fr]
+        return out
+
+    def sync(self):
+        self.ctx.sync()
+
+    # -- helpers --------------------------------------------------------------------------
+    def _as_dev(self, a, dtype, shape):
+        if isinstance(a, torch.Tensor):
+            t = a
+            if dtype is not None and t.dtype != dev.torch_dtype(dtype):
+                t = t.to(dev.torch_dtype(dtype))
+            if t.device != self.device:
+                t = t.to(self.device)
+            t = t.contiguous()
+        else:
+            a = np.asarray(a)
+            if dtype is not None:
+                a = a.astype(dtype, copy=False)
+            elif a.dtype not in _lib._DTYPES:
+                a = a.astype(np.float64)
+            t = dev.to_device(a, self.device)
+        if shape is not None:
+            t = t.reshape(tuple(shape))
+        return t
+
+    @staticmethod
+    def _code(t: torch.Tensor) -> int:
+        return _lib.dtype_code(str(t.dtype).replace("torch.", ""))
+
+
+# --------------------------------------------------------------------------------------------
+# Reference-signature functions
+# --------------------------------------------------------------------------------------------
+def get_displacement(fixed, moving, alpha=(2, 2, 2), update_lag=10, iterations=20, min_level=0, levels=50,
+                     eta=0.8, a_smooth=0.5, a_data=0.45, const_assumption="gc", uvw=None, weight=None):
+    """Drop-in for flowreg3d.core.optical_flow_3d.get_displacement (:319-542): dense 3-D flow of
+    `moving` towards `fixed`, (Z,Y,X[,C]) arrays in, (Z,Y,X,3) float64 out, [...,0]=dx.
+    `const_assumption` is accepted and ignored exactly as in the reference (gradient constancy is
+    hard-wired, :457).  a_smooth must be 1.0 on this path (nonlinear smoothness: NotImplementedError)."""
+    fixed = np.asarray(fixed)
+    moving = np.asarray(moving)
+    if fixed.ndim == 3:
+        fixed = fixed[..., None]
+        moving = moving[..., None]
+    if fixed.ndim != 4 or fixed.shape != moving.shape:
+        raise ValueError(f"fixed/moving must be (Z,Y,X) or (Z,Y,X,C) of equal shape, got {fixed.shape} / {moving.shape}")
+    if float(a_smooth) != 1.0:
+        raise NotImplementedError("a_smooth != 1.0 (nonlinear smoothness term) is not implemented on the B200 path")
+    if isinstance(alpha, (int, float)):
+        alpha = (alpha,) * 3
+    Z, Y, X, Cn = fixed.shape
+    fp = FlowParams(alpha=tuple(alpha), update_lag=update_lag, iterations=iterations, min_level=min_level,
+                    levels=levels, eta=eta, a_smooth=a_smooth, a_data=a_data)
+    reg = Registration((Z, Y, X), Cn, fp, max_batch=1)
+    reg.set_reference(fixed.astype(np.float32), weight=weight)
+    uv = None if uvw is None else np.asarray(uvw).astype(np.float32)
+    out = reg.get_displacement(moving.astype(np.float32)[None], uvw=uv, out_dtype=np.float64)
+    reg.sync()
+    res = dev.to_host(out)[0].copy()
+    reg.ctx.close()
+    return res
+
+
+def imregister_wrapper(f2_level, u, v, w, f1_level, interpolation_method="cubic"):
+    """Drop-in for flowreg3d.core.optical_flow_3d.imregister_wrapper (:22-74): backward warp
+    warped(x) = f2(x + (u,v,w)); voxels leaving the volume take f1's value; float32 result with the
+    channel axis squeezed for single-channel input."""
+    meth = str(interpolation_method).lower()
+    if meth == "cubic":
+        order = 3
+    elif meth == "linear":
+        order = 1
+    else:
+        raise ValueError("Unsupported interpolation method. Use 'linear' or 'cubic'.")
+    f2 = np.asarray(f2_level)
+    f1 = np.asarray(f1_level)
+    if f2.ndim == 3:
+        f2 = f2[..., None]
+        f1 = f1[..., None]
+    Z, Y, X, Cn = f2.shape
+    ctx = bare_context()
+    d = ctx.device
+
+    def up(a, dt=None):
+        a = np.asarray(a)
+        if dt is not None:
+            a = a.astype(dt, copy=False)
+        elif a.dtype not in _lib._DTYPES:
+            a = a.astype(np.float64)
+        return dev.to_device(a, d)
+
+    f2t, f1t = up(f2), up(np.broadcast_to(f1, f2.shape))
+    ut, vt, wt = (up(np.broadcast_to(np.asarray(a), (Z, Y, X)), np.float64) for a in (u, v, w))
+    out = dev.empty((Z, Y, X, Cn), np.float32, d)
+    code = lambda t: _lib.dtype_code(str(t.dtype).replace("torch.", ""))
+    _check(ctx.h, ctx.lib.fr3d_warp(ctx.h, dev.ptr(f2t), code(f2t), dev.ptr(ut), dev.ptr(vt), dev.ptr(wt),
+                                    dev.ptr(f1t), code(f1t), Z, Y, X, Cn, order, dev.ptr(out)))
+    ctx.sync()
+    res = dev.to_host(out).copy()
+    return res[..., 0] if Cn == 1 else res
+
+
+# --------------------------------------------------------------------------------------------
+# Stage wrappers (numpy in / numpy out) used by the stage-wise parity tests
+# --------------------------------------------------------------------------------------------
+def _np_stage(fn):
+    return fn
+
+
+def resize(img, size):
+    """imresize_fused_gauss_cubic3D (util/resize_util_3D.py:114-156) for float images."""
+    img = np.asarray(img)
+    x = img.astype(np.float32)
+    squeeze = x.ndim == 3
+    if squeeze:
+        x = x[..., None]
+    D, H, W, Cn = x.shape
+    size = tuple(int(s) for s in size[:3])
+    ts = make_tables((D, H, W), size)
+    ctx = bare_context()
+    src = dev.to_device(np.ascontiguousarray(np.moveaxis(x, -1, 0)), ctx.device)
+    dst = dev.empty((Cn,) + size, np.float32, ctx.device)
+    _check(ctx.h, ctx.lib.fr3d_resize3d(ctx.h, dev.ptr(src), Cn, D, H, W, ts.c_tables(), dev.ptr(dst)))
+    ctx.sync()
+    y = np.moveaxis(dev.to_host(dst), 0, -1)
+    y = y[..., 0] if squeeze else y
+    return np.ascontiguousarray(y).astype(img.dtype if np.issubdtype(img.dtype, np.floating) else np.float32)
+
+
+def motion_tensor(f1, f2, hz, hy, hx):
+    """get_motion_tensor_gc (core/optical_flow_3d.py:92-152) without its zero ring: (10,p,m,n)."""
+    f1 = np.asarray(f1)
+    f2 = np.asarray(f2)
+    f2f32 = 1 if f2.dtype == np.float32 else 0
+    p, m, n = f1.shape
+    ctx = bare_context()
+    a = dev.to_device(f1.astype(np.float32), ctx.device)
+    b = dev.to_device(f2.astype(np.float32), ctx.device)
+    J = dev.empty((10, p, m, n), np.float64, ctx.device)
+    _check(ctx.h, ctx.lib.fr3d_motion_tensor(ctx.h, dev.ptr(a), dev.ptr(b), p, m, n, float(hz), float(hy),
+                                             float(hx), f2f32, dev.ptr(J)))
+    ctx.sync()
+    return dev.to_host(J).copy()
+
+
+def sor_level(J, weight, uvw, alpha, h, iterations, update_lag, a_data, a_smooth=1.0, sweep=SWEEP_LEXICOGRAPHIC):
+    """compute_flow_3d (core/level_solver_3d.py:314-546) on interior arrays:
+    J (C,10,p,m,n), weight (C,p,m,n), uvw (3,p,m,n), alpha (x,y,z), h (hz,hy,hx) -> (3,p,m,n)."""
+    J = np.ascontiguousarray(J, np.float64)
+    Cn, _, p, m, n = J.shape
+    ctx = bare_context()
+    Jt = dev.to_device(J, ctx.device)
+    wt = dev.to_device(np.ascontiguousarray(weight, np.float64), ctx.device)
+    ut = dev.to_device(np.ascontiguousarray(uvw, np.float64), ctx.device)
+    out = dev.empty((3, p, m, n), np.float64, ctx.device)
+    al = np.asarray(alpha, float)
+    ad = np.broadcast_to(np.asarray(a_data, float), (Cn,)).copy()
+    _check(ctx.h, ctx.lib.fr3d_sor_level(ctx.h, dev.ptr(Jt), dev.ptr(wt), dev.ptr(ut), p, m, n, Cn,
+                                         al.ctypes.data, float(h[0]), float(h[1]), float(h[2]), int(iterations),
+                                         int(update_lag), ad.ctypes.data, float(a_smooth), int(sweep), dev.ptr(out)))
+    ctx.sync()
+    return dev.to_host(out).copy()
+
+
+def median5(vols):
+    """scipy.ndimage.median_filter(size=(5,5,5), mode="mirror") on (nvol,p,m,n) float64."""
+    v = np.ascontiguousarray(vols, np.float64)
+    if v.ndim == 3:
+        v = v[None]
+    nv, p, m, n = v.shape
+    ctx = bare_context()
+    s = dev.to_device(v, ctx.device)
+    o = dev.empty(v.shape, np.float64, ctx.device)
+    _check(ctx.h, ctx.lib.fr3d_median5(ctx.h, dev.ptr(s), nv, p, m, n, dev.ptr(o)))
+    ctx.sync()
+    return dev.to_host(o).copy()

@@ -1,0 +1,688 @@
+// fr3d_api.cu -- C ABI (include/fr3d.h) and the coarse-to-fine level driver
+// (core/optical_flow_3d.py:389-541 of the reference) on top of the kernels in fr3d_kernels.h and
+// fr3d_sor.h.  Built for sm_100a by flowreg3d_b200/build.py; the FR3D_EMU build of this same file
+// is the test-only kernel-logic emulator (tests/emu).
+#include <memory>
+
+#include "fr3d_sor.h"
+
+using namespace fr3d;
+
+namespace {
+
+struct DevTable {
+    int in_len = 0, out_len = 0, P = 0;
+    Buf<int32_t> idx;
+    Buf<float> wt;
+    void upload(Device& d, const fr3d_axis_table& t)
+    {
+        in_len = t.in_len;
+        out_len = t.out_len;
+        P = t.P;
+        if (P > 0) {
+            FR3D_REQUIRE(t.idx && t.wt && t.in_len > 0 && t.out_len > 0, "axis table with null data");
+            idx.upload(d, t.idx, (size_t)t.out_len * t.P);
+            wt.upload(d, t.wt, (size_t)t.out_len * t.P);
+        }
+    }
+};
+
+struct LevelDev {
+    int pz = 0, py = 0, px = 0;
+    int64_t N = 0;
+    double hz = 1, hy = 1, hx = 1;
+    double alpha[3] = {0, 0, 0};
+    bool median = false;
+    DevTable full[3], prev[3];
+    Buf<float> f1;     // (C, N) natural planar: the reference pyramid level
+    Buf<double> wskew; // (C, N) skewed: resized channel weights
+};
+
+// element strides of a 5-D view (o0, o1, z, y, x)
+struct View {
+    int64_t s0, s1, sz, sy, sx;
+};
+inline View planar(int64_t n1, int64_t D, int64_t H, int64_t W)
+{
+    return View{n1 * D * H * W, D * H * W, H * W, W, 1};
+}
+
+} // namespace
+
+struct fr3d_ctx {
+    Device dev;
+    std::string err;
+    bool has_plan = false, ref_set = false;
+    int Z = 0, Y = 0, X = 0, C = 0, max_batch = 0;
+    int iterations = 0, update_lag = 1, sweep = 0, interp = 3;
+    double a_data[FR3D_MAX_CHANNELS] = {0, 0, 0, 0};
+    double a_smooth = 1.0;
+    std::vector<std::unique_ptr<LevelDev>> levels;
+    DevTable to_full[3];
+    PreGauss pre;
+    Buf<double> pre_w[FR3D_MAX_CHANNELS][3];
+    // workspaces (grow-only)
+    Buf<float> t1, t2, f2, tmp, fscr;
+    Buf<double> uvw_a, uvw_b, coef, J, L, AB, d, dnat, g1, g2, wnat;
+    Buf<unsigned> bar;
+    DevTable stage_tab[3];
+};
+
+static thread_local std::string g_create_err;
+
+// ---- building blocks -------------------------------------------------------------------------
+template <class SrcT, class DstT>
+static void resize_pass(fr3d_ctx* c, const SrcT* src, const int64_t ss[5], DstT* dst, const int64_t ds[5],
+                        const int64_t n[5], int r, const DevTable& t)
+{
+    ResizePassK<SrcT, DstT> k;
+    k.src = src;
+    k.dst = dst;
+    for (int q = 0; q < 5; ++q) {
+        k.n[q] = n[q];
+        k.ss[q] = ss[q];
+        k.ds[q] = ds[q];
+    }
+    k.r = r;
+    k.P = t.P;
+    k.idx = t.idx.p;
+    k.wt = t.wt.p;
+    launch(c->dev, k, n[0] * n[1] * n[2] * n[3] * n[4]);
+}
+
+// Separable resize of n0*n1 volumes (D,H,W) -> (od,oh,ow): X, then Y, then Z pass
+// (util/resize_util_3D.py:132-145), float32 intermediates.
+template <class SrcT, class DstT>
+static void resize3(fr3d_ctx* c, const SrcT* src, View sv, int64_t n0, int64_t n1, int D, int H, int W,
+                    DstT* dst, View dv, const DevTable tabs[3])
+{
+    const int ow = tabs[0].out_len, oh = tabs[1].out_len, od = tabs[2].out_len;
+    FR3D_REQUIRE(tabs[0].in_len == W && tabs[1].in_len == H && tabs[2].in_len == D,
+                 "resize tables (%d,%d,%d) do not match volume (%d,%d,%d)", tabs[2].in_len, tabs[1].in_len,
+                 tabs[0].in_len, D, H, W);
+    float* a = c->t1.ensure(c->dev, (size_t)(n0 * n1) * D * H * ow);
+    float* b = c->t2.ensure(c->dev, (size_t)(n0 * n1) * D * oh * ow);
+    const View av = planar(n1, D, H, ow), bv = planar(n1, D, oh, ow);
+    {
+        const int64_t n[5] = {n0, n1, D, H, ow};
+        const int64_t ss[5] = {sv.s0, sv.s1, sv.sz, sv.sy, sv.sx};
+        const int64_t ds[5] = {av.s0, av.s1, av.sz, av.sy, av.sx};
+        resize_pass<SrcT, float>(c, src, ss, a, ds, n, 4, tabs[0]);
+    }
+    {
+        const int64_t n[5] = {n0, n1, D, oh, ow};
+        const int64_t ss[5] = {av.s0, av.s1, av.sz, av.sy, av.sx};
+        const int64_t ds[5] = {bv.s0, bv.s1, bv.sz, bv.sy, bv.sx};
+        resize_pass<float, float>(c, a, ss, b, ds, n, 3, tabs[1]);
+    }
+    {
+        const int64_t n[5] = {n0, n1, od, oh, ow};
+        const int64_t ss[5] = {bv.s0, bv.s1, bv.sz, bv.sy, bv.sx};
+        const int64_t ds[5] = {dv.s0, dv.s1, dv.sz, dv.sy, dv.sx};
+        resize_pass<float, DstT>(c, b, ss, dst, ds, n, 2, tabs[2]);
+    }
+}
+
+// Cubic B-spline coefficients of B*C volumes (any dtype / strides) -> c->coef.
+static void spline_prefilter(fr3d_ctx* c, const void* src, int dt, int64_t sb, int64_t sc, int64_t sz,
+                             int64_t sy, int64_t sx, int B, int C, int Z, int Y, int X)
+{
+    const size_t n = (size_t)B * C * (Z + 3) * (Y + 3) * (X + 3);
+    double* coef = c->coef.ensure(c->dev, n);
+    SplineZK kz{src, dt, sb, sc, sz, sy, sx, coef, B, C, Z, Y, X};
+    launch(c->dev, kz, (int64_t)B * Y * X * C);
+    SplineYK ky{coef, Z, Y, X};
+    launch(c->dev, ky, (int64_t)B * C * (Z + 3) * X);
+    SplineXK kx{coef, X};
+    launch(c->dev, kx, (int64_t)B * C * (Z + 3) * (Y + 3));
+}
+
+static void check_dtype(int dt)
+{
+    FR3D_REQUIRE(dtype_size(dt) != 0, "unsupported dtype code %d", dt);
+}
+
+// Level solve on skewed storage; J, L assembled; result du,dv,dw in c->d (skewed).
+static void run_sor(fr3d_ctx* c, int B, int C, int p, int m, int n, const double* J, const double* wgt,
+                    const double* L, double ax, double ay, double az, int T, int lag, const double* a_data,
+                    int sweep)
+{
+    FR3D_REQUIRE(sweep == FR3D_SWEEP_LEXICOGRAPHIC, "sweep order %d is not implemented", sweep);
+    const int64_t N = (int64_t)p * m * n;
+    SorParams P;
+    P.p = p;
+    P.m = m;
+    P.n = n;
+    P.C = C;
+    P.B = B;
+    P.T = T;
+    P.lag = lag;
+    P.ax = ax;
+    P.ay = ay;
+    P.az = az;
+    for (int q = 0; q < FR3D_MAX_CHANNELS; ++q)
+        P.a_data[q] = q < C ? a_data[q] : 1.0;
+    P.J = J;
+    P.wgt = wgt;
+    P.L = L;
+    P.AB = c->AB.ensure(c->dev, (size_t)B * 9 * N);
+    P.d = c->d.ensure(c->dev, (size_t)B * 3 * N);
+    c->dev.zero(P.d, (size_t)B * 3 * N * sizeof(double));
+    sor_run(c->dev, P, c->bar.ensure(c->dev, 4));
+}
+
+// ---- C ABI -------------------------------------------------------------------------------------
+#define FR3D_API_BEGIN(ctx_)                  \
+    fr3d_ctx* _c = (ctx_);                    \
+    if (!_c)                                  \
+        return FR3D_ERR_ARG;                  \
+    try {
+#define FR3D_API_END()                        \
+    }                                         \
+    catch (const Error& e)                    \
+    {                                         \
+        _c->err = e.msg;                      \
+        return e.code;                        \
+    }                                         \
+    catch (const std::exception& e)           \
+    {                                         \
+        _c->err = e.what();                   \
+        return FR3D_ERR_NOMEM;                \
+    }                                         \
+    return FR3D_OK;
+
+extern "C" {
+
+int fr3d_abi_version(void) { return FR3D_ABI_VERSION; }
+
+const char* fr3d_last_error(const fr3d_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int64_t fr3d_launch_count(const fr3d_ctx* ctx) { return ctx ? ctx->dev.launches : 0; }
+int64_t fr3d_device_bytes(const fr3d_ctx* ctx) { return ctx ? ctx->dev.bytes : 0; }
+
+int fr3d_create(fr3d_ctx** out, int device, const fr3d_plan* plan, void* stream)
+{
+    if (!out)
+        return FR3D_ERR_ARG;
+    *out = nullptr;
+    fr3d_ctx* c = nullptr;
+    try {
+        c = new fr3d_ctx();
+#ifndef FR3D_EMU
+        FR3D_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        FR3D_CUDA(cudaGetDeviceProperties(&prop, device));
+        FR3D_REQUIRE(prop.major >= 10, "libfr3d is built for sm_100a (B200); device %d is sm_%d%d", device,
+                     prop.major, prop.minor);
+        FR3D_REQUIRE(prop.cooperativeLaunch, "device %d lacks cooperative launch", device);
+        c->dev.sm_count = prop.multiProcessorCount;
+        c->dev.stream = (cudaStream_t)stream;
+#else
+        (void)device;
+        (void)stream;
+#endif
+        if (plan) {
+            FR3D_REQUIRE(plan->abi_version == FR3D_ABI_VERSION, "plan ABI %d != library ABI %d",
+                         plan->abi_version, FR3D_ABI_VERSION);
+            FR3D_REQUIRE(plan->Z > 0 && plan->Y > 0 && plan->X > 0, "bad volume size");
+            FR3D_REQUIRE(plan->C >= 1 && plan->C <= FR3D_MAX_CHANNELS, "C must be 1..%d", FR3D_MAX_CHANNELS);
+            FR3D_REQUIRE(plan->max_batch >= 1, "max_batch must be >= 1");
+            FR3D_REQUIRE(plan->n_levels >= 1 && plan->n_levels <= FR3D_MAX_LEVELS && plan->levels, "bad level list");
+            FR3D_REQUIRE(plan->iterations >= 1 && plan->update_lag >= 1, "iterations/update_lag must be >= 1");
+            FR3D_REQUIRE(plan->a_smooth == 1.0,
+                         "a_smooth != 1 (nonlinear smoothness) is not implemented in libfr3d");
+            FR3D_REQUIRE(plan->interp == 3 || plan->interp == 1, "interp must be 3 (cubic) or 1 (linear)");
+            FR3D_REQUIRE(plan->sweep == FR3D_SWEEP_LEXICOGRAPHIC, "sweep order %d is not implemented", plan->sweep);
+            c->Z = plan->Z;
+            c->Y = plan->Y;
+            c->X = plan->X;
+            c->C = plan->C;
+            c->max_batch = plan->max_batch;
+            c->iterations = plan->iterations;
+            c->update_lag = plan->update_lag;
+            c->sweep = plan->sweep;
+            c->interp = plan->interp;
+            c->a_smooth = plan->a_smooth;
+            for (int q = 0; q < FR3D_MAX_CHANNELS; ++q)
+                c->a_data[q] = plan->a_data[q];
+            for (int li = 0; li < plan->n_levels; ++li) {
+                const fr3d_level& s = plan->levels[li];
+                c->levels.emplace_back(new LevelDev());
+                LevelDev& L = *c->levels[li];
+                L.pz = s.size[0];
+                L.py = s.size[1];
+                L.px = s.size[2];
+                FR3D_REQUIRE(L.pz > 0 && L.py > 0 && L.px > 0, "level %d has an empty grid", li);
+                L.N = (int64_t)L.pz * L.py * L.px;
+                L.hz = s.h[0];
+                L.hy = s.h[1];
+                L.hx = s.h[2];
+                for (int q = 0; q < 3; ++q)
+                    L.alpha[q] = s.alpha[q];
+                L.median = s.median != 0;
+                for (int q = 0; q < 3; ++q) {
+                    L.full[q].upload(c->dev, s.from_full[q]);
+                    FR3D_REQUIRE(L.full[q].P > 0, "level %d: from_full table %d missing", li, q);
+                    if (li > 0) {
+                        L.prev[q].upload(c->dev, s.from_prev[q]);
+                        FR3D_REQUIRE(L.prev[q].P > 0, "level %d: from_prev table %d missing", li, q);
+                    }
+                }
+                FR3D_REQUIRE(L.full[0].out_len == L.px && L.full[1].out_len == L.py && L.full[2].out_len == L.pz,
+                             "level %d: from_full tables do not produce the level size", li);
+            }
+            for (int q = 0; q < 3; ++q)
+                c->to_full[q].upload(c->dev, plan->to_full[q]);
+            for (int ch = 0; ch < c->C; ++ch)
+                for (int a = 0; a < 3; ++a) {
+                    const int r = plan->gauss_radius[ch][a];
+                    FR3D_REQUIRE(r >= 0 && (r == 0 || plan->gauss_w[ch][a]), "bad Gaussian kernel (c=%d, axis=%d)", ch, a);
+                    c->pre.r[ch][a] = r;
+                    std::vector<double> one(1, 1.0);
+                    const double* hw = plan->gauss_w[ch][a] ? plan->gauss_w[ch][a] : one.data();
+                    c->pre.w[ch][a] = c->pre_w[ch][a].upload(c->dev, hw, (size_t)r + 1);
+                }
+            c->has_plan = true;
+        }
+        c->dev.sync();
+    } catch (const Error& e) {
+        g_create_err = e.msg;
+        delete c;
+        return e.code;
+    } catch (const std::exception& e) {
+        g_create_err = e.what();
+        delete c;
+        return FR3D_ERR_NOMEM;
+    }
+    *out = c;
+    return FR3D_OK;
+}
+
+void fr3d_destroy(fr3d_ctx* ctx)
+{
+    if (!ctx)
+        return;
+#ifndef FR3D_EMU
+    cudaStreamSynchronize(ctx->dev.stream);
+#endif
+    delete ctx;
+}
+
+int fr3d_synchronize(fr3d_ctx* ctx)
+{
+    FR3D_API_BEGIN(ctx)
+    _c->dev.sync();
+    FR3D_API_END()
+}
+
+int fr3d_preprocess(fr3d_ctx* ctx, const void* raw, int dtype, int B, const double* lo, const double* den,
+                    float* out)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(_c->has_plan, "fr3d_preprocess needs a context created with a plan");
+    FR3D_REQUIRE(raw && out && lo && den && B >= 1, "null argument");
+    check_dtype(dtype);
+    const int Z = _c->Z, Y = _c->Y, X = _c->X, C = _c->C;
+    PreGauss g = _c->pre;
+    for (int ch = 0; ch < C; ++ch) {
+        g.lo[ch] = lo[ch];
+        g.den[ch] = den[ch];
+        FR3D_REQUIRE(den[ch] != 0.0, "normalisation denominator is zero");
+    }
+    const size_t n = (size_t)B * C * Z * Y * X;
+    double* a = _c->g1.ensure(_c->dev, n);
+    double* b = _c->g2.ensure(_c->dev, n);
+    launch(_c->dev, PreZK{raw, dtype, a, B, Z, Y, X, C, g}, (int64_t)n);
+    launch(_c->dev, PreYK{a, b, C, Z, Y, X, g}, (int64_t)n);
+    launch(_c->dev, PreXK{b, out, B, Z, Y, X, C, g}, (int64_t)n);
+    FR3D_API_END()
+}
+
+int fr3d_set_reference(fr3d_ctx* ctx, const float* ref_proc, const float* weight, const double* weight_const)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(_c->has_plan, "fr3d_set_reference needs a context created with a plan");
+    FR3D_REQUIRE(ref_proc && (weight || weight_const), "null argument");
+    const int Z = _c->Z, Y = _c->Y, X = _c->X, C = _c->C;
+    const View cl{0, 1, (int64_t)Y * X * C, (int64_t)X * C, C}; // channels-last (Z,Y,X,C), o1 = channel
+    const float* wsrc = weight;
+    if (!wsrc) {
+        FillK<float> f;
+        f.dst = _c->fscr.ensure(_c->dev, (size_t)Z * Y * X * C);
+        f.C = C;
+        f.inner = 0;
+        for (int q = 0; q < FR3D_MAX_CHANNELS; ++q)
+            f.v[q] = q < C ? weight_const[q] : 0.0;
+        launch(_c->dev, f, (int64_t)Z * Y * X * C);
+        wsrc = f.dst;
+    }
+    for (auto& Lp : _c->levels) {
+        LevelDev& L = *Lp;
+        float* f1 = L.f1.ensure(_c->dev, (size_t)C * L.N);
+        resize3<float, float>(_c, ref_proc, cl, 1, C, Z, Y, X, f1, planar(C, L.pz, L.py, L.px), L.full);
+        // weights: resized like an image (core/optical_flow_3d.py:475), widened to float64, skewed
+        double* wn = _c->wnat.ensure(_c->dev, (size_t)C * L.N);
+        resize3<float, double>(_c, wsrc, cl, 1, C, Z, Y, X, wn, planar(C, L.pz, L.py, L.px), L.full);
+        double* ws = L.wskew.ensure(_c->dev, (size_t)C * L.N);
+        launch(_c->dev, ToSkewK{wn, ws, Skew{L.pz, L.py, L.px}}, (int64_t)C * L.N);
+    }
+    _c->ref_set = true;
+    FR3D_API_END()
+}
+
+int fr3d_get_displacement(fr3d_ctx* ctx, const float* moving, const float* uvw_init, int B, void* flow_out,
+                          int out_dtype)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(_c->has_plan, "fr3d_get_displacement needs a context created with a plan");
+    if (!_c->ref_set)
+        FR3D_THROW(FR3D_ERR_STATE, "fr3d_set_reference has not been called");
+    FR3D_REQUIRE(moving && flow_out, "null argument");
+    FR3D_REQUIRE(B >= 1 && B <= _c->max_batch, "B=%d outside 1..max_batch=%d", B, _c->max_batch);
+    FR3D_REQUIRE(out_dtype == FR3D_F32 || out_dtype == FR3D_F64, "flow_out dtype must be F32 or F64");
+    Device& dev = _c->dev;
+    const int Z = _c->Z, Y = _c->Y, X = _c->X, C = _c->C;
+    const int64_t NF = (int64_t)Z * Y * X;
+    int64_t Nmax = 0;
+    for (const auto& L : _c->levels)
+        Nmax = L->N > Nmax ? L->N : Nmax;
+    float* f2 = _c->f2.ensure(dev, (size_t)B * C * Nmax);
+    float* tmp = _c->tmp.ensure(dev, (size_t)B * C * Nmax);
+    double* ucur = _c->uvw_a.ensure(dev, (size_t)B * 3 * Nmax);
+    double* uprev = _c->uvw_b.ensure(dev, (size_t)B * 3 * Nmax);
+    double* Jb = _c->J.ensure(dev, (size_t)B * C * 10 * Nmax);
+    double* Lb = _c->L.ensure(dev, (size_t)B * 3 * Nmax);
+    double* dnat = _c->dnat.ensure(dev, (size_t)B * 3 * Nmax);
+    const View mov_cl{NF * C, 1, (int64_t)Y * X * C, (int64_t)X * C, C};
+
+    for (size_t li = 0; li < _c->levels.size(); ++li) {
+        LevelDev& L = *_c->levels[li];
+        const int p = L.pz, m = L.py, n = L.px;
+        const int64_t N = L.N;
+        // moving image at this level: always resampled from full resolution (:409-410)
+        resize3<float, float>(_c, moving, mov_cl, B, C, Z, Y, X, f2, planar(C, p, m, n), L.full);
+        const float* warped = f2;
+        int f2f32 = 0;
+        if (li == 0) {
+            if (uvw_init) {
+                // (:417-420) the initial field is shared by the batch: resample once, broadcast
+                float* u0 = _c->fscr.ensure(dev, (size_t)3 * N);
+                const View uv{0, 1, (int64_t)Y * X * 3, (int64_t)X * 3, 3};
+                resize3<float, float>(_c, uvw_init, uv, 1, 3, Z, Y, X, u0, planar(3, p, m, n), L.full);
+                launch(dev, BroadcastF32toF64K{u0, ucur, 3 * N}, (int64_t)B * 3 * N);
+            } else {
+                dev.zero(ucur, (size_t)B * 3 * N * sizeof(double));
+            }
+        } else {
+            // (:424-434) upsample the flow from the coarser level, then warp the moving image
+            const LevelDev& Lp = *_c->levels[li - 1];
+            double* t = ucur;
+            ucur = uprev;
+            uprev = t;
+            resize3<double, double>(_c, uprev, planar(3, Lp.pz, Lp.py, Lp.px), B, 3, Lp.pz, Lp.py, Lp.px, ucur,
+                                    planar(3, p, m, n), L.prev);
+            spline_prefilter(_c, f2, FR3D_F32, C * N, N, (int64_t)m * n, n, 1, B, C, p, m, n);
+            WarpGatherK g;
+            g.order = 3;
+            g.coef = _c->coef.p;
+            g.src = nullptr;
+            g.sdt = FR3D_F32;
+            g.sb = g.sc = g.sz = g.sy = g.sx = 0;
+            g.disp64 = ucur;
+            g.disp32 = nullptr;
+            g.hx = L.hx;
+            g.hy = L.hy;
+            g.hz = L.hz;
+            g.ref = L.f1.p;
+            g.rdt = FR3D_F32;
+            g.rc = N;
+            g.rz = (int64_t)m * n;
+            g.ry = n;
+            g.rx = 1;
+            g.out = tmp;
+            g.ob = C * N;
+            g.oc = N;
+            g.oz = (int64_t)m * n;
+            g.oy = n;
+            g.ox = 1;
+            g.B = B;
+            g.C = C;
+            g.Z = p;
+            g.Y = m;
+            g.X = n;
+            launch(dev, g, (int64_t)B * N);
+            warped = tmp;
+            f2f32 = 1; // numpy keeps the float32 warp output in float32 through its derivatives
+        }
+        const double ax = L.alpha[0] / (L.hx * L.hx), ay = L.alpha[1] / (L.hy * L.hy),
+                     az = L.alpha[2] / (L.hz * L.hz);
+        AssembleK as;
+        as.f1 = L.f1.p;
+        as.f2 = warped;
+        as.uvw = ucur;
+        as.J = Jb;
+        as.L = Lb;
+        as.g = MTGeom{p, m, n, L.hz, L.hy, L.hx, f2f32};
+        as.B = B;
+        as.C = C;
+        as.ax = ax;
+        as.ay = ay;
+        as.az = az;
+        launch(dev, as, (int64_t)B * N);
+        run_sor(_c, B, C, p, m, n, Jb, L.wskew.p, Lb, ax, ay, az, _c->iterations, _c->update_lag, _c->a_data,
+                _c->sweep);
+        launch(dev, FromSkewK{_c->d.p, dnat, Skew{p, m, n}}, (int64_t)B * 3 * N);
+        if (L.median)
+            launch(dev, Median5K{dnat, ucur, ucur, p, m, n}, (int64_t)B * 3 * N); // (:517-529)
+        else
+            launch(dev, AddK{ucur, dnat, ucur}, (int64_t)B * 3 * N);
+    }
+    const LevelDev& Lf = *_c->levels.back();
+    if (_c->to_full[0].P > 0) {
+        // (:536-541) resample the flow to full resolution; values are not rescaled
+        const View fo{NF * 3, 1, (int64_t)Y * X * 3, (int64_t)X * 3, 3};
+        if (out_dtype == FR3D_F32)
+            resize3<double, float>(_c, ucur, planar(3, Lf.pz, Lf.py, Lf.px), B, 3, Lf.pz, Lf.py, Lf.px,
+                                   (float*)flow_out, fo, _c->to_full);
+        else
+            resize3<double, double>(_c, ucur, planar(3, Lf.pz, Lf.py, Lf.px), B, 3, Lf.pz, Lf.py, Lf.px,
+                                    (double*)flow_out, fo, _c->to_full);
+    } else {
+        FR3D_REQUIRE(Lf.pz == Z && Lf.py == Y && Lf.px == X, "finest level is not full resolution but to_full is empty");
+        if (out_dtype == FR3D_F32)
+            launch(dev, InterleaveFlowK<float>{ucur, (float*)flow_out, NF}, (int64_t)B * NF * 3);
+        else
+            launch(dev, InterleaveFlowK<double>{ucur, (double*)flow_out, NF}, (int64_t)B * NF * 3);
+    }
+    FR3D_API_END()
+}
+
+static void warp_common(fr3d_ctx* c, const void* vol, int vdt, const double* d64, const float* d32,
+                        const void* ref, int rdt, int B, int Z, int Y, int X, int C, int interp, float* out)
+{
+    check_dtype(vdt);
+    check_dtype(rdt);
+    FR3D_REQUIRE(interp == 3 || interp == 1, "Unsupported interpolation method. Use 'linear' or 'cubic'.");
+    const int64_t NF = (int64_t)Z * Y * X;
+    if (interp == 3)
+        spline_prefilter(c, vol, vdt, NF * C, 1, (int64_t)Y * X * C, (int64_t)X * C, C, B, C, Z, Y, X);
+    WarpGatherK g;
+    g.order = interp;
+    g.coef = c->coef.p;
+    g.src = vol;
+    g.sdt = vdt;
+    g.sb = NF * C;
+    g.sc = 1;
+    g.sz = (int64_t)Y * X * C;
+    g.sy = (int64_t)X * C;
+    g.sx = C;
+    g.disp64 = d64;
+    g.disp32 = d32;
+    g.hx = g.hy = g.hz = 1.0;
+    g.ref = ref;
+    g.rdt = rdt;
+    g.rc = 1;
+    g.rz = (int64_t)Y * X * C;
+    g.ry = (int64_t)X * C;
+    g.rx = C;
+    g.out = out;
+    g.ob = NF * C;
+    g.oc = 1;
+    g.oz = (int64_t)Y * X * C;
+    g.oy = (int64_t)X * C;
+    g.ox = C;
+    g.B = B;
+    g.C = C;
+    g.Z = Z;
+    g.Y = Y;
+    g.X = X;
+    launch(c->dev, g, (int64_t)B * NF);
+}
+
+int fr3d_compensate(fr3d_ctx* ctx, const void* vol, int vol_dtype, const float* flow, const void* ref,
+                    int ref_dtype, int B, float* out)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(_c->has_plan, "fr3d_compensate needs a context created with a plan");
+    FR3D_REQUIRE(vol && flow && ref && out && B >= 1, "null argument");
+    warp_common(_c, vol, vol_dtype, nullptr, flow, ref, ref_dtype, B, _c->Z, _c->Y, _c->X, _c->C, _c->interp, out);
+    FR3D_API_END()
+}
+
+int fr3d_warp(fr3d_ctx* ctx, const void* vol, int vol_dtype, const double* u, const double* v, const double* w,
+              const void* ref, int ref_dtype, int Z, int Y, int X, int C, int interp, float* out)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(vol && u && v && w && ref && out, "null argument");
+    FR3D_REQUIRE(Z > 0 && Y > 0 && X > 0 && C >= 1 && C <= FR3D_MAX_CHANNELS, "bad shape");
+    const int64_t NF = (int64_t)Z * Y * X;
+    double* d = _c->dnat.ensure(_c->dev, (size_t)3 * NF);
+    _c->dev.d2d(d, u, NF * sizeof(double));
+    _c->dev.d2d(d + NF, v, NF * sizeof(double));
+    _c->dev.d2d(d + 2 * NF, w, NF * sizeof(double));
+    warp_common(_c, vol, vol_dtype, d, nullptr, ref, ref_dtype, 1, Z, Y, X, C, interp, out);
+    FR3D_API_END()
+}
+
+int fr3d_resize3d(fr3d_ctx* ctx, const float* src, int nvol, int D, int H, int W, const fr3d_axis_table tables[3],
+                  float* dst)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(src && dst && tables && nvol >= 1, "null argument");
+    for (int q = 0; q < 3; ++q) {
+        _c->stage_tab[q].upload(_c->dev, tables[q]);
+        FR3D_REQUIRE(_c->stage_tab[q].P > 0, "empty table");
+    }
+    const int od = tables[2].out_len, oh = tables[1].out_len, ow = tables[0].out_len;
+    resize3<float, float>(_c, src, planar(nvol, D, H, W), 1, nvol, D, H, W, dst, planar(nvol, od, oh, ow),
+                          _c->stage_tab);
+    FR3D_API_END()
+}
+
+int fr3d_motion_tensor(fr3d_ctx* ctx, const float* f1, const float* f2, int p, int m, int n, double hz, double hy,
+                       double hx, int f2_f32_math, double* J)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(f1 && f2 && J && p > 0 && m > 0 && n > 0, "bad argument");
+    MotionTensorK k{MTImages{f1, f2, MTGeom{p, m, n, hz, hy, hx, f2_f32_math}}, J};
+    launch(_c->dev, k, (int64_t)p * m * n);
+    FR3D_API_END()
+}
+
+int fr3d_sor_level(fr3d_ctx* ctx, const double* J, const double* weight, const double* uvw, int p, int m, int n,
+                   int C, const double* alpha, double hz, double hy, double hx, int iterations, int update_lag,
+                   const double* a_data, double a_smooth, int sweep, double* d)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(J && weight && uvw && alpha && a_data && d, "null argument");
+    FR3D_REQUIRE(p > 0 && m > 0 && n > 0 && C >= 1 && C <= FR3D_MAX_CHANNELS, "bad shape");
+    FR3D_REQUIRE(iterations >= 1 && update_lag >= 1, "iterations/update_lag must be >= 1");
+    FR3D_REQUIRE(a_smooth == 1.0, "a_smooth != 1 (nonlinear smoothness) is not implemented in libfr3d");
+    const int64_t N = (int64_t)p * m * n;
+    const Skew sk{p, m, n};
+    double* Js = _c->J.ensure(_c->dev, (size_t)C * 10 * N);
+    double* ws = _c->wnat.ensure(_c->dev, (size_t)C * N);
+    double* Ls = _c->L.ensure(_c->dev, (size_t)3 * N);
+    launch(_c->dev, ToSkewK{J, Js, sk}, (int64_t)C * 10 * N);
+    launch(_c->dev, ToSkewK{weight, ws, sk}, (int64_t)C * N);
+    const double ax = alpha[0] / (hx * hx), ay = alpha[1] / (hy * hy), az = alpha[2] / (hz * hz);
+    // reuse AssembleK for the Laplacian part only: C = 0 skips the tensor
+    AssembleK as;
+    as.f1 = nullptr;
+    as.f2 = nullptr;
+    as.uvw = uvw;
+    as.J = nullptr;
+    as.L = Ls;
+    as.g = MTGeom{p, m, n, hz, hy, hx, 0};
+    as.B = 1;
+    as.C = 0;
+    as.ax = ax;
+    as.ay = ay;
+    as.az = az;
+    launch(_c->dev, as, N);
+    run_sor(_c, 1, C, p, m, n, Js, ws, Ls, ax, ay, az, iterations, update_lag, a_data, sweep);
+    launch(_c->dev, FromSkewK{_c->d.p, d, sk}, (int64_t)3 * N);
+    FR3D_API_END()
+}
+
+int fr3d_median5(fr3d_ctx* ctx, const double* src, int nvol, int p, int m, int n, double* dst)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(src && dst && nvol >= 1 && p > 0 && m > 0 && n > 0, "bad argument");
+    FR3D_REQUIRE(src != dst, "fr3d_median5 cannot run in place");
+    launch(_c->dev, Median5K{src, dst, nullptr, p, m, n}, (int64_t)nvol * p * m * n);
+    FR3D_API_END()
+}
+
+int fr3d_mean_frames(fr3d_ctx* ctx, const float* frames, int T, int64_t n, float* out)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(frames && out && T >= 1 && n >= 1, "bad argument");
+    launch(_c->dev, MeanFramesK{frames, out, T, n}, n);
+    FR3D_API_END()
+}
+
+// util/resize_util_3D.py:76-95 (numba fastmath hoists 1/scale: follow the compiled arithmetic so
+// that floor() lands on the same tap window as the reference at exact-integer sample positions).
+int fr3d_fill_resize_table(int in_len, int out_len, const float* g, int R, int32_t* idx, float* wt)
+{
+    if (in_len < 1 || out_len < 1 || R < 0 || !g || !idx || !wt)
+        return FR3D_ERR_ARG;
+    const int P = 2 * R + 4;
+    const double A = -0.75;
+    const double rscale = 1.0 / ((double)out_len / (double)in_len);
+    for (int i = 0; i < out_len; ++i) {
+        const double x = ((double)i + 0.5) * rscale - 0.5;
+        const int64_t left = (int64_t)floor(x - 2.0) - R;
+        double ssum = 0.0;
+        for (int p = 0; p < P; ++p) {
+            const int64_t j = left + p;
+            int64_t jj = j;
+            if (in_len <= 1)
+                jj = 0;
+            else
+                while (jj < 0 || jj >= in_len)
+                    jj = jj < 0 ? -jj - 1 : 2 * (int64_t)in_len - 1 - jj;
+            idx[(int64_t)i * P + p] = (int32_t)jj;
+            const double dd = x - (double)j;
+            double acc = 0.0;
+            for (int u = -R; u <= R; ++u) {
+                const double ax = fabs(dd - (double)u);
+                double kx = 0.0;
+                if (ax < 1.0)
+                    kx = (A + 2.0) * ax * ax * ax - (A + 3.0) * ax * ax + 1.0;
+                else if (ax < 2.0)
+                    kx = A * ax * ax * ax - 5.0 * A * ax * ax + 8.0 * A * ax - 4.0 * A;
+                acc += (double)g[u + R] * kx;
+            }
+            wt[(int64_t)i * P + p] = (float)acc;
+            ssum += acc;
+        }
+        const double inv = 1.0 / ssum;
+        for (int p = 0; p < P; ++p)
+            wt[(int64_t)i * P + p] = (float)((double)wt[(int64_t)i * P + p] * inv);
+    }
+    return FR3D_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,240 @@
+// fr3d_common.h -- device abstraction shared by every kernel of libfr3d.
+//
+// Product build: nvcc, sm_100a.  Every kernel body is a functor whose operator()(int64_t item)
+// is executed by one CUDA thread (fr3d_launch).
+//
+// FR3D_EMU build (tests/emu only, never shipped or loaded by flowreg3d_b200): the same functors
+// are compiled by g++ and run as a serial loop, so the not-gpu tests can check the kernel LOGIC
+// against the oracle in a container without a GPU.  It is a test harness, not a fallback: the
+// Python package only ever loads the CUDA library and raises if it is missing.
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/fr3d.h"
+
+#ifdef FR3D_EMU
+#define FR3D_HD inline
+#define FR3D_D inline
+#define FR3D_LDCG(ptr) (*(ptr))
+#define FR3D_STCG(ptr, v) (*(ptr) = (v))
+typedef void* fr3d_stream_t;
+#else
+#include <cuda_runtime.h>
+#define FR3D_HD __host__ __device__ __forceinline__
+#define FR3D_D __device__ __forceinline__
+#ifdef __CUDA_ARCH__
+#define FR3D_LDCG(ptr) __ldcg(ptr)
+#define FR3D_STCG(ptr, v) __stcg(ptr, v)
+#else
+#define FR3D_LDCG(ptr) (*(ptr))
+#define FR3D_STCG(ptr, v) (*(ptr) = (v))
+#endif
+typedef cudaStream_t fr3d_stream_t;
+#endif
+
+namespace fr3d {
+
+struct Error {
+    int code;
+    std::string msg;
+};
+
+#define FR3D_THROW(code_, ...)                         \
+    do {                                               \
+        char _b[512];                                  \
+        snprintf(_b, sizeof(_b), __VA_ARGS__);         \
+        throw ::fr3d::Error{(code_), std::string(_b)}; \
+    } while (0)
+
+#define FR3D_REQUIRE(cond, ...)                 \
+    do {                                        \
+        if (!(cond))                            \
+            FR3D_THROW(FR3D_ERR_ARG, __VA_ARGS__); \
+    } while (0)
+
+#ifndef FR3D_EMU
+#define FR3D_CUDA(expr)                                                                   \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess)                                                            \
+            FR3D_THROW(_e == cudaErrorMemoryAllocation ? FR3D_ERR_NOMEM : FR3D_ERR_CUDA,  \
+                       "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,  \
+                       __LINE__);                                                         \
+    } while (0)
+#endif
+
+// ---- device memory ------------------------------------------------------------------------
+struct Device {
+    fr3d_stream_t stream = nullptr;
+    int64_t launches = 0;
+    int64_t bytes = 0;
+    int sm_count = 1;
+
+    void* alloc(size_t n)
+    {
+        if (n == 0)
+            n = 8;
+        void* p = nullptr;
+#ifdef FR3D_EMU
+        p = malloc(n);
+        if (!p)
+            FR3D_THROW(FR3D_ERR_NOMEM, "host alloc of %zu bytes failed", n);
+#else
+        FR3D_CUDA(cudaMalloc(&p, n));
+#endif
+        bytes += (int64_t)n;
+        return p;
+    }
+    void release(void* p, size_t n)
+    {
+        if (!p)
+            return;
+#ifdef FR3D_EMU
+        free(p);
+#else
+        cudaFree(p);
+#endif
+        bytes -= (int64_t)(n ? n : 8);
+    }
+    void h2d(void* dst, const void* src, size_t n)
+    {
+        if (!n)
+            return;
+#ifdef FR3D_EMU
+        memcpy(dst, src, n);
+#else
+        // tables and small parameter blocks only: pageable source, synchronous semantics wanted
+        FR3D_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, stream));
+        FR3D_CUDA(cudaStreamSynchronize(stream));
+#endif
+    }
+    void d2d(void* dst, const void* src, size_t n)
+    {
+        if (!n)
+            return;
+#ifdef FR3D_EMU
+        memmove(dst, src, n);
+#else
+        FR3D_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, stream));
+#endif
+    }
+    void zero(void* dst, size_t n)
+    {
+        if (!n)
+            return;
+#ifdef FR3D_EMU
+        memset(dst, 0, n);
+#else
+        FR3D_CUDA(cudaMemsetAsync(dst, 0, n, stream));
+#endif
+    }
+    void sync()
+    {
+#ifndef FR3D_EMU
+        FR3D_CUDA(cudaStreamSynchronize(stream));
+#endif
+    }
+};
+
+// Grow-only typed device buffer.
+template <class T>
+struct Buf {
+    T* p = nullptr;
+    size_t cap = 0; // elements
+    Device* dev = nullptr;
+    Buf() {}
+    Buf(const Buf&) = delete;
+    Buf& operator=(const Buf&) = delete;
+    ~Buf() { reset(); }
+    void reset()
+    {
+        if (p && dev)
+            dev->release(p, cap * sizeof(T));
+        p = nullptr;
+        cap = 0;
+    }
+    T* ensure(Device& d, size_t n)
+    {
+        if (n > cap) {
+            reset();
+            dev = &d;
+            p = (T*)d.alloc(n * sizeof(T));
+            cap = n;
+        }
+        return p;
+    }
+    T* upload(Device& d, const T* host, size_t n)
+    {
+        ensure(d, n);
+        d.h2d(p, host, n * sizeof(T));
+        return p;
+    }
+};
+
+// ---- launch -------------------------------------------------------------------------------
+#ifndef FR3D_EMU
+template <class K>
+__global__ void __launch_bounds__(256) fr3d_kernel(const K k, const int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        k(i);
+}
+#endif
+
+// One logical thread per item.
+template <class K>
+void launch(Device& dev, const K& k, int64_t n)
+{
+    if (n <= 0)
+        return;
+#ifdef FR3D_EMU
+    for (int64_t i = 0; i < n; ++i)
+        k(i);
+#else
+    const int threads = 256;
+    const int64_t blocks = (n + threads - 1) / threads;
+    FR3D_REQUIRE(blocks < (int64_t)2147483647, "launch too large: %lld items", (long long)n);
+    fr3d_kernel<K><<<(unsigned)blocks, threads, 0, dev.stream>>>(k, n);
+    FR3D_CUDA(cudaGetLastError());
+#endif
+    dev.launches++;
+}
+
+FR3D_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+FR3D_HD size_t dtype_size(int dt)
+{
+    switch (dt) {
+    case FR3D_F32: return 4;
+    case FR3D_F64: return 8;
+    case FR3D_U8: return 1;
+    case FR3D_U16: return 2;
+    case FR3D_I16: return 2;
+    case FR3D_I32: return 4;
+    }
+    return 0;
+}
+
+// Read one element of a dtype-tagged array as double (exact for every supported dtype).
+FR3D_HD double load_as_double(const void* base, int dt, int64_t i)
+{
+    switch (dt) {
+    case FR3D_F32: return (double)((const float*)base)[i];
+    case FR3D_F64: return ((const double*)base)[i];
+    case FR3D_U8: return (double)((const uint8_t*)base)[i];
+    case FR3D_U16: return (double)((const uint16_t*)base)[i];
+    case FR3D_I16: return (double)((const int16_t*)base)[i];
+    case FR3D_I32: return (double)((const int32_t*)base)[i];
+    }
+    return 0.0;
+}
+
+} // namespace fr3d

@@ -1,0 +1,51 @@
+"""Device-memory plumbing: PyTorch tensors own the buffers, libfr3d gets raw pointers.
+
+torch is used for allocation, host<->device copies and streams only -- no torch op touches the
+data.  Under the test-suite's kernel-logic emulator (FR3D_LIBRARY_OVERRIDE, CPU-only containers)
+the same code runs with CPU tensors.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_TORCH_DT = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
+             np.dtype(np.uint8): torch.uint8, np.dtype(np.uint16): torch.uint16,
+             np.dtype(np.int16): torch.int16, np.dtype(np.int32): torch.int32}
+
+
+def torch_dtype(dt):
+    return _TORCH_DT[np.dtype(dt)]
+
+
+def default_device(index=None) -> torch.device:
+    if _lib.is_emulator():
+        return torch.device("cpu")
+    if not torch.cuda.is_available():
+        raise RuntimeError("flowreg3d_b200 needs a CUDA device (B200, sm_100a); none is visible and "
+                           "there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device() if index is None else index)
+
+
+def to_device(a: np.ndarray, device: torch.device, pin: bool = False) -> torch.Tensor:
+    a = np.ascontiguousarray(a)
+    t = torch.from_numpy(a)
+    if device.type == "cpu":
+        return t
+    if pin:
+        t = t.pin_memory()
+    return t.to(device, non_blocking=pin)
+
+
+def empty(shape, dtype, device: torch.device) -> torch.Tensor:
+    return torch.empty(tuple(int(s) for s in shape), dtype=torch_dtype(dtype), device=device)
+
+
+def to_host(t: torch.Tensor) -> np.ndarray:
+    return t.cpu().numpy() if t.device.type != "cpu" else t.numpy()
+
+
+def ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()

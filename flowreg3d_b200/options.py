@@ -1,0 +1,182 @@
+"""OFOptions -- the hot-path subset of the reference's configuration object (drop-in boundary B3).
+
+Mirrors flowreg3d.motion_correction.OF_options_3D.OFOptions (OF_options_3D.py:130-686): same field
+names, defaults, validators (alpha -> 3-tuple, weight normalisation, sigma -> (n,4)), quality
+presets, ``effective_min_level``, ``get_weight_at``, ``to_dict`` and ``copy``.  File I/O fields
+(readers/writers, output paths, naming) belong to the reference's storage layer and are not part
+of this path; unknown fields are rejected exactly like the reference (extra="forbid").  When the
+real flowreg3d package is importable its own OFOptions can be passed to every entry point here
+instead -- only the attributes below are read.
+"""
+from __future__ import annotations
+
+from enum import Enum
+from typing import Any, List, Optional, Tuple, Union
+
+import numpy as np
+from pydantic import BaseModel, ConfigDict, Field, StrictInt, field_validator, model_validator
+
+
+class QualitySetting(str, Enum):
+    QUALITY = "quality"
+    BALANCED = "balanced"
+    FAST = "fast"
+    CUSTOM = "custom"
+
+
+class ChannelNormalization(str, Enum):
+    JOINT = "joint"
+    SEPARATE = "separate"
+
+
+class InterpolationMethod(str, Enum):
+    NEAREST = "nearest"
+    LINEAR = "linear"
+    CUBIC = "cubic"
+
+
+class ConstancyAssumption(str, Enum):
+    GRAY = "gray"
+    GRADIENT = "gc"
+
+
+class OFOptions(BaseModel):
+    model_config = ConfigDict(arbitrary_types_allowed=True, validate_assignment=False, extra="forbid",
+                              populate_by_name=True)
+
+    # flow parameters (OF_options_3D.py:155-174)
+    alpha: Union[float, Tuple[float, float], Tuple[float, float, float]] = Field((0.25, 0.25, 0.25))
+    weight: Union[List[float], np.ndarray] = Field([0.5, 0.5])
+    levels: StrictInt = Field(100, ge=1)
+    min_level: StrictInt = Field(5, ge=-1)
+    quality_setting: QualitySetting = Field(QualitySetting.QUALITY)
+    eta: float = Field(0.8, gt=0, le=1)
+    update_lag: StrictInt = Field(5, ge=1)
+    iterations: StrictInt = Field(100, ge=1)
+    a_smooth: float = Field(1.0, ge=0)
+    a_data: float = Field(0.45, gt=0, le=1)
+    # preprocessing (:177-182)
+    sigma: Any = Field([[1.0, 1.0, 1.0, 0.1], [1.0, 1.0, 1.0, 0.1]])
+    buffer_size: StrictInt = Field(10, ge=1)
+    # reference (:185-192)
+    reference_frames: Union[List[int], np.ndarray] = Field(list(range(50, 500)))
+    update_reference: bool = Field(False)
+    # processing options (:197-224)
+    verbose: bool = Field(False)
+    output_typename: Optional[str] = Field("double")
+    channel_normalization: ChannelNormalization = Field(ChannelNormalization.JOINT)
+    interpolation_method: InterpolationMethod = Field(InterpolationMethod.CUBIC)
+    cc_initialization: bool = Field(False)
+    cc_hw: Union[int, Tuple[int, int]] = Field(256)
+    cc_up: int = Field(10, ge=1)
+    update_initialization_w: bool = Field(True)
+    constancy_assumption: ConstancyAssumption = Field(ConstancyAssumption.GRADIENT, alias="constancy")
+
+    _quality_setting_old: QualitySetting = QualitySetting.QUALITY
+
+    @field_validator("alpha", mode="before")
+    @classmethod
+    def _alpha(cls, v):
+        # OF_options_3D.py:236-263: scalar -> (a,a,a); (a,b) -> (a,a,b); all positive
+        if isinstance(v, (int, float)):
+            vals = (v, v, v)
+        elif isinstance(v, (list, tuple)) and len(v) in (1, 2, 3):
+            vals = (v[0],) * 3 if len(v) == 1 else ((v[0], v[0], v[1]) if len(v) == 2 else tuple(v))
+        else:
+            raise ValueError("Alpha must be scalar, 2-element, or 3-element tuple")
+        if any(a <= 0 for a in vals):
+            raise ValueError("All alpha values must be positive")
+        return tuple(float(a) for a in vals)
+
+    @field_validator("weight", mode="before")
+    @classmethod
+    def _weight(cls, v):
+        # :265-283: 1-D weights are normalised to sum 1
+        if isinstance(v, np.ndarray):
+            if v.ndim == 1 and v.sum() > 0:
+                return (v / v.sum()).tolist()
+            return v.tolist()
+        if isinstance(v, (list, tuple)):
+            arr = np.asarray(v, dtype=float)
+            if arr.ndim == 1 and arr.sum() > 0:
+                return (arr / arr.sum()).tolist()
+        return v
+
+    @field_validator("sigma", mode="before")
+    @classmethod
+    def _sigma(cls, v):
+        # :285-310: rows [sx, sy, sz, st]; 3-vectors get sz = 1 inserted
+        sig = np.asarray(v, dtype=float)
+        if sig.ndim == 1:
+            if sig.size == 3:
+                sig = np.insert(sig, 2, 1.0)
+            elif sig.size != 4:
+                raise ValueError("1D sigma must be [sx, sy, sz, st] or [sx, sy, st] for 3D")
+            return sig.reshape(1, 4).tolist()
+        if sig.ndim == 2:
+            if sig.shape[1] == 3:
+                sig = np.insert(sig, 2, 1.0, axis=1)
+            elif sig.shape[1] != 4:
+                raise ValueError("2D sigma must be (n_channels, 4) for 3D")
+            return sig.tolist()
+        raise ValueError("Sigma must be [sx,sy,sz,st] or (n_channels, 4) for 3D")
+
+    @model_validator(mode="after")
+    def _quality(self):
+        # :312-327
+        if self.quality_setting != QualitySetting.CUSTOM:
+            self._quality_setting_old = self.quality_setting
+        if self.min_level >= 0:
+            self.quality_setting = QualitySetting.CUSTOM
+        elif self.min_level == -1 and self.quality_setting == QualitySetting.CUSTOM:
+            self.quality_setting = self._quality_setting_old
+        return self
+
+    @property
+    def effective_min_level(self) -> int:
+        # :329-341
+        if self.min_level >= 0:
+            return self.min_level
+        return {QualitySetting.QUALITY: 0, QualitySetting.BALANCED: 4, QualitySetting.FAST: 6,
+                QualitySetting.CUSTOM: max(self.min_level, 0)}.get(self.quality_setting, 0)
+
+    @property
+    def constancy(self) -> str:
+        return self.constancy_assumption.value
+
+    def get_sigma_at(self, i: int) -> np.ndarray:
+        sig = np.asarray(self.sigma, dtype=float)
+        if sig.ndim == 1:
+            return sig
+        return sig[0] if i >= sig.shape[0] else sig[i]
+
+    def get_weight_at(self, i: int, n_channels: int):
+        # :371-399
+        w = np.asarray(self.weight, dtype=float)
+        if w.ndim <= 1:
+            if w.size == 1:
+                return float(w.reshape(-1)[0])
+            if w.size > n_channels:
+                w = w[:n_channels]
+                w = w / w.sum()
+                self.weight = w.tolist()
+            if i >= w.size:
+                return 1.0 / n_channels
+            return float(w[i])
+        if i >= w.shape[0]:
+            return np.ones(w.shape[1:]) / n_channels
+        return w[i]
+
+    def copy(self) -> "OFOptions":
+        return self.model_copy(deep=True)
+
+    def to_dict(self) -> dict:
+        # :667-680
+        return {"alpha": self.alpha, "weight": self.weight, "levels": self.levels,
+                "min_level": self.effective_min_level, "eta": self.eta, "iterations": self.iterations,
+                "update_lag": self.update_lag, "a_data": self.a_data, "a_smooth": self.a_smooth,
+                "const_assumption": self.constancy_assumption.value}
+
+    def __repr__(self) -> str:
+        return (f"OFOptions(quality={self.quality_setting.value}, alpha={self.alpha}, "
+                f"levels={self.levels}, min_level={self.effective_min_level})")

@@ -1,0 +1,181 @@
+/*
+ * fr3d.h -- C ABI of libfr3d: B200-native (sm_100a) dense 3-D variational optical-flow
+ * registration, the hot path of flowreg3D.
+ *
+ * The reference (FlowRegSuite/flowreg3D) is pure Python and has no FFI; the seams this library
+ * sits under are the reference's Python-level interfaces (paths relative to src/flowreg3d/):
+ *   B1  BaseExecutor3D.process_batch        motion_correction/parallelization/base_3d.py:38-71
+ *   B2  get_displacement / imregister_wrapper   core/optical_flow_3d.py:319-333 / :22
+ *   B3  OFOptions                           motion_correction/OF_options_3D.py:130-686
+ * flowreg3d_b200/ mirrors those interfaces in Python and calls the entry points below through
+ * ctypes.  INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - return 0 on success, a negative fr3d_status otherwise; never throws; message via
+ *     fr3d_last_error().
+ *   - unless a parameter says "host", pointers are CUDA DEVICE pointers owned by the caller.
+ *   - volumes are row-major (Z, Y, X[, C]) channels-last, exactly as the reference lays them out;
+ *     flow fields are (Z, Y, X, 3) with [...,0]=u=dx (X axis), [...,1]=v=dy, [...,2]=w=dz, in
+ *     full-resolution voxel units.
+ *   - all work is enqueued on the context's stream; calls return without synchronising unless
+ *     stated.  A context is not thread-safe; use one per thread/stream.
+ *   - the host computes the (tiny) level schedule and tap tables (numpy expressions identical to
+ *     the reference's, see flowreg3d_b200/plan.py) and passes them in fr3d_plan; the library does
+ *     every per-voxel computation on the GPU.  There is no CPU fallback.
+ */
+#ifndef FR3D_H
+#define FR3D_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FR3D_MAX_CHANNELS 4
+#define FR3D_MAX_LEVELS 64
+#define FR3D_ABI_VERSION 1
+
+typedef enum {
+    FR3D_OK = 0,
+    FR3D_ERR_ARG = -1,     /* bad argument / unsupported option */
+    FR3D_ERR_CUDA = -2,    /* CUDA runtime error */
+    FR3D_ERR_NOMEM = -3,   /* device or host allocation failed */
+    FR3D_ERR_STATE = -4    /* call order (e.g. no reference set) */
+} fr3d_status;
+
+typedef enum {
+    FR3D_F32 = 0,
+    FR3D_F64 = 1,
+    FR3D_U8 = 2,
+    FR3D_U16 = 3,
+    FR3D_I16 = 4,
+    FR3D_I32 = 5
+} fr3d_dtype;
+
+typedef enum {
+    FR3D_SWEEP_LEXICOGRAPHIC = 0, /* hyperplane wavefront: reproduces the reference's sweep order */
+    FR3D_SWEEP_REDBLACK = 1       /* checkerboard; faster, outside the parity tolerance */
+} fr3d_sweep;
+
+/* Per-axis resampling table of the fused Gauss (x) Keys-cubic resize
+ * (util/resize_util_3D.py:76-111): out[i] = sum_p wt[i*P+p] * src[idx[i*P+p]].  HOST pointers. */
+typedef struct {
+    int32_t in_len, out_len, P;
+    const int32_t* idx; /* host, out_len*P */
+    const float* wt;    /* host, out_len*P */
+} fr3d_axis_table;
+
+/* One pyramid level (core/optical_flow_3d.py:403-529), listed coarse -> fine. */
+typedef struct {
+    int32_t size[3];              /* level grid (pz, py, px) */
+    double h[3];                  /* (hz, hy, hx) = full_dim / level_dim */
+    double alpha[3];              /* (x, y, z) regularisation, already scaled for the level */
+    int32_t median;               /* 1: 5x5x5 median of the increments (min(size) > 5) */
+    fr3d_axis_table from_full[3]; /* (x, y, z) tables full resolution -> this level */
+    fr3d_axis_table from_prev[3]; /* (x, y, z) tables previous (coarser) level -> this level; unused at [0] */
+} fr3d_level;
+
+typedef struct {
+    int32_t abi_version;          /* FR3D_ABI_VERSION */
+    int32_t Z, Y, X, C;           /* full-resolution volume, channels */
+    int32_t max_batch;            /* frames processed concurrently per call */
+    int32_t n_levels;
+    const fr3d_level* levels;     /* host, n_levels entries, coarse -> fine */
+    fr3d_axis_table to_full[3];   /* (x, y, z) finest solved level -> full resolution; P = 0 if min_level == 0 */
+    int32_t iterations, update_lag;
+    double a_data[FR3D_MAX_CHANNELS];
+    double a_smooth;              /* only 1.0 (linear smoothness) is implemented; else FR3D_ERR_ARG */
+    int32_t sweep;                /* fr3d_sweep */
+    int32_t interp;               /* compensation warp: 3 = cubic B-spline, 1 = trilinear */
+    /* pre-filter (util/image_processing_3D.py:95-162): normalised Gaussian half-kernels
+     * w[0..r] (w[0] = centre) per channel and axis (z, y, x); r = 0 means identity.  HOST. */
+    int32_t gauss_radius[FR3D_MAX_CHANNELS][3];
+    const double* gauss_w[FR3D_MAX_CHANNELS][3];
+} fr3d_plan;
+
+typedef struct fr3d_ctx fr3d_ctx;
+
+/* ---- context ---------------------------------------------------------------------------- */
+/* plan may be NULL: a "bare" context that only serves the stage entry points. stream: a
+ * cudaStream_t cast to void* (NULL = the legacy default stream). */
+int fr3d_create(fr3d_ctx** out, int device, const fr3d_plan* plan, void* stream);
+void fr3d_destroy(fr3d_ctx* ctx);
+const char* fr3d_last_error(const fr3d_ctx* ctx); /* ctx may be NULL: last create() error */
+int fr3d_abi_version(void);
+int fr3d_synchronize(fr3d_ctx* ctx);
+/* number of kernel launches issued by this context so far (for bench.py's gpu_launches) */
+int64_t fr3d_launch_count(const fr3d_ctx* ctx);
+/* bytes of device memory currently held by the context */
+int64_t fr3d_device_bytes(const fr3d_ctx* ctx);
+
+/* ---- pipeline (needs a plan) ------------------------------------------------------------ */
+/* Normalise + Gaussian pre-filter (compensate_recording_3D.py:229-254): out = G * ((raw-lo)/den),
+ * float64 math, one rounding to float32 (the reference's first resize rounds it the same way).
+ * raw: (B,Z,Y,X,C) of `dtype`; lo, den: host, C doubles; out: (B,Z,Y,X,C) float32. */
+int fr3d_preprocess(fr3d_ctx* ctx, const void* raw, int dtype, int B, const double* lo,
+                    const double* den, float* out);
+
+/* Cache the fixed volume's pyramid and the weight pyramid (frame-invariant).
+ * ref_proc: (Z,Y,X,C) float32 pre-processed reference.  weight: (Z,Y,X,C) float32 or NULL, in which
+ * case weight_const (host, C doubles, already normalised) is broadcast. */
+int fr3d_set_reference(fr3d_ctx* ctx, const float* ref_proc, const float* weight,
+                       const double* weight_const);
+
+/* get_displacement for B frames against the cached reference (core/optical_flow_3d.py:319-542).
+ * moving_proc: (B,Z,Y,X,C) float32.  uvw_init: (Z,Y,X,3) float32 shared by all B frames, or NULL.
+ * flow_out: (B,Z,Y,X,3) of out_dtype (FR3D_F32 or FR3D_F64). */
+int fr3d_get_displacement(fr3d_ctx* ctx, const float* moving_proc, const float* uvw_init, int B,
+                          void* flow_out, int out_dtype);
+
+/* Compensation warp of B raw frames (parallelization/sequential_3d.py:153-160):
+ * out(x) = vol(x + flow(x)), plan.interp interpolation, out-of-volume voxels take ref's value.
+ * vol: (B,Z,Y,X,C) of vol_dtype; flow: (B,Z,Y,X,3) float32; ref: (Z,Y,X,C) of ref_dtype;
+ * out: (B,Z,Y,X,C) float32. */
+int fr3d_compensate(fr3d_ctx* ctx, const void* vol, int vol_dtype, const float* flow,
+                    const void* ref, int ref_dtype, int B, float* out);
+
+/* ---- stage entry points (any context; explicit sizes; used by the stage-wise parity tests
+ *      and by the per-pair imregister_wrapper shim) ---------------------------------------- */
+/* src: nvol planar volumes (D,H,W) float32 -> dst: nvol x (od,oh,ow); tables host, order (x,y,z). */
+int fr3d_resize3d(fr3d_ctx* ctx, const float* src, int nvol, int D, int H, int W,
+                  const fr3d_axis_table tables[3], float* dst);
+
+/* imregister_wrapper (core/optical_flow_3d.py:22-74) on an arbitrary volume:
+ * vol (Z,Y,X,C) vol_dtype; u,v,w (Z,Y,X) float64 displacements in voxels; ref (Z,Y,X,C) ref_dtype;
+ * out (Z,Y,X,C) float32; interp 3|1. */
+int fr3d_warp(fr3d_ctx* ctx, const void* vol, int vol_dtype, const double* u, const double* v,
+              const double* w, const void* ref, int ref_dtype, int Z, int Y, int X, int C,
+              int interp, float* out);
+
+/* get_motion_tensor_gc (core/optical_flow_3d.py:92-152) for one channel:
+ * f1, f2 (p,m,n) float32; f2_f32_math != 0 reproduces numpy's float32 arithmetic on a float32 f2
+ * (every level below the top); J: (10,p,m,n) float64, order J11,J22,J33,J44,J12,J13,J23,J14,J24,J34
+ * (the reference's zero ring is not stored). */
+int fr3d_motion_tensor(fr3d_ctx* ctx, const float* f1, const float* f2, int p, int m, int n,
+                       double hz, double hy, double hx, int f2_f32_math, double* J);
+
+/* compute_flow_3d (core/level_solver_3d.py:314-546) on interior arrays (no ring):
+ * J (C,10,p,m,n) float64; weight (C,p,m,n) float64; uvw (3,p,m,n) float64; alpha (x,y,z) host;
+ * a_data host C doubles; out d (3,p,m,n) float64 = du,dv,dw. */
+int fr3d_sor_level(fr3d_ctx* ctx, const double* J, const double* weight, const double* uvw, int p,
+                   int m, int n, int C, const double* alpha, double hz, double hy, double hx,
+                   int iterations, int update_lag, const double* a_data, double a_smooth,
+                   int sweep, double* d);
+
+/* scipy.ndimage.median_filter(size=5^3, mode="mirror") on nvol planar float64 volumes. */
+int fr3d_median5(fr3d_ctx* ctx, const double* src, int nvol, int p, int m, int n, double* dst);
+
+/* numpy.mean(frames, axis=0) of T float32 arrays of n elements: the w_init bootstrap / chaining of
+ * BatchMotionCorrector (compensate_recording_3D.py:388, 481-485), float32 accumulation in frame order. */
+int fr3d_mean_frames(fr3d_ctx* ctx, const float* frames, int T, int64_t n, float* out);
+
+/* ---- host helpers ----------------------------------------------------------------------- */
+/* util/resize_util_3D.py:76-95: fill idx/wt (host, out_len*(2R+4)) from the float32 Gaussian g
+ * (host, 2R+1 taps; numpy-computed by the caller so that it is bit-identical to the reference). */
+int fr3d_fill_resize_table(int in_len, int out_len, const float* g, int R, int32_t* idx, float* wt);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FR3D_H */
