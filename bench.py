@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the flowreg3D hot path on B200 (BASELINE.json metric: volumes/s on a
+2-channel 32x512x512 recording, fixed reference volume, frames sharded over the GPUs of one box).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one batch of B frames per GPU through the whole path: normalise + Gaussian pre-filter,
+pyramid, per-level cubic warp / motion tensor / wavefront SOR / 5^3 median, flow up-sampling and the
+cubic compensation warp of both channels, with the reference's w_init chaining between batches
+(OFOptions defaults: alpha 0.25, 100 iterations, update_lag 5, min_level 5, eta 0.8).
+
+  value  frames/s with the raw frames already resident in HBM (kernel-side throughput)
+  e2e    frames/s through the public API with pinned HOST buffers: H2D of the raw frames and D2H of
+         the registered frames and flow fields inside the timed region
+  roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md "Measurement".
+
+--impl reference times the reference's CPU implementation of the same path (its restatement in
+oracle/, the reference being Python and unable to travel) on the host cores, one frame per worker
+process per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+SHAPE = (32, 512, 512)
+CHANNELS = 2
+WORKLOAD = "config2: 2-channel 32x512x512 recording, fixed reference, OFOptions defaults (min_level 5 -> 2 levels, 100 it)"
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic inputs (numpy/scipy only; SURVEY.md 8(d) recipe)
+# ------------------------------------------------------------------------------------------------
+def make_reference():
+    from tests_inputs import synth_volume
+    return np.stack([synth_volume(SHAPE, 10 + c) for c in range(CHANNELS)], -1)
+
+
+def lowres_flow(seed, magnitude=2.0):
+    rng = np.random.default_rng(seed)
+    f = rng.standard_normal((3, 4, 8, 8)).astype(np.float32)
+    return f * (magnitude / np.abs(f).max())
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path, one frame per worker process
+# ------------------------------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_init(ref, frame):
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from oracle import oracle as O
+    O.build()
+    _CPU["O"] = O
+    _CPU["ref"] = ref
+    _CPU["frame"] = frame
+    sigma = np.array([[1.0, 1.0, 1.0, 0.1]] * CHANNELS)
+    _CPU["sigma"] = sigma
+    _CPU["ref_proc"] = O.preprocess(ref, sigma)          # once per recording, as the reference does
+
+
+def _cpu_frame(_):
+    O = _CPU["O"]
+    ref, frame = _CPU["ref"], _CPU["frame"]
+    mp_ = O.preprocess(frame[None], _CPU["sigma"], ref)[0]
+    flow = O.get_displacement(_CPU["ref_proc"], mp_, alpha=(0.25,) * 3, update_lag=5, iterations=100,
+                              min_level=5, levels=100, eta=0.8, a_smooth=1.0, a_data=0.45,
+                              weight=np.full(ref.shape, 0.5)).astype(np.float32)
+    reg = O.imregister_wrapper(frame, flow[..., 0], flow[..., 1], flow[..., 2], ref, "cubic")
+    return float(reg[3, 5, 7, 0])
+
+
+def cpu_cores():
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        import psutil
+        n = min(n, max(1, int(psutil.virtual_memory().available // (6 << 30))))  # ~6 GB per worker
+    except Exception:
+        pass
+    return max(1, min(n, 64))
+
+
+def cpu_frame_inputs():
+    from oracle import oracle as O
+    from tests_inputs import smooth_flow
+    ref = make_reference().astype(np.float64)
+    g = smooth_flow(SHAPE, 1000, 2.0, 12.0)
+    frame = O.imregister_wrapper(ref, -g[..., 0], -g[..., 1], -g[..., 2], ref, "linear")
+    return ref, frame
+
+
+def run_cpu(steps, warmup, cores=None):
+    """Returns (frames/s, cores, seconds per step).  Each step: `cores` frames, one per worker."""
+    cores = cores or cpu_cores()
+    ref, frame = cpu_frame_inputs()
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_cpu_init, initargs=(ref, frame)) as pool:
+        for _ in range(warmup):
+            pool.map(_cpu_frame, range(cores))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            pool.map(_cpu_frame, range(cores))
+        dt = time.perf_counter() - t0
+    return cores * steps / dt, cores, dt / max(steps, 1)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes(name, plan_levels, B, C, iters, lag):
+    """ALGORITHMIC HBM bytes of ONE launch of kernel `name`."""
+    Z, Y, X = SHAPE
+    NF = Z * Y * X
+    if name == "fr3d_sor_wavefront":
+        # parity-safe storage: 108 B / voxel / sweep + (12C+84) B per psi refresh; mean over the levels
+        per = [B * n * (108 * iters + (12 * C + 84) * -(-iters // lag)) for n in plan_levels]
+        return float(np.mean(per))
+    if "WarpGather" in name:
+        # cubic compensation warp (the full-resolution launch dominates): flow 12 B + C*(s_in + 12) + C*s_out
+        return float(B * NF * (12 + C * (4 + 12) + C * 4))
+    if "Spline" in name:
+        return float(B * C * NF * (4 + 8) if "SplineZ" in name else B * C * NF * 16)
+    if "PreZ" in name:
+        return float(B * C * NF * (4 + 8))
+    if "PreY" in name:
+        return float(B * C * NF * 16)
+    if "PreX" in name:
+        return float(B * C * NF * (8 + 4))
+    if "ResizePass" in name:
+        return float(B * C * NF * 4)
+    return None
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import flowreg3d_b200 as F
+    from flowreg3d_b200 import core, device as dev
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and world == 1 and args.gpus > 1:
+        raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        # first thing, before any CUDA call in this process: the worker pool forks
+        v, cores, sec = run_cpu(steps=1, warmup=0)
+        cpu = {"value": round(v, 4), "unit": "volumes/s", "cores": cores, "kind": "port",
+               "sample": f"{cores} frames of the same workload (one per worker process, {sec:.1f} s): oracle "
+                         "port of the reference CPU path (pre-filter + get_displacement + cubic warp)"}
+
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        import datetime
+        dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(minutes=20))
+
+    B = args.batch
+    Z, Y, X = SHAPE
+    C = CHANNELS
+    ref = make_reference()
+    opts = F.OFOptions(buffer_size=B)        # defaults: alpha .25, 100 it, lag 5, min_level 5, cubic, weight [.5,.5]
+    seq = F.SequenceCorrector(ref, opts, max_batch=B, device=device, group=None)
+    reg = seq.reg
+
+    # synthetic frames, generated ON the GPU with the library's own resize + linear warp (not timed):
+    # frame_t = backwarp(R, -g_t) + 0.01 N(0,1), g_t a smooth random field of <= 2 voxels
+    ctxb = core.bare_context(device)
+    ref_dev = dev.to_device(ref, device)
+    n_sets = 2
+    sets = []
+    gen = torch.Generator(device=device)
+    for s in range(n_sets):
+        frames = torch.empty((B, Z, Y, X, C), dtype=torch.float32, device=device)
+        for b in range(B):
+            seed = 1000 + 7919 * rank + s * B + b
+            lr = lowres_flow(seed)
+            g = np.stack([core.resize(lr[q], SHAPE) for q in range(3)], 0).astype(np.float64)
+            u, v, w = (dev.to_device(-g[q], device) for q in range(3))
+            out = frames[b]
+            core._check(ctxb.h, ctxb.lib.fr3d_warp(ctxb.h, dev.ptr(ref_dev), 0, dev.ptr(u), dev.ptr(v), dev.ptr(w),
+                                                   dev.ptr(ref_dev), 0, Z, Y, X, C, 1, dev.ptr(out)))
+            ctxb.sync()
+            gen.manual_seed(2000 + seed)
+            frames[b] += 0.01 * torch.randn(frames[b].shape, generator=gen, device=device)
+        sets.append(frames)
+    host_sets = [s.cpu().pin_memory() for s in sets]
+    out_reg = torch.empty((B, Z, Y, X, C), dtype=torch.float32).pin_memory()
+    out_flow = torch.empty((B, Z, Y, X, 3), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(device)
+
+    def step_resident(i):
+        return seq.process_batch(sets[i % n_sets], global_size=B * world, local_offset=B * rank)
+
+    def step_e2e(i):
+        r, f = seq.process_batch(host_sets[i % n_sets], global_size=B * world, local_offset=B * rank)
+        out_reg.copy_(r, non_blocking=True)
+        out_flow.copy_(f, non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+
+    # ---- device-resident throughput ("value") ----
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    reg.ctx.profile(True)
+    l0 = reg.ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step_resident(args.warmup + i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = reg.ctx.launches - l0
+    prof = reg.ctx.profile_report()
+    reg.ctx.profile(False)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end through the public API with host buffers ----
+    for i in range(min(args.warmup, 2)):
+        step_e2e(i)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step_e2e(args.warmup + i)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    t = torch.tensor([ms, ms_e2e, float(launches)], dtype=torch.float64, device=device)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, ms_e2e, launches = float(tmax[0]), float(tmax[1]), int(tsum[2])
+    frames_total = B * world * args.steps
+
+    if rank == 0:
+        peaks = {}
+        pk = ROOT / "MEASURED_PEAKS.json"
+        if pk.exists():
+            peaks = json.loads(pk.read_text())
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        level_n = [int(np.prod(s)) for _, s in reg.plan.sched]
+        table = []
+        for name, (cnt, tot) in prof.items():
+            ab = algorithmic_bytes(name, level_n, B, C, opts.iterations, opts.update_lag)
+            table.append({"kernel": name.replace("fr3d::", ""), "launches": cnt, "ms_total": round(tot, 3),
+                          "share": round(tot / ms, 4),
+                          "gbs": None if ab is None else round(ab / (tot / cnt * 1e-3) / 1e9, 1)})
+        table.sort(key=lambda r: -r["ms_total"])
+        top = table[0]
+        top_name = [n for n in prof if n.replace("fr3d::", "") == top["kernel"]][0]
+        ab = algorithmic_bytes(top_name, level_n, B, C, opts.iterations, opts.update_lag)
+        ach = None if ab is None else ab / (prof[top_name][1] / prof[top_name][0] * 1e-3) / 1e9
+        line = {
+            "metric": "volumes/s (32x512x512, 2 channels)", "value": round(frames_total / (ms * 1e-3), 3),
+            "unit": "volumes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": B, "global_batch": B * world,
+                       "sharding": f"frames x{world}, one all-reduce of w_init per batch" if world > 1 else "single GPU",
+                       "solver_sweep": "lexicographic (wavefront)",
+                       "arithmetic": "f64 solver/spline/pre-filter math on f32 images (the reference's rounding points)",
+                       "l2": "inputs (1.07 GB per step) exceed the 126 MB L2"},
+            "e2e": {"value": round(frames_total / (ms_e2e * 1e-3), 3), "unit": "volumes/s",
+                    "h2d_bytes_per_step": int(B * Z * Y * X * C * 4),
+                    "d2h_bytes_per_step": int(B * Z * Y * X * (C + 3) * 4)},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": top["kernel"], "achieved": None if ach is None else round(ach, 1),
+                         "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                         "frac": None if ach is None else round(ach / peak, 4), "traffic": None,
+                         "share_of_step": top["share"]},
+            "kernels": table[:8],
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    v, cores, sec = run_cpu(steps=args.steps, warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": "volumes/s (32x512x512, 2 channels)", "value": round(v, 4),
+        "unit": "volumes/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(sec * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step": cores},
+        "cpu_baseline": {"value": round(v, 4), "unit": "volumes/s", "cores": cores, "kind": "port",
+                         "sample": f"each step = {cores} frames of the workload, one per worker process "
+                                   "(oracle port of the reference CPU path: pre-filter + get_displacement + cubic warp)"},
+        "e2e": {"value": round(v, 4), "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="frames per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

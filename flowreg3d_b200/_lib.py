@@ -93,6 +93,8 @@ def load():
         "fr3d_sor_level": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, vp, cd, cd, cd, ci, ci, vp, cd, ci, vp]),
         "fr3d_median5": (ci, [vp, vp, ci, ci, ci, ci, vp]),
         "fr3d_mean_frames": (ci, [vp, vp, ci, i64, vp]),
+        "fr3d_profile_enable": (ci, [vp, ci]),
+        "fr3d_profile_report": (i64, [vp, C.c_char_p, i64]),
         "fr3d_fill_resize_table": (ci, [ci, ci, vp, ci, vp, vp]),
     }
     for name, (res, args) in sig.items():
@@ -109,9 +111,25 @@ EXPORTED_SYMBOLS = [
     "fr3d_abi_version", "fr3d_create", "fr3d_destroy", "fr3d_last_error", "fr3d_synchronize",
     "fr3d_launch_count", "fr3d_device_bytes", "fr3d_preprocess", "fr3d_set_reference",
     "fr3d_get_displacement", "fr3d_compensate", "fr3d_resize3d", "fr3d_warp", "fr3d_motion_tensor",
-    "fr3d_sor_level", "fr3d_median5", "fr3d_mean_frames", "fr3d_fill_resize_table",
+    "fr3d_sor_level", "fr3d_median5", "fr3d_mean_frames", "fr3d_profile_enable",
+    "fr3d_profile_report", "fr3d_fill_resize_table",
 ]
 
 
 def is_emulator() -> bool:
     return bool(os.environ.get("FR3D_LIBRARY_OVERRIDE"))
+
+
+def _select_for_tests(path) -> None:
+    """tests/conftest.py only: point the binding at the kernel-logic emulator (or back at the CUDA
+    library with None) and drop everything cached from the previous choice."""
+    global _lib
+    if path is None:
+        os.environ.pop("FR3D_LIBRARY_OVERRIDE", None)
+    else:
+        os.environ["FR3D_LIBRARY_OVERRIDE"] = str(path)
+    _lib = None
+    from . import core
+    for c in core._bare.values():
+        c.h = None  # the old library owns them; do not destroy through the new one
+    core._bare.clear()

@@ -61,6 +61,21 @@ class Context:
     def sync(self):
         _check(self.h, self.lib.fr3d_synchronize(self.h))
 
+    def profile(self, on: bool):
+        _check(self.h, self.lib.fr3d_profile_enable(self.h, 1 if on else 0))
+
+    def profile_report(self) -> dict:
+        """{kernel name: (launches, total_ms)} since the last report; synchronises."""
+        buf = C.create_string_buffer(1 << 16)
+        n = self.lib.fr3d_profile_report(self.h, buf, len(buf))
+        if n < 0:
+            _check(self.h, int(n))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.rsplit("\t", 2)
+            out[name] = (int(cnt), float(ms))
+        return out
+
     @property
     def launches(self) -> int:
         return int(self.lib.fr3d_launch_count(self.h))

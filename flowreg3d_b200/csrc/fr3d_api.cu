@@ -3,6 +3,9 @@
 // fr3d_sor.h.  Built for sm_100a by flowreg3d_b200/build.py; the FR3D_EMU build of this same file
 // is the test-only kernel-logic emulator (tests/emu).
 #include <memory>
+#ifndef FR3D_EMU
+#include <cxxabi.h>
+#endif
 
 #include "fr3d_sor.h"
 
@@ -632,6 +635,43 @@ int fr3d_median5(fr3d_ctx* ctx, const double* src, int nvol, int p, int m, int n
     FR3D_REQUIRE(src != dst, "fr3d_median5 cannot run in place");
     launch(_c->dev, Median5K{src, dst, nullptr, p, m, n}, (int64_t)nvol * p * m * n);
     FR3D_API_END()
+}
+
+int fr3d_profile_enable(fr3d_ctx* ctx, int on)
+{
+    FR3D_API_BEGIN(ctx)
+    _c->dev.profile_collect();
+    _c->dev.profiling = on != 0;
+    FR3D_API_END()
+}
+
+// Writes "name\tcount\ttotal_ms\n" lines (kernel names demangled); returns the number of bytes the
+// full report needs (excluding the terminator), or a negative status.
+int64_t fr3d_profile_report(fr3d_ctx* ctx, char* buf, int64_t cap)
+{
+    if (!ctx)
+        return FR3D_ERR_ARG;
+    std::string out;
+    for (auto& kv : ctx->dev.profile_collect()) {
+        std::string name = kv.first;
+#ifndef FR3D_EMU
+        int st = 0;
+        char* dm = abi::__cxa_demangle(name.c_str(), nullptr, nullptr, &st);
+        if (st == 0 && dm) {
+            name = dm;
+            free(dm);
+        }
+#endif
+        char line[256];
+        snprintf(line, sizeof(line), "\t%lld\t%.6f\n", (long long)kv.second.first, kv.second.second);
+        out += name + line;
+    }
+    if (buf && cap > 0) {
+        const size_t n = out.size() < (size_t)cap - 1 ? out.size() : (size_t)cap - 1;
+        memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)out.size();
 }
 
 int fr3d_mean_frames(fr3d_ctx* ctx, const float* frames, int T, int64_t n, float* out)

@@ -14,7 +14,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
+#include <typeinfo>
 #include <vector>
 
 #include "../../include/fr3d.h"
@@ -76,6 +78,67 @@ struct Device {
     int64_t launches = 0;
     int64_t bytes = 0;
     int sm_count = 1;
+
+    // Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline
+    // figures).  Off by default; when on, every launch is bracketed by two event records.
+    bool profiling = false;
+#ifndef FR3D_EMU
+    struct Span {
+        const char* name;
+        cudaEvent_t a, b;
+    };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get_event()
+    {
+        cudaEvent_t e;
+        if (!pool.empty()) {
+            e = pool.back();
+            pool.pop_back();
+            return e;
+        }
+        cudaEventCreate(&e);
+        return e;
+    }
+#endif
+    void span_begin(const char* name)
+    {
+#ifndef FR3D_EMU
+        if (!profiling)
+            return;
+        Span s{name, get_event(), get_event()};
+        cudaEventRecord(s.a, stream);
+        spans.push_back(s);
+#else
+        (void)name;
+#endif
+    }
+    void span_end()
+    {
+#ifndef FR3D_EMU
+        if (profiling)
+            cudaEventRecord(spans.back().b, stream);
+#endif
+    }
+    // name -> (launch count, total milliseconds); synchronises the stream; clears the spans
+    std::map<std::string, std::pair<int64_t, double>> profile_collect()
+    {
+        std::map<std::string, std::pair<int64_t, double>> out;
+#ifndef FR3D_EMU
+        cudaStreamSynchronize(stream);
+        for (Span& s : spans) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, s.a, s.b);
+            auto& e = out[s.name];
+            e.first += 1;
+            e.second += ms;
+            pool.push_back(s.a);
+            pool.push_back(s.b);
+        }
+        spans.clear();
+#endif
+        return out;
+    }
 
     void* alloc(size_t n)
     {
@@ -202,7 +265,9 @@ void launch(Device& dev, const K& k, int64_t n)
     const int threads = 256;
     const int64_t blocks = (n + threads - 1) / threads;
     FR3D_REQUIRE(blocks < (int64_t)2147483647, "launch too large: %lld items", (long long)n);
+    dev.span_begin(typeid(K).name());
     fr3d_kernel<K><<<(unsigned)blocks, threads, 0, dev.stream>>>(k, n);
+    dev.span_end();
     FR3D_CUDA(cudaGetLastError());
 #endif
     dev.launches++;

@@ -246,8 +246,10 @@ inline void sor_run(Device& dev, const SorParams& P, unsigned* bar)
     FR3D_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), dev.stream));
     SorParams Pc = P;
     void* args[] = {(void*)&Pc, (void*)&bar};
+    dev.span_begin("fr3d_sor_wavefront");
     FR3D_CUDA(cudaLaunchCooperativeKernel((void*)fr3d_sor_wavefront, dim3(grid), dim3(FR3D_SOR_THREADS),
                                           args, 0, dev.stream));
+    dev.span_end();
     dev.launches++;
 }
 #endif

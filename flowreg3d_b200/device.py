@@ -31,6 +31,8 @@ def default_device(index=None) -> torch.device:
 
 def to_device(a: np.ndarray, device: torch.device, pin: bool = False) -> torch.Tensor:
     a = np.ascontiguousarray(a)
+    if not a.flags.writeable:
+        a = a.copy()
     t = torch.from_numpy(a)
     if device.type == "cpu":
         return t

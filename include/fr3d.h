@@ -109,6 +109,12 @@ int64_t fr3d_launch_count(const fr3d_ctx* ctx);
 /* bytes of device memory currently held by the context */
 int64_t fr3d_device_bytes(const fr3d_ctx* ctx);
 
+/* Per-kernel timing with CUDA events on the context's stream (used by bench.py for the roofline
+ * figures).  fr3d_profile_report synchronises, writes "name<TAB>launches<TAB>total_ms" lines into buf
+ * (host) and clears the record; returns the byte length of the full report or a negative status. */
+int fr3d_profile_enable(fr3d_ctx* ctx, int on);
+int64_t fr3d_profile_report(fr3d_ctx* ctx, char* buf, int64_t cap);
+
 /* ---- pipeline (needs a plan) ------------------------------------------------------------ */
 /* Normalise + Gaussian pre-filter (compensate_recording_3D.py:229-254): out = G * ((raw-lo)/den),
  * float64 math, one rounding to float32 (the reference's first resize rounds it the same way).

@@ -1,0 +1,137 @@
+"""End-to-end parity of the drop-in entry points against the live reference's golden outputs and
+the oracle.  North-star tolerances (BASELINE.json): flow mean EPE <= 0.01 voxel, max EPE <= 0.05
+voxel, corrected volume relative L2 <= 1e-4.  The assertions below are much tighter: the path
+reproduces the reference's rounding points, so what remains is the reference's own float64
+last-bit noise (numba fastmath) amplified by float32 re-rounding between levels."""
+import numpy as np
+import pytest
+
+from conftest import epe_stats, rel_l2
+from oracle import oracle as O
+from tests_inputs import synth_volume
+
+RUNS = {
+    "ml0": dict(alpha=(0.25,) * 3, update_lag=5, iterations=30, min_level=0, levels=100, eta=0.8,
+                a_smooth=1.0, a_data=0.45),
+    "ml2w": dict(alpha=(0.25, 0.3, 0.2), update_lag=5, iterations=20, min_level=2, levels=100, eta=0.8,
+                 a_smooth=1.0, a_data=0.45, weight=np.array([0.3, 0.7])),
+}
+
+
+@pytest.mark.parametrize("run", ["ml2w", "ml0", "ml2w_uvw"])
+def test_get_displacement_vs_reference_and_oracle(backend, golden, run):
+    import flowreg3d_b200 as F
+    g = golden("flow_small")
+    kw = dict(RUNS[run.replace("_uvw", "")])
+    if run.endswith("_uvw"):
+        kw["uvw"] = g["uvw"].copy()
+    flow = F.get_displacement(g["fixed"], g["moving"], **kw)
+    assert flow.dtype == np.float64 and flow.shape == g["fixed"].shape[:3] + (3,)
+    mean, mx = epe_stats(flow, g[f"flow_{run}"])
+    assert mean <= 1e-4 and mx <= 5e-3, ("vs reference", mean, mx)     # tolerance: 0.01 / 0.05
+    mean, mx = epe_stats(flow, O.get_displacement(g["fixed"], g["moving"], **kw))
+    assert mean <= 1e-6 and mx <= 1e-4, ("vs oracle", mean, mx)
+
+
+def test_get_displacement_argument_handling(backend, golden):
+    import flowreg3d_b200 as F
+    g = golden("flow_small")
+    fx, mv = g["fixed"][:12, :20, :24, 0], g["moving"][:12, :20, :24, 0]
+    kw = dict(alpha=0.3, update_lag=5, iterations=5, min_level=0, levels=100, eta=0.8, a_smooth=1.0)
+    f3 = F.get_displacement(fx, mv, **kw)                      # 3-D input, scalar alpha
+    f4 = F.get_displacement(fx[..., None], mv[..., None], **{**kw, "alpha": (0.3,) * 3}, const_assumption="gray")
+    assert np.array_equal(f3, f4)                              # const_assumption is ignored, like the reference
+    o = O.get_displacement(fx, mv, **{**kw, "alpha": (0.3,) * 3})
+    assert epe_stats(f3, o)[1] <= 1e-6
+    with pytest.raises(NotImplementedError):
+        F.get_displacement(fx, mv, a_smooth=0.5)
+    with pytest.raises(ValueError):
+        F.get_displacement(fx, mv[:-1], **kw)
+
+
+def test_executor_matches_sequential_semantics(backend, golden):
+    """Boundary B1: process_batch == the reference's per-frame loop (oracle.process_batch)."""
+    import flowreg3d_b200 as F
+    g = golden("sequence")
+    ml, it, lag, _ = (int(v) for v in g["params"])
+    ref_raw = g["ref"].astype(np.float64)
+    sigma = np.array([[1.0, 1.0, 1.0, 0.1]] * 2)
+    ref_proc = O.preprocess(ref_raw, sigma)
+    batch = g["video"][:3]
+    bproc = O.preprocess(batch, sigma, ref_raw)
+    fp = dict(alpha=(0.25,) * 3, weight=np.full(ref_raw.shape, 0.5), levels=100, min_level=ml, eta=0.8,
+              update_lag=lag, iterations=it, a_smooth=1.0, a_data=0.45)
+    w0 = (0.3 * np.ones(ref_raw.shape[:3] + (3,))).astype(np.float32)
+    seen = []
+    ex = F.B200Executor3D(max_batch=2)  # 3 frames in chunks of 2: ragged last chunk
+    with ex:
+        reg, flows = ex.process_batch(batch, bproc, ref_raw, ref_proc, w0, None, None, "cubic", seen.append,
+                                      flow_params=fp)
+        reg2, flows2 = ex.process_batch(batch[:1], bproc[:1], ref_raw, ref_proc, w0, None, None, "linear",
+                                        None, flow_params=fp)
+    oreg, oflows = O.process_batch(batch, bproc, ref_raw, ref_proc, w0, "cubic", fp)
+    assert reg.dtype == batch.dtype and flows.dtype == np.float32 and sum(seen) == 3
+    mean, mx = epe_stats(flows, oflows)
+    assert mean <= 1e-6 and mx <= 1e-4
+    assert rel_l2(reg, oreg) <= 1e-6
+    oreg2, _ = O.process_batch(batch[:1], bproc[:1], ref_raw, ref_proc, w0, "linear", fp)
+    assert rel_l2(reg2, oreg2) <= 1e-6
+    with pytest.raises(NotImplementedError):
+        ex.process_batch(batch, bproc, ref_raw, ref_proc, w0, flow_params={**fp, "cc_initialization": True})
+
+
+def test_compensate_arr_3D_vs_reference(backend, golden):
+    """Sequence entry point incl. GPU pre-processing, w_init bootstrap and chaining."""
+    import flowreg3d_b200 as F
+    g = golden("sequence")
+    ml, it, lag, buf = (int(v) for v in g["params"])
+    opts = F.OFOptions(alpha=(0.25, 0.25, 0.25), levels=100, min_level=ml, iterations=it, update_lag=lag,
+                       buffer_size=buf, weight=[0.5, 0.5], output_typename=None)
+    ticks = []
+    reg, w = F.compensate_arr_3D(g["video"], g["ref"], opts, progress_callback=lambda c, t: ticks.append((c, t)))
+    assert reg.shape == g["video"].shape and reg.dtype == g["video"].dtype and w.dtype == np.float32
+    assert ticks[-1] == (g["video"].shape[0], g["video"].shape[0])
+    mean, mx = epe_stats(w, g["w"])
+    assert mean <= 1e-4 and mx <= 5e-3, (mean, mx)              # tolerance: 0.01 / 0.05
+    assert rel_l2(reg, g["registered"]) <= 1e-5                  # tolerance: 1e-4
+    assert opts.buffer_size == buf                               # caller's options are not mutated
+
+
+def test_compensate_arr_3D_shapes(backend, golden):
+    import flowreg3d_b200 as F
+    g = golden("sequence")
+    v = g["video"][:2, :10, :20, :24, 0]
+    r = g["ref"][:10, :20, :24, 0]
+    opts = F.OFOptions(min_level=1, iterations=4, buffer_size=2)
+    reg4, w4 = F.compensate_arr_3D(v, r, opts)                   # (T,Z,Y,X) + (Z,Y,X)
+    assert reg4.shape == v.shape and reg4.dtype == np.float64 and w4.shape == v.shape + (3,)
+    reg5, w5 = F.compensate_arr_3D(v[..., None], r[..., None], opts)
+    assert reg5.shape == v.shape + (1,)
+    np.testing.assert_allclose(reg4, reg5[..., 0], rtol=1e-4)    # reference test_compensate_arr_3D.py:402-427
+    reg3, w3 = F.compensate_arr_3D(v[0], r, opts)                # single volume
+    assert reg3.shape == r.shape and w3.shape == r.shape + (3,)
+    with pytest.raises(ValueError):
+        F.compensate_arr_3D(np.empty((0, 4, 4, 4)), r, opts)
+
+
+def test_config1_default_options(backend, golden):
+    """BASELINE config 1: 64x128x128 pair, OFOptions-default parameters, vs the live reference."""
+    import flowreg3d_b200 as F
+    from flowreg3d_b200 import device as dev
+    from flowreg3d_b200.compensate import normalization_range
+    g = golden("config1")
+    V = synth_volume((64, 128, 128), 1)
+    V64 = V.astype(np.float64)[..., None]
+    mov = g["low_moving"][..., None]
+    opts = F.OFOptions(sigma=[[1.0, 1.0, 1.0, 0.1]], weight=[1.0])
+    seq = F.SequenceCorrector(V64, opts, max_batch=1)
+    lo, den = normalization_range(V64, "joint")
+    mp = seq.reg.preprocess(mov[None], lo, den)
+    flow = seq.reg.get_displacement(mp)
+    reg = seq.reg.compensate(mov[None], flow)
+    seq.reg.sync()
+    flow, reg = dev.to_host(flow)[0], dev.to_host(reg)[0, ..., 0]
+    seq.close()
+    mean, mx = epe_stats(flow[::2, ::2, ::2], g["low_flow_s2"])
+    assert mean <= 1e-4 and mx <= 5e-3, (mean, mx)              # tolerance: 0.01 / 0.05
+    assert rel_l2(reg[::2, ::2, ::2], g["low_reg_s2"]) <= 1e-5   # tolerance: 1e-4
