@@ -718,37 +718,40 @@ struct Median5K {
         const float med = ForgetStep<64>::run(a, rest);
         // recover the float64 value of rank 62 (0-based)
         int less = 0, eq = 0;
-        double cand = 0.0;
+        double tmin = 0.0, tmax = 0.0;
         for (int t = 0; t < 125; ++t) {
             const double v = f[((int64_t)zi[t / 25] * m + yi[(t / 5) % 5]) * n + xi[t % 5]];
             const float key = (float)v;
             less += key < med;
             if (key == med) {
+                tmin = (eq == 0 || v < tmin) ? v : tmin;
+                tmax = (eq == 0 || v > tmax) ? v : tmax;
                 ++eq;
-                cand = v;
             }
         }
-        double res = cand;
-        if (eq > 1) {
-            // several data values round to the median key: take the (62 - less)-th smallest of them
-            const int want = 62 - less;
-            for (int t = 0; t < 125; ++t) {
-                const double v = f[((int64_t)zi[t / 25] * m + yi[(t / 5) % 5]) * n + xi[t % 5]];
-                if ((float)v != med)
-                    continue;
-                int lt = 0, le = 0;
-                for (int s = 0; s < 125; ++s) {
-                    const double u = f[((int64_t)zi[s / 25] * m + yi[(s / 5) % 5]) * n + xi[s % 5]];
-                    if ((float)u != med)
+        double res = tmin;
+        if (tmin != tmax) {
+            // distinct float64 values share the median key (rare; mirrored duplicates are equal and
+            // never get here): walk the tied values in increasing order up to rank (62 - less)
+            int want = 62 - less;
+            double cur = tmin;
+            for (;;) {
+                int mult = 0;
+                double next = tmax;
+                for (int t = 0; t < 125; ++t) {
+                    const double v = f[((int64_t)zi[t / 25] * m + yi[(t / 5) % 5]) * n + xi[t % 5]];
+                    if ((float)v != med)
                         continue;
-                    lt += u < v;
-                    le += u <= v;
+                    mult += v == cur;
+                    if (v > cur && v < next)
+                        next = v;
                 }
-                if (lt <= want && want < le) {
-                    res = v;
+                if (want < mult || cur == tmax)
                     break;
-                }
+                want -= mult;
+                cur = next;
             }
+            res = cur;
         }
         dst[item] = add ? add[item] + res : res;
     }

@@ -39,110 +39,139 @@ struct SorParams {
 
 #define FR3D_SOR_OMEGA 1.95
 
-// One voxel of sweep t on hyperplane s = k+j+i.
-FR3D_HD void sor_voxel(const SorParams& P, int b, int t, int s, int k, int j)
+// psi refresh + pre-combination for one voxel (sweeps with t % lag == 0): reads the 10C tensor
+// entries and the C weights, returns the 9 system entries A11,A22,A33,A12,A13,A23,b1,b2,b3.
+FR3D_HD void sor_refresh(const SorParams& P, const double* Jb, int64_t N, int64_t a0, double du, double dv,
+                         double dw, double* A)
 {
-    const int i = s - k - j;
-    const int64_t pm = (int64_t)P.p * P.m;
-    const int64_t N = pm * P.n;
-    const int cs = s % P.n;
-    const int cm = (cs + P.n - 1) % P.n;
-    const int cp = (cs + 1) % P.n;
-    const int64_t o = (int64_t)k * P.m + j;
-    const int64_t a0 = cs * pm + o;
-    double* d = P.d + (int64_t)b * 3 * N;
-    const double du = FR3D_LDCG(d + a0), dv = FR3D_LDCG(d + N + a0), dw = FR3D_LDCG(d + 2 * N + a0);
-
-    double A11, A22, A33, A12, A13, A23, b1, b2, b3;
-    double* AB = P.AB + (int64_t)b * 9 * N + a0;
-    if (t % P.lag == 0) {
-        A11 = A22 = A33 = A12 = A13 = A23 = b1 = b2 = b3 = 0.0;
-        for (int c = 0; c < P.C; ++c) {
-            const double* Jc = P.J + (((int64_t)b * P.C + c) * 10) * N + a0;
+#pragma unroll
+    for (int q = 0; q < 9; ++q)
+        A[q] = 0.0;
+#pragma unroll
+    for (int c = 0; c < FR3D_MAX_CHANNELS; ++c) {
+        if (c < P.C) {
+            const double* Jc = Jb + (int64_t)c * 10 * N + a0;
             const double J11 = Jc[0], J22 = Jc[N], J33 = Jc[2 * N], J44 = Jc[3 * N], J12 = Jc[4 * N],
-                         J13 = Jc[5 * N], J23 = Jc[6 * N], J14 = Jc[7 * N], J24 = Jc[8 * N],
-                         J34 = Jc[9 * N];
+                         J13 = Jc[5 * N], J23 = Jc[6 * N], J14 = Jc[7 * N], J24 = Jc[8 * N], J34 = Jc[9 * N];
             double ww = P.wgt[(int64_t)c * N + a0];
             const double adc = P.a_data[c];
             if (adc != 1.0) {
                 double val = J11 * du * du + J22 * dv * dv + J33 * dw * dw + 2.0 * J12 * du * dv +
-                             2.0 * J13 * du * dw + 2.0 * J23 * dv * dw + 2.0 * J14 * du +
-                             2.0 * J24 * dv + 2.0 * J34 * dw + J44;
+                             2.0 * J13 * du * dw + 2.0 * J23 * dv * dw + 2.0 * J14 * du + 2.0 * J24 * dv +
+                             2.0 * J34 * dw + J44;
                 if (val < 0.0)
                     val = 0.0;
                 ww *= adc * pow(val + 1e-6, adc - 1.0);
             }
-            A11 += ww * J11;
-            A22 += ww * J22;
-            A33 += ww * J33;
-            A12 += ww * J12;
-            A13 += ww * J13;
-            A23 += ww * J23;
-            b1 += ww * J14;
-            b2 += ww * J24;
-            b3 += ww * J34;
+            A[0] += ww * J11;
+            A[1] += ww * J22;
+            A[2] += ww * J33;
+            A[3] += ww * J12;
+            A[4] += ww * J13;
+            A[5] += ww * J23;
+            A[6] += ww * J14;
+            A[7] += ww * J24;
+            A[8] += ww * J34;
         }
-        FR3D_STCG(AB, A11);
-        FR3D_STCG(AB + N, A22);
-        FR3D_STCG(AB + 2 * N, A33);
-        FR3D_STCG(AB + 3 * N, A12);
-        FR3D_STCG(AB + 4 * N, A13);
-        FR3D_STCG(AB + 5 * N, A23);
-        FR3D_STCG(AB + 6 * N, b1);
-        FR3D_STCG(AB + 7 * N, b2);
-        FR3D_STCG(AB + 8 * N, b3);
-    } else {
-        A11 = FR3D_LDCG(AB);
-        A22 = FR3D_LDCG(AB + N);
-        A33 = FR3D_LDCG(AB + 2 * N);
-        A12 = FR3D_LDCG(AB + 3 * N);
-        A13 = FR3D_LDCG(AB + 4 * N);
-        A23 = FR3D_LDCG(AB + 5 * N);
-        b1 = FR3D_LDCG(AB + 6 * N);
-        b2 = FR3D_LDCG(AB + 7 * N);
-        b3 = FR3D_LDCG(AB + 8 * N);
     }
-
-    // neighbour increments: minus side from this sweep, plus side from the previous one
-    const int64_t am = cm * pm + o, ap = cp * pm + o;
-    const bool hx0 = i > 0, hx1 = i < P.n - 1, hy0 = j > 0, hy1 = j < P.m - 1, hz0 = k > 0,
-               hz1 = k < P.p - 1;
-    double sx[3], sy[3], sz[3];
-    const double own[3] = {du, dv, dw};
-    for (int q = 0; q < 3; ++q) {
-        const double* dq = d + q * N;
-        const double xm = hx0 ? FR3D_LDCG(dq + am) : own[q];
-        const double xp = hx1 ? FR3D_LDCG(dq + ap) : own[q];
-        const double ym = hy0 ? FR3D_LDCG(dq + am - 1) : own[q];
-        const double yp = hy1 ? FR3D_LDCG(dq + ap + 1) : own[q];
-        const double zm = hz0 ? FR3D_LDCG(dq + am - P.m) : own[q];
-        const double zp = hz1 ? FR3D_LDCG(dq + ap + P.m) : own[q];
-        sx[q] = xp + xm;
-        sy[q] = yp + ym;
-        sz[q] = zp + zm;
-    }
-    const double* Lb = P.L + (int64_t)b * 3 * N + a0;
-    const double den0 = 2.0 * P.ax + 2.0 * P.ay + 2.0 * P.az;
-    const double num_u = Lb[0] + P.ax * sx[0] + P.ay * sy[0] + P.az * sz[0];
-    const double num_v = Lb[N] + P.ax * sx[1] + P.ay * sy[1] + P.az * sz[1];
-    const double num_w = Lb[2 * N] + P.ax * sx[2] + P.ay * sy[2] + P.az * sz[2];
-    const double den_u = den0 + A11, den_v = den0 + A22, den_w = den0 + A33;
-
-    const double u1 = den_u != 0.0 ? (num_u - (b1 + A12 * dv + A13 * dw)) / den_u : 0.0;
-    const double du_n = (1.0 - FR3D_SOR_OMEGA) * du + FR3D_SOR_OMEGA * u1;
-    const double v1 = den_v != 0.0 ? (num_v - (b2 + A12 * du_n + A23 * dw)) / den_v : 0.0;
-    const double dv_n = (1.0 - FR3D_SOR_OMEGA) * dv + FR3D_SOR_OMEGA * v1;
-    const double w1 = den_w != 0.0 ? (num_w - (b3 + A13 * du_n + A23 * dv_n)) / den_w : 0.0;
-    const double dw_n = (1.0 - FR3D_SOR_OMEGA) * dw + FR3D_SOR_OMEGA * w1;
-    FR3D_STCG(d + a0, du_n);
-    FR3D_STCG(d + N + a0, dv_n);
-    FR3D_STCG(d + 2 * N + a0, dw_n);
 }
 
-// Wave bookkeeping shared by the CUDA kernel and the emulation loop.
+// Everything of a (frame b, sweep t, plane k) row that does not depend on j.
+struct SorRow {
+    int64_t N;
+    int64_t base0, basem, basep; // slab*pm + k*m for the voxel's slab and the two adjacent slabs
+    double* d;                   // frame's (3, N) increments
+    double* AB;                  // frame's (9, N) system
+    const double* L;             // frame's (3, N)
+    const double* J;             // frame's (C, 10, N)
+    int s, k, refresh;
+    bool hz0, hz1;
+};
+
+FR3D_HD SorRow sor_row(const SorParams& P, int b, int t, int s, int k)
+{
+    SorRow r;
+    const int64_t pm = (int64_t)P.p * P.m;
+    r.N = pm * P.n;
+    const int cs = s % P.n;
+    const int cm = cs == 0 ? P.n - 1 : cs - 1;
+    const int cp = cs == P.n - 1 ? 0 : cs + 1;
+    const int64_t row = (int64_t)k * P.m;
+    r.base0 = cs * pm + row;
+    r.basem = cm * pm + row;
+    r.basep = cp * pm + row;
+    r.d = P.d + (int64_t)b * 3 * r.N;
+    r.AB = P.AB + (int64_t)b * 9 * r.N;
+    r.L = P.L + (int64_t)b * 3 * r.N;
+    r.J = P.J + (int64_t)b * P.C * 10 * r.N;
+    r.s = s;
+    r.k = k;
+    r.refresh = (t % P.lag) == 0;
+    r.hz0 = k > 0;
+    r.hz1 = k < P.p - 1;
+    return r;
+}
+
+// One voxel (row r, column j) of sweep t on hyperplane s = k+j+i.  All loads are unconditional (an
+// out-of-domain neighbour reads the voxel's own, not yet updated, increment) and are issued before
+// the first use, so the memory latency is paid once per voxel.
+FR3D_HD void sor_voxel(const SorParams& P, const SorRow& r, int j)
+{
+    const int i = r.s - r.k - j;
+    const int64_t N = r.N;
+    const int64_t a0 = r.base0 + j;
+    const int64_t am = r.basem + j, ap = r.basep + j;
+    // neighbour addresses; minus side = this sweep, plus side = previous sweep
+    const int64_t axm = i > 0 ? am : a0, axp = i < P.n - 1 ? ap : a0;
+    const int64_t aym = j > 0 ? am - 1 : a0, ayp = j < P.m - 1 ? ap + 1 : a0;
+    const int64_t azm = r.hz0 ? am - P.m : a0, azp = r.hz1 ? ap + P.m : a0;
+    double* d0 = r.d;
+    double* d1 = d0 + N;
+    double* d2 = d1 + N;
+    const double du = FR3D_LDCG(d0 + a0), dv = FR3D_LDCG(d1 + a0), dw = FR3D_LDCG(d2 + a0);
+    double A[9];
+    double* AB = r.AB + a0;
+    if (!r.refresh) {
+#pragma unroll
+        for (int q = 0; q < 9; ++q)
+            A[q] = FR3D_LDCG(AB + q * N);
+    }
+    const double uxp = FR3D_LDCG(d0 + axp), uxm = FR3D_LDCG(d0 + axm), uyp = FR3D_LDCG(d0 + ayp),
+                 uym = FR3D_LDCG(d0 + aym), uzp = FR3D_LDCG(d0 + azp), uzm = FR3D_LDCG(d0 + azm);
+    const double vxp = FR3D_LDCG(d1 + axp), vxm = FR3D_LDCG(d1 + axm), vyp = FR3D_LDCG(d1 + ayp),
+                 vym = FR3D_LDCG(d1 + aym), vzp = FR3D_LDCG(d1 + azp), vzm = FR3D_LDCG(d1 + azm);
+    const double wxp = FR3D_LDCG(d2 + axp), wxm = FR3D_LDCG(d2 + axm), wyp = FR3D_LDCG(d2 + ayp),
+                 wym = FR3D_LDCG(d2 + aym), wzp = FR3D_LDCG(d2 + azp), wzm = FR3D_LDCG(d2 + azm);
+    const double* Lb = r.L + a0;
+    const double Lu = Lb[0], Lv = Lb[N], Lw = Lb[2 * N];
+    if (r.refresh) {
+        sor_refresh(P, r.J, N, a0, du, dv, dw, A);
+#pragma unroll
+        for (int q = 0; q < 9; ++q)
+            FR3D_STCG(AB + q * N, A[q]);
+    }
+    const double den0 = 2.0 * P.ax + 2.0 * P.ay + 2.0 * P.az;
+    const double num_u = Lu + P.ax * (uxp + uxm) + P.ay * (uyp + uym) + P.az * (uzp + uzm);
+    const double num_v = Lv + P.ax * (vxp + vxm) + P.ay * (vyp + vym) + P.az * (vzp + vzm);
+    const double num_w = Lw + P.ax * (wxp + wxm) + P.ay * (wyp + wym) + P.az * (wzp + wzm);
+    const double den_u = den0 + A[0], den_v = den0 + A[1], den_w = den0 + A[2];
+
+    const double u1 = den_u != 0.0 ? (num_u - (A[6] + A[3] * dv + A[4] * dw)) / den_u : 0.0;
+    const double du_n = (1.0 - FR3D_SOR_OMEGA) * du + FR3D_SOR_OMEGA * u1;
+    const double v1 = den_v != 0.0 ? (num_v - (A[7] + A[3] * du_n + A[5] * dw)) / den_v : 0.0;
+    const double dv_n = (1.0 - FR3D_SOR_OMEGA) * dv + FR3D_SOR_OMEGA * v1;
+    const double w1 = den_w != 0.0 ? (num_w - (A[8] + A[4] * du_n + A[5] * dv_n)) / den_w : 0.0;
+    const double dw_n = (1.0 - FR3D_SOR_OMEGA) * dw + FR3D_SOR_OMEGA * w1;
+    FR3D_STCG(d0 + a0, du_n);
+    FR3D_STCG(d1 + a0, dv_n);
+    FR3D_STCG(d2 + a0, dw_n);
+}
+
+// Wave bookkeeping shared by the CUDA kernel and the emulation loop.  A wave's work is a list of
+// rows (b, t, k); a warp takes a row and walks its valid j range 32 columns at a time.
 struct SorWave {
     int tlo, nT;
-    int64_t items; // warp-items: (b, t, k, j-chunk of 32)
+    int rows;
 };
 FR3D_HD int sor_num_waves(const SorParams& P) { return (P.p + P.m + P.n - 2) + 2 * (P.T - 1); }
 FR3D_HD SorWave sor_wave(const SorParams& P, int q)
@@ -156,24 +185,27 @@ FR3D_HD SorWave sor_wave(const SorParams& P, int q)
     SorWave w;
     w.tlo = tlo;
     w.nT = thi >= tlo ? thi - tlo + 1 : 0;
-    w.items = (int64_t)P.B * w.nT * P.p * ((P.m + 31) / 32);
+    w.rows = P.B * w.nT * P.p;
     return w;
 }
-// Execute lane `lane` of warp-item `it` of wave q.
-FR3D_HD void sor_item(const SorParams& P, int q, const SorWave& w, int64_t it, int lane)
+// Execute lane `lane` of row `row` of wave q.
+FR3D_HD void sor_do_row(const SorParams& P, int q, const SorWave& w, int row, int lane)
 {
-    const int chunks = (P.m + 31) / 32;
-    const int jc = (int)(it % chunks);
-    int64_t r = it / chunks;
-    const int k = (int)(r % P.p);
-    r /= P.p;
-    const int t = w.tlo + (int)(r % w.nT);
-    const int b = (int)(r / w.nT);
+    const int k = row % P.p;
+    int r = row / P.p;
+    const int t = w.tlo + r % w.nT;
+    const int b = r / w.nT;
     const int s = q - 2 * t;
-    const int j = jc * 32 + lane;
-    const int i = s - k - j;
-    if (j < P.m && i >= 0 && i < P.n)
-        sor_voxel(P, b, t, s, k, j);
+    int jlo = s - k - (P.n - 1);
+    jlo = jlo < 0 ? 0 : jlo;
+    int jhi = s - k;
+    jhi = jhi > P.m - 1 ? P.m - 1 : jhi;
+    if (jlo > jhi)
+        return;
+    const SorRow rc = sor_row(P, b, t, s, k);
+    for (int j = (jlo & ~31) + lane; j <= jhi; j += 32)
+        if (j >= jlo)
+            sor_voxel(P, rc, j);
 }
 
 #ifdef FR3D_EMU
@@ -182,9 +214,9 @@ inline void sor_run(Device& dev, const SorParams& P, unsigned*)
     const int nw = sor_num_waves(P);
     for (int q = 0; q < nw; ++q) {
         const SorWave w = sor_wave(P, q);
-        for (int64_t it = 0; it < w.items; ++it)
+        for (int row = 0; row < w.rows; ++row)
             for (int lane = 0; lane < 32; ++lane)
-                sor_item(P, q, w, it, lane);
+                sor_do_row(P, q, w, row, lane);
     }
     dev.launches++;
 }
@@ -205,7 +237,7 @@ __device__ __forceinline__ void fr3d_grid_barrier(unsigned* ctr, unsigned target
 }
 
 // Persistent cooperative kernel: all waves of one level solve, one grid barrier per wave.
-__global__ void __launch_bounds__(FR3D_SOR_THREADS) fr3d_sor_wavefront(const SorParams P, unsigned* bar)
+__global__ void __launch_bounds__(FR3D_SOR_THREADS, 2) fr3d_sor_wavefront(const SorParams P, unsigned* bar)
 {
     const int nw = sor_num_waves(P);
     const int wpb = blockDim.x >> 5;
@@ -213,8 +245,8 @@ __global__ void __launch_bounds__(FR3D_SOR_THREADS) fr3d_sor_wavefront(const Sor
     unsigned gen = 0;
     for (int q = 0; q < nw; ++q) {
         const SorWave w = sor_wave(P, q);
-        for (int64_t it = (int64_t)blockIdx.x * wpb + warp; it < w.items; it += (int64_t)gridDim.x * wpb)
-            sor_item(P, q, w, it, lane);
+        for (int row = blockIdx.x * wpb + warp; row < w.rows; row += gridDim.x * wpb)
+            sor_do_row(P, q, w, row, lane);
         ++gen;
         fr3d_grid_barrier(bar, gen * gridDim.x);
     }
@@ -226,16 +258,15 @@ inline void sor_run(Device& dev, const SorParams& P, unsigned* bar)
     FR3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fr3d_sor_wavefront,
                                                             FR3D_SOR_THREADS, 0));
     FR3D_REQUIRE(per_sm >= 1, "SOR kernel does not fit on an SM");
-    if (per_sm > 2)
-        per_sm = 2;
+    FR3D_REQUIRE((int64_t)P.B * P.T * P.p < 2147483647LL, "level too large for 32-bit row ids");
     // no more CTAs than the busiest wave can use
     int64_t peak = 0;
     {
         const int nw = sor_num_waves(P);
         for (int q = 0; q < nw; q += 1) {
             const SorWave w = sor_wave(P, q);
-            if (w.items > peak)
-                peak = w.items;
+            if (w.rows > peak)
+                peak = w.rows;
         }
     }
     const int wpb = FR3D_SOR_THREADS / 32;
