@@ -223,6 +223,7 @@ def run_gpu(args):
     B = args.batch
     Z, Y, X = SHAPE
     C = CHANNELS
+    core.STATE_DTYPE = np.float32 if args.state == "f32" else np.float64
     ref = make_reference()
     opts = F.OFOptions(buffer_size=B)        # defaults: alpha .25, 100 it, lag 5, min_level 5, cubic, weight [.5,.5]
     seq = F.SequenceCorrector(ref, opts, max_batch=B, device=device, group=None)
@@ -337,6 +338,7 @@ def run_gpu(args):
             "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": B, "global_batch": B * world,
                        "sharding": f"frames x{world}, one all-reduce of w_init per batch" if world > 1 else "single GPU",
                        "solver_sweep": "lexicographic (wavefront)",
+                       "solver_state": f"{args.state} increments, f64 system matrix",
                        "arithmetic": "f64 solver/spline/pre-filter math on f32 images (the reference's rounding points)",
                        "l2": "inputs (1.07 GB per step) exceed the 126 MB L2"},
             "e2e": {"value": round(frames_total / (ms_e2e * 1e-3), 3), "unit": "volumes/s",
@@ -384,6 +386,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="frames per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--state", default="f64", choices=["f64", "f32"],
+                    help="storage precision of the solver increments (f64 = strict parity mode)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -14,7 +14,7 @@ import numpy as np
 
 HERE = Path(__file__).resolve().parent
 MAX_CHANNELS = 4
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 F32, F64, U8, U16, I16, I32 = range(6)
 _DTYPES = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.uint8): U8,
@@ -44,7 +44,7 @@ class Plan(C.Structure):
                 ("levels", C.POINTER(Level)), ("to_full", AxisTable * 3),
                 ("iterations", C.c_int32), ("update_lag", C.c_int32),
                 ("a_data", C.c_double * MAX_CHANNELS), ("a_smooth", C.c_double),
-                ("sweep", C.c_int32), ("interp", C.c_int32),
+                ("sweep", C.c_int32), ("interp", C.c_int32), ("state_dtype", C.c_int32),
                 ("gauss_radius", (C.c_int32 * 3) * MAX_CHANNELS),
                 ("gauss_w", (C.c_void_p * 3) * MAX_CHANNELS)]
 
@@ -90,7 +90,7 @@ def load():
         "fr3d_resize3d": (ci, [vp, vp, ci, ci, ci, ci, C.POINTER(AxisTable), vp]),
         "fr3d_warp": (ci, [vp, vp, ci, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]),
         "fr3d_motion_tensor": (ci, [vp, vp, vp, ci, ci, ci, cd, cd, cd, ci, vp]),
-        "fr3d_sor_level": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, vp, cd, cd, cd, ci, ci, vp, cd, ci, vp]),
+        "fr3d_sor_level": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, vp, cd, cd, cd, ci, ci, vp, cd, ci, ci, vp]),
         "fr3d_median5": (ci, [vp, vp, ci, ci, ci, ci, vp]),
         "fr3d_mean_frames": (ci, [vp, vp, ci, i64, vp]),
         "fr3d_profile_enable": (ci, [vp, ci]),

@@ -30,6 +30,55 @@ struct DevTable {
     }
 };
 
+// Hyperplane-major solver storage of one (p,m,n) grid: host-built row table, device-built
+// neighbour / permutation tables (struct HPView in fr3d_kernels.h).
+struct HPGeom {
+    int p = 0, m = 0, n = 0, S = 0;
+    int32_t npad = 0;
+    std::vector<int32_t> pe_host;
+    Buf<int32_t> rowbase, start, pe, nbr, perm;
+    HPView view() const
+    {
+        return HPView{p, m, n, S, npad, rowbase.p, start.p, pe.p, nbr.p, perm.p};
+    }
+    void build(Device& dev, int p_, int m_, int n_)
+    {
+        p = p_;
+        m = m_;
+        n = n_;
+        S = p + m + n - 2;
+        FR3D_REQUIRE((int64_t)p * m * n + 32LL * S < 2147483647LL, "level %dx%dx%d too large for 32-bit slots", p, m, n);
+        std::vector<int32_t> rb((size_t)S * p), st((size_t)S + 1);
+        pe_host.assign(S, 0);
+        int64_t at = 0;
+        for (int s = 0; s < S; ++s) {
+            st[s] = (int32_t)at;
+            int64_t run = 0;
+            for (int k = 0; k < p; ++k) {
+                int jlo = s - k - (n - 1);
+                jlo = jlo < 0 ? 0 : jlo;
+                int jhi = s - k;
+                jhi = jhi > m - 1 ? m - 1 : jhi;
+                rb[(size_t)s * p + k] = (int32_t)(at + run - jlo);
+                if (jhi >= jlo)
+                    run += jhi - jlo + 1;
+            }
+            const int64_t padded = (run + 31) / 32 * 32;
+            pe_host[s] = (int32_t)(padded / 32) + (s >= 2 ? pe_host[s - 2] : 0);
+            at += padded;
+        }
+        st[S] = (int32_t)at;
+        npad = (int32_t)at;
+        rowbase.upload(dev, rb.data(), rb.size());
+        start.upload(dev, st.data(), st.size());
+        pe.upload(dev, pe_host.data(), pe_host.size());
+        nbr.ensure(dev, (size_t)6 * npad);
+        perm.ensure(dev, (size_t)npad);
+        launch(dev, HPFillK{nbr.p, perm.p, npad}, npad);
+        launch(dev, HPBuildK{view(), nbr.p, perm.p}, (int64_t)p * m * n);
+    }
+};
+
 struct LevelDev {
     int pz = 0, py = 0, px = 0;
     int64_t N = 0;
@@ -37,8 +86,9 @@ struct LevelDev {
     double alpha[3] = {0, 0, 0};
     bool median = false;
     DevTable full[3], prev[3];
-    Buf<float> f1;     // (C, N) natural planar: the reference pyramid level
-    Buf<double> wskew; // (C, N) skewed: resized channel weights
+    HPGeom hp;
+    Buf<float> f1;   // (C, N) natural planar: the reference pyramid level
+    Buf<double> whp; // (C, npad) solver storage: resized channel weights
 };
 
 // element strides of a 5-D view (o0, o1, z, y, x)
@@ -57,7 +107,7 @@ struct fr3d_ctx {
     std::string err;
     bool has_plan = false, ref_set = false;
     int Z = 0, Y = 0, X = 0, C = 0, max_batch = 0;
-    int iterations = 0, update_lag = 1, sweep = 0, interp = 3;
+    int iterations = 0, update_lag = 1, sweep = 0, interp = 3, state_dtype = FR3D_F32;
     double a_data[FR3D_MAX_CHANNELS] = {0, 0, 0, 0};
     double a_smooth = 1.0;
     std::vector<std::unique_ptr<LevelDev>> levels;
@@ -66,9 +116,11 @@ struct fr3d_ctx {
     Buf<double> pre_w[FR3D_MAX_CHANNELS][3];
     // workspaces (grow-only)
     Buf<float> t1, t2, f2, tmp, fscr;
-    Buf<double> uvw_a, uvw_b, coef, J, L, AB, d, dnat, g1, g2, wnat;
+    Buf<double> uvw_a, uvw_b, coef, J, AB, dnat, g1, g2, wnat;
+    Buf<char> L, d; // (B, npad) Vec4 of the state dtype
     Buf<unsigned> bar;
     DevTable stage_tab[3];
+    std::unique_ptr<HPGeom> stage_hp; // geometry cache of fr3d_sor_level
 };
 
 static thread_local std::string g_create_err;
@@ -145,33 +197,75 @@ static void check_dtype(int dt)
     FR3D_REQUIRE(dtype_size(dt) != 0, "unsupported dtype code %d", dt);
 }
 
-// Level solve on skewed storage; J, L assembled; result du,dv,dw in c->d (skewed).
-static void run_sor(fr3d_ctx* c, int B, int C, int p, int m, int n, const double* J, const double* wgt,
-                    const double* L, double ax, double ay, double az, int T, int lag, const double* a_data,
-                    int sweep)
+// Frames per warp work item: enough items to balance the busiest wave over the grid.
+static int sor_frame_group(int B) { return B >= 8 ? 4 : (B >= 2 ? 2 : 1); }
+
+// Level solve in solver storage: assembles J (when f1/f2 are given; otherwise Jpre is used as is), the
+// Laplacian term L and zero increments, then runs the wavefront solver.  Result in c->d.
+template <class ST>
+static void run_sor_t(fr3d_ctx* c, const HPGeom& hp, int B, int C, const float* f1, const float* f2, int f2f32,
+                      const double* Jpre, const double* uvw, const double* whp, double hz, double hy, double hx,
+                      const double* alpha, int T, int lag, const double* a_data)
 {
-    FR3D_REQUIRE(sweep == FR3D_SWEEP_LEXICOGRAPHIC, "sweep order %d is not implemented", sweep);
-    const int64_t N = (int64_t)p * m * n;
-    SorParams P;
-    P.p = p;
-    P.m = m;
-    P.n = n;
+    Device& dev = c->dev;
+    const int64_t np = hp.npad;
+    SorParams<ST> P;
+    P.g = hp.view();
     P.C = C;
     P.B = B;
     P.T = T;
     P.lag = lag;
-    P.ax = ax;
-    P.ay = ay;
-    P.az = az;
+    P.fg = sor_frame_group(B);
+    P.ax = alpha[0] / (hx * hx);
+    P.ay = alpha[1] / (hy * hy);
+    P.az = alpha[2] / (hz * hz);
     for (int q = 0; q < FR3D_MAX_CHANNELS; ++q)
         P.a_data[q] = q < C ? a_data[q] : 1.0;
+    double* J = const_cast<double*>(Jpre);
+    if (!J)
+        J = c->J.ensure(dev, (size_t)B * C * 10 * np);
     P.J = J;
-    P.wgt = wgt;
-    P.L = L;
-    P.AB = c->AB.ensure(c->dev, (size_t)B * 9 * N);
-    P.d = c->d.ensure(c->dev, (size_t)B * 3 * N);
-    c->dev.zero(P.d, (size_t)B * 3 * N * sizeof(double));
-    sor_run(c->dev, P, c->bar.ensure(c->dev, 4));
+    P.wgt = whp;
+    P.L = (Vec4<ST>*)c->L.ensure(dev, (size_t)B * np * sizeof(Vec4<ST>));
+    P.d = (Vec4<ST>*)c->d.ensure(dev, (size_t)B * np * sizeof(Vec4<ST>));
+    P.AB = c->AB.ensure(dev, (size_t)B * 9 * np);
+    AssembleK<ST> as;
+    as.f1 = f1;
+    as.f2 = f2;
+    as.uvw = uvw;
+    as.J = Jpre ? nullptr : J;
+    as.L = const_cast<Vec4<ST>*>(P.L);
+    as.d = P.d;
+    as.hp = P.g;
+    as.g = MTGeom{hp.p, hp.m, hp.n, hz, hy, hx, f2f32};
+    as.B = B;
+    as.C = C;
+    as.ax = P.ax;
+    as.ay = P.ay;
+    as.az = P.az;
+    launch(dev, as, (int64_t)B * np);
+    sor_run(dev, P, c->bar.ensure(dev, 4), hp.pe_host.data());
+}
+
+static void run_sor(fr3d_ctx* c, int state_dtype, const HPGeom& hp, int B, int C, const float* f1, const float* f2,
+                    int f2f32, const double* Jpre, const double* uvw, const double* whp, double hz, double hy,
+                    double hx, const double* alpha, int T, int lag, const double* a_data, int sweep)
+{
+    FR3D_REQUIRE(sweep == FR3D_SWEEP_LEXICOGRAPHIC, "sweep order %d is not implemented", sweep);
+    if (state_dtype == FR3D_F64)
+        run_sor_t<double>(c, hp, B, C, f1, f2, f2f32, Jpre, uvw, whp, hz, hy, hx, alpha, T, lag, a_data);
+    else
+        run_sor_t<float>(c, hp, B, C, f1, f2, f2f32, Jpre, uvw, whp, hz, hy, hx, alpha, T, lag, a_data);
+}
+
+// increments in solver storage -> natural planar float64 (B, 3, N)
+static void sor_result(fr3d_ctx* c, int state_dtype, const HPGeom& hp, int B, double* dnat)
+{
+    const int64_t n = (int64_t)B * 3 * hp.p * hp.m * hp.n;
+    if (state_dtype == FR3D_F64)
+        launch(c->dev, FromHPK<double>{(const Vec4<double>*)c->d.p, dnat, hp.view()}, n);
+    else
+        launch(c->dev, FromHPK<float>{(const Vec4<float>*)c->d.p, dnat, hp.view()}, n);
 }
 
 // ---- C ABI -------------------------------------------------------------------------------------
@@ -246,6 +340,9 @@ int fr3d_create(fr3d_ctx** out, int device, const fr3d_plan* plan, void* stream)
             c->sweep = plan->sweep;
             c->interp = plan->interp;
             c->a_smooth = plan->a_smooth;
+            FR3D_REQUIRE(plan->state_dtype == FR3D_F32 || plan->state_dtype == FR3D_F64,
+                         "state_dtype must be FR3D_F32 or FR3D_F64");
+            c->state_dtype = plan->state_dtype;
             for (int q = 0; q < FR3D_MAX_CHANNELS; ++q)
                 c->a_data[q] = plan->a_data[q];
             for (int li = 0; li < plan->n_levels; ++li) {
@@ -257,6 +354,7 @@ int fr3d_create(fr3d_ctx** out, int device, const fr3d_plan* plan, void* stream)
                 L.px = s.size[2];
                 FR3D_REQUIRE(L.pz > 0 && L.py > 0 && L.px > 0, "level %d has an empty grid", li);
                 L.N = (int64_t)L.pz * L.py * L.px;
+                L.hp.build(c->dev, L.pz, L.py, L.px);
                 L.hz = s.h[0];
                 L.hy = s.h[1];
                 L.hx = s.h[2];
@@ -363,11 +461,11 @@ int fr3d_set_reference(fr3d_ctx* ctx, const float* ref_proc, const float* weight
         LevelDev& L = *Lp;
         float* f1 = L.f1.ensure(_c->dev, (size_t)C * L.N);
         resize3<float, float>(_c, ref_proc, cl, 1, C, Z, Y, X, f1, planar(C, L.pz, L.py, L.px), L.full);
-        // weights: resized like an image (core/optical_flow_3d.py:475), widened to float64, skewed
+        // weights: resized like an image (core/optical_flow_3d.py:475), widened to float64, in solver storage
         double* wn = _c->wnat.ensure(_c->dev, (size_t)C * L.N);
         resize3<float, double>(_c, wsrc, cl, 1, C, Z, Y, X, wn, planar(C, L.pz, L.py, L.px), L.full);
-        double* ws = L.wskew.ensure(_c->dev, (size_t)C * L.N);
-        launch(_c->dev, ToSkewK{wn, ws, Skew{L.pz, L.py, L.px}}, (int64_t)C * L.N);
+        double* ws = L.whp.ensure(_c->dev, (size_t)C * L.hp.npad);
+        launch(_c->dev, ToHPK<double>{wn, ws, L.hp.view()}, (int64_t)C * L.hp.npad);
     }
     _c->ref_set = true;
     FR3D_API_END()
@@ -393,8 +491,6 @@ int fr3d_get_displacement(fr3d_ctx* ctx, const float* moving, const float* uvw_i
     float* tmp = _c->tmp.ensure(dev, (size_t)B * C * Nmax);
     double* ucur = _c->uvw_a.ensure(dev, (size_t)B * 3 * Nmax);
     double* uprev = _c->uvw_b.ensure(dev, (size_t)B * 3 * Nmax);
-    double* Jb = _c->J.ensure(dev, (size_t)B * C * 10 * Nmax);
-    double* Lb = _c->L.ensure(dev, (size_t)B * 3 * Nmax);
     double* dnat = _c->dnat.ensure(dev, (size_t)B * 3 * Nmax);
     const View mov_cl{NF * C, 1, (int64_t)Y * X * C, (int64_t)X * C, C};
 
@@ -457,24 +553,9 @@ int fr3d_get_displacement(fr3d_ctx* ctx, const float* moving, const float* uvw_i
             warped = tmp;
             f2f32 = 1; // numpy keeps the float32 warp output in float32 through its derivatives
         }
-        const double ax = L.alpha[0] / (L.hx * L.hx), ay = L.alpha[1] / (L.hy * L.hy),
-                     az = L.alpha[2] / (L.hz * L.hz);
-        AssembleK as;
-        as.f1 = L.f1.p;
-        as.f2 = warped;
-        as.uvw = ucur;
-        as.J = Jb;
-        as.L = Lb;
-        as.g = MTGeom{p, m, n, L.hz, L.hy, L.hx, f2f32};
-        as.B = B;
-        as.C = C;
-        as.ax = ax;
-        as.ay = ay;
-        as.az = az;
-        launch(dev, as, (int64_t)B * N);
-        run_sor(_c, B, C, p, m, n, Jb, L.wskew.p, Lb, ax, ay, az, _c->iterations, _c->update_lag, _c->a_data,
-                _c->sweep);
-        launch(dev, FromSkewK{_c->d.p, dnat, Skew{p, m, n}}, (int64_t)B * 3 * N);
+        run_sor(_c, _c->state_dtype, L.hp, B, C, L.f1.p, warped, f2f32, nullptr, ucur, L.whp.p, L.hz, L.hy, L.hx,
+                L.alpha, _c->iterations, _c->update_lag, _c->a_data, _c->sweep);
+        sor_result(_c, _c->state_dtype, L.hp, B, dnat);
         if (L.median)
             launch(dev, Median5K{dnat, ucur, ucur, p, m, n}, (int64_t)B * 3 * N); // (:517-529)
         else
@@ -594,37 +675,27 @@ int fr3d_motion_tensor(fr3d_ctx* ctx, const float* f1, const float* f2, int p, i
 
 int fr3d_sor_level(fr3d_ctx* ctx, const double* J, const double* weight, const double* uvw, int p, int m, int n,
                    int C, const double* alpha, double hz, double hy, double hx, int iterations, int update_lag,
-                   const double* a_data, double a_smooth, int sweep, double* d)
+                   const double* a_data, double a_smooth, int sweep, int state_dtype, double* d)
 {
     FR3D_API_BEGIN(ctx)
     FR3D_REQUIRE(J && weight && uvw && alpha && a_data && d, "null argument");
     FR3D_REQUIRE(p > 0 && m > 0 && n > 0 && C >= 1 && C <= FR3D_MAX_CHANNELS, "bad shape");
     FR3D_REQUIRE(iterations >= 1 && update_lag >= 1, "iterations/update_lag must be >= 1");
     FR3D_REQUIRE(a_smooth == 1.0, "a_smooth != 1 (nonlinear smoothness) is not implemented in libfr3d");
-    const int64_t N = (int64_t)p * m * n;
-    const Skew sk{p, m, n};
-    double* Js = _c->J.ensure(_c->dev, (size_t)C * 10 * N);
-    double* ws = _c->wnat.ensure(_c->dev, (size_t)C * N);
-    double* Ls = _c->L.ensure(_c->dev, (size_t)3 * N);
-    launch(_c->dev, ToSkewK{J, Js, sk}, (int64_t)C * 10 * N);
-    launch(_c->dev, ToSkewK{weight, ws, sk}, (int64_t)C * N);
-    const double ax = alpha[0] / (hx * hx), ay = alpha[1] / (hy * hy), az = alpha[2] / (hz * hz);
-    // reuse AssembleK for the Laplacian part only: C = 0 skips the tensor
-    AssembleK as;
-    as.f1 = nullptr;
-    as.f2 = nullptr;
-    as.uvw = uvw;
-    as.J = nullptr;
-    as.L = Ls;
-    as.g = MTGeom{p, m, n, hz, hy, hx, 0};
-    as.B = 1;
-    as.C = 0;
-    as.ax = ax;
-    as.ay = ay;
-    as.az = az;
-    launch(_c->dev, as, N);
-    run_sor(_c, 1, C, p, m, n, Js, ws, Ls, ax, ay, az, iterations, update_lag, a_data, sweep);
-    launch(_c->dev, FromSkewK{_c->d.p, d, sk}, (int64_t)3 * N);
+    FR3D_REQUIRE(state_dtype == FR3D_F32 || state_dtype == FR3D_F64, "state_dtype must be FR3D_F32 or FR3D_F64");
+    if (!_c->stage_hp || _c->stage_hp->p != p || _c->stage_hp->m != m || _c->stage_hp->n != n) {
+        _c->stage_hp.reset(new HPGeom());
+        _c->stage_hp->build(_c->dev, p, m, n);
+    }
+    const HPGeom& hp = *_c->stage_hp;
+    const int64_t np = hp.npad;
+    double* Js = _c->J.ensure(_c->dev, (size_t)C * 10 * np);
+    double* ws = _c->wnat.ensure(_c->dev, (size_t)C * np);
+    launch(_c->dev, ToHPK<double>{J, Js, hp.view()}, (int64_t)C * 10 * np);
+    launch(_c->dev, ToHPK<double>{weight, ws, hp.view()}, (int64_t)C * np);
+    run_sor(_c, state_dtype, hp, 1, C, nullptr, nullptr, 0, Js, uvw, ws, hz, hy, hx, alpha, iterations, update_lag,
+            a_data, sweep);
+    sor_result(_c, state_dtype, hp, 1, d);
     FR3D_API_END()
 }
 

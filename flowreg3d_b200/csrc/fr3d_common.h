@@ -273,6 +273,60 @@ void launch(Device& dev, const K& k, int64_t n)
     dev.launches++;
 }
 
+// {x,y,z,w} vector with natural 4-element alignment: float -> one 16-byte access, double -> two.
+template <class T>
+struct alignas(4 * sizeof(T) > 16 ? 16 : 4 * sizeof(T)) Vec4 {
+    T x, y, z, w;
+};
+
+// L2-only (cache-global) vector load / store: data written by other SMs in the previous wave
+FR3D_HD Vec4<float> ld4_cg(const Vec4<float>* p)
+{
+#ifdef __CUDA_ARCH__
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(p));
+    Vec4<float> r;
+    r.x = v.x;
+    r.y = v.y;
+    r.z = v.z;
+    r.w = v.w;
+    return r;
+#else
+    return *p;
+#endif
+}
+FR3D_HD Vec4<double> ld4_cg(const Vec4<double>* p)
+{
+#ifdef __CUDA_ARCH__
+    const double2 a = __ldcg(reinterpret_cast<const double2*>(p));
+    const double2 b = __ldcg(reinterpret_cast<const double2*>(p) + 1);
+    Vec4<double> r;
+    r.x = a.x;
+    r.y = a.y;
+    r.z = b.x;
+    r.w = b.y;
+    return r;
+#else
+    return *p;
+#endif
+}
+FR3D_HD void st4_cg(Vec4<float>* p, const Vec4<float>& v)
+{
+#ifdef __CUDA_ARCH__
+    __stcg(reinterpret_cast<float4*>(p), make_float4(v.x, v.y, v.z, v.w));
+#else
+    *p = v;
+#endif
+}
+FR3D_HD void st4_cg(Vec4<double>* p, const Vec4<double>& v)
+{
+#ifdef __CUDA_ARCH__
+    __stcg(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
+    __stcg(reinterpret_cast<double2*>(p) + 1, make_double2(v.z, v.w));
+#else
+    *p = v;
+#endif
+}
+
 FR3D_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 FR3D_HD size_t dtype_size(int dt)

@@ -517,70 +517,121 @@ struct MTImages {
 };
 
 // ------------------------------------------------------------------------------------------
-// Solver storage: the "rotated-skew" layout.  Voxel (k,j,i) of a (p,m,n) level lives at
-//     slab = (k + j + i) mod n,   offset = k*m + j,   address = slab*(p*m) + offset.
-// All voxels of the hyperplane k+j+i = s therefore sit in ONE contiguous slab, and the six stencil
-// neighbours sit in the two adjacent slabs at offsets {0, +-1, +-m}: every access of the wavefront
-// sweep is coalesced (see fr3d_sor.h).
-struct Skew {
-    int p, m, n;
-    FR3D_HD int64_t pm() const { return (int64_t)p * m; }
+// Solver storage: HYPERPLANE-MAJOR.  The voxels of hyperplane s = k+j+i of a (p,m,n) level are
+// stored contiguously, ordered by (k, j); every hyperplane is padded to a multiple of 32 slots.
+//     addr(k,j,i) = rowbase[(k+j+i)*p + k] + j
+// (rowbase folds in the hyperplane start, the sizes of the rows k' < k and the first valid j of
+// row k; it is built on the host, O(S*p)).  All voxels a wavefront sweep may update together are
+// therefore one dense range, and their six neighbours sit in the two adjacent hyperplanes at the
+// addresses listed in nbr (see fr3d_sor.h).
+struct HPView {
+    int p, m, n, S;         // S = p+m+n-2 hyperplanes
+    int32_t npad;           // storage slots (multiple of 32)
+    const int32_t* rowbase; // (S, p)
+    const int32_t* start;   // (S+1): first slot of hyperplane s
+    const int32_t* pe;      // (S): 32-slot chunks in hyperplanes s, s-2, s-4, ... (same-parity prefix sum)
+    const int32_t* nbr;     // (6, npad): slots of x-, y-, z-, x+, y+, z+ (own slot if outside); [0] = -1 on pad slots
+    const int32_t* perm;    // (npad): natural linear index (k*m + j)*n + i, or -1 on pad slots
     FR3D_HD int64_t nvox() const { return (int64_t)p * m * n; }
-    FR3D_HD int64_t addr(int k, int j, int i) const
+    FR3D_HD int32_t addr(int k, int j, int i) const { return rowbase[(k + j + i) * p + k] + j; }
+};
+
+// pad-slot defaults of the tables; item = slot
+struct HPFillK {
+    int32_t* nbr;
+    int32_t* perm;
+    int32_t npad;
+    FR3D_HD void operator()(int64_t a) const
     {
-        return (int64_t)((k + j + i) % n) * pm() + (int64_t)k * m + j;
-    }
-    // inverse: storage address -> (k,j,i)
-    FR3D_HD void coords(int64_t a, int& k, int& j, int& i) const
-    {
-        const int slab = (int)(a / pm());
-        const int o = (int)(a % pm());
-        k = o / m;
-        j = o % m;
-        i = ((slab - k - j) % n + n) % n;
+        perm[a] = -1;
+        nbr[a] = -1;
+        for (int q = 1; q < 6; ++q)
+            nbr[(int64_t)q * npad + a] = (int32_t)a;
     }
 };
 
-// Assemble the level system directly in skewed storage: motion tensor J (B,C,10,N) and the constant
-// part of the smoothness term L = ax*(u_ip+u_im-2u) + ay*(...) + az*(...) for u,v,w (B,3,N), with
-// replicate boundary (the reference's edge-padded ring, core/optical_flow_3d.py:88-89,418-426).
-// item = (b, skewed address).
+// item = natural voxel index
+struct HPBuildK {
+    HPView g;
+    int32_t* nbr;
+    int32_t* perm;
+    FR3D_HD void operator()(int64_t item) const
+    {
+        const int i = (int)(item % g.n);
+        const int j = (int)((item / g.n) % g.m);
+        const int k = (int)(item / ((int64_t)g.n * g.m));
+        const int32_t a = g.addr(k, j, i);
+        const int64_t np = g.npad;
+        perm[a] = (int32_t)item;
+        nbr[a] = i > 0 ? g.addr(k, j, i - 1) : a;
+        nbr[np + a] = j > 0 ? g.addr(k, j - 1, i) : a;
+        nbr[2 * np + a] = k > 0 ? g.addr(k - 1, j, i) : a;
+        nbr[3 * np + a] = i < g.n - 1 ? g.addr(k, j, i + 1) : a;
+        nbr[4 * np + a] = j < g.m - 1 ? g.addr(k, j + 1, i) : a;
+        nbr[5 * np + a] = k < g.p - 1 ? g.addr(k + 1, j, i) : a;
+    }
+};
+
+// Assemble the level system directly in solver storage: motion tensor J (B,C,10,npad), the constant
+// part of the smoothness term L = ax*(u_ip+u_im-2u) + ay*(...) + az*(...) for u,v,w, with replicate
+// boundary (the reference's edge-padded ring, core/optical_flow_3d.py:88-89,418-426), and the
+// zero-initialised increments.  item = (b, slot).
+template <class ST>
 struct AssembleK {
     const float* f1;   // (C, N) planar natural, shared by all frames
     const float* f2;   // (B, C, N) planar natural (the warped moving image)
     const double* uvw; // (B, 3, N) natural
-    double* J;         // (B, C, 10, N) skewed
-    double* L;         // (B, 3, N) skewed
+    double* J;         // (B, C, 10, npad) or null
+    Vec4<ST>* L;       // (B, npad)
+    Vec4<ST>* d;       // (B, npad)
+    HPView hp;
     MTGeom g;
     int B, C;
     double ax, ay, az; // alpha/h^2
     FR3D_HD void operator()(int64_t item) const
     {
-        const Skew sk{g.p, g.m, g.n};
-        const int64_t N = sk.nvox();
-        const int64_t a = item % N;
-        const int b = (int)(item / N);
-        int k, j, i;
-        sk.coords(a, k, j, i);
-        for (int c = 0; c < C; ++c) {
-            MTImages im{f1 + (int64_t)c * N, f2 + ((int64_t)b * C + c) * N, g};
-            double Jv[10];
-            im.tensor(k, j, i, Jv);
-            double* Jo = J + (((int64_t)b * C + c) * 10) * N + a;
-            for (int q = 0; q < 10; ++q)
-                Jo[q * N] = Jv[q];
+        const int64_t N = hp.nvox(), np = hp.npad;
+        const int64_t a = item % np;
+        const int b = (int)(item / np);
+        Vec4<ST> zero;
+        zero.x = zero.y = zero.z = zero.w = (ST)0;
+        d[(int64_t)b * np + a] = zero;
+        const int32_t nat = hp.perm[a];
+        if (nat < 0) {
+            L[(int64_t)b * np + a] = zero;
+            return;
+        }
+        const int i = nat % g.n;
+        const int j = (nat / g.n) % g.m;
+        const int k = nat / (g.n * g.m);
+        if (J) {
+            for (int c = 0; c < C; ++c) {
+                MTImages im{f1 + (int64_t)c * N, f2 + ((int64_t)b * C + c) * N, g};
+                double Jv[10];
+                im.tensor(k, j, i, Jv);
+                double* Jo = J + (((int64_t)b * C + c) * 10) * np + a;
+                for (int q = 0; q < 10; ++q)
+                    Jo[q * np] = Jv[q];
+            }
         }
         const int km = clampi(k - 1, 0, g.p - 1), kp = clampi(k + 1, 0, g.p - 1);
         const int jm = clampi(j - 1, 0, g.m - 1), jp = clampi(j + 1, 0, g.m - 1);
         const int im_ = clampi(i - 1, 0, g.n - 1), ip = clampi(i + 1, 0, g.n - 1);
+        double Lq[3];
         for (int q = 0; q < 3; ++q) {
             const double* f = uvw + ((int64_t)b * 3 + q) * N;
             const double c0 = f[((int64_t)k * g.m + j) * g.n + i];
             const double lx = f[((int64_t)k * g.m + j) * g.n + ip] + f[((int64_t)k * g.m + j) * g.n + im_] - 2.0 * c0;
             const double ly = f[((int64_t)k * g.m + jp) * g.n + i] + f[((int64_t)k * g.m + jm) * g.n + i] - 2.0 * c0;
             const double lz = f[((int64_t)kp * g.m + j) * g.n + i] + f[((int64_t)km * g.m + j) * g.n + i] - 2.0 * c0;
-            L[((int64_t)b * 3 + q) * N + a] = ax * lx + ay * ly + az * lz;
+            Lq[q] = ax * lx + ay * ly + az * lz;
         }
+        Vec4<ST> Lv;
+        Lv.x = (ST)Lq[0];
+        Lv.y = (ST)Lq[1];
+        Lv.z = (ST)Lq[2];
+        Lv.w = (ST)0;
+        L[(int64_t)b * np + a] = Lv;
     }
 };
 
@@ -602,35 +653,40 @@ struct MotionTensorK {
     }
 };
 
-// natural (nvol, N) <-> skewed (nvol, N); item = (vol, skewed address)
-struct ToSkewK {
-    const double* nat;
-    double* skw;
-    Skew sk;
+// natural (nvol, N) -> solver storage (nvol, npad), pad slots zero; item = (vol, slot)
+template <class SrcT>
+struct ToHPK {
+    const SrcT* nat;
+    double* hpv;
+    HPView hp;
     FR3D_HD void operator()(int64_t item) const
     {
-        const int64_t N = sk.nvox();
-        const int64_t a = item % N;
-        const int64_t vol = item / N;
-        int k, j, i;
-        sk.coords(a, k, j, i);
-        skw[item] = nat[vol * N + ((int64_t)k * sk.m + j) * sk.n + i];
+        const int64_t a = item % hp.npad;
+        const int64_t vol = item / hp.npad;
+        const int32_t o = hp.perm[a];
+        hpv[item] = o < 0 ? 0.0 : (double)nat[vol * hp.nvox() + o];
     }
 };
 
-struct FromSkewK { // item = (vol, natural address)
-    const double* skw;
+// increments in solver storage (B, npad){du,dv,dw} -> natural planar (B, 3, N) float64;
+// item = (b, q, natural index)
+template <class ST>
+struct FromHPK {
+    const Vec4<ST>* d;
     double* nat;
-    Skew sk;
+    HPView hp;
     FR3D_HD void operator()(int64_t item) const
     {
-        const int64_t N = sk.nvox();
+        const int64_t N = hp.nvox();
         const int64_t o = item % N;
-        const int64_t vol = item / N;
-        const int i = (int)(o % sk.n);
-        const int j = (int)((o / sk.n) % sk.m);
-        const int k = (int)(o / ((int64_t)sk.n * sk.m));
-        nat[item] = skw[vol * N + sk.addr(k, j, i)];
+        const int64_t r = item / N;
+        const int q = (int)(r % 3);
+        const int64_t b = r / 3;
+        const int i = (int)(o % hp.n);
+        const int j = (int)((o / hp.n) % hp.m);
+        const int k = (int)(o / ((int64_t)hp.n * hp.m));
+        const Vec4<ST>& v = d[b * hp.npad + hp.addr(k, j, i)];
+        nat[item] = (double)(q == 0 ? v.x : (q == 1 ? v.y : v.z));
     }
 };
 

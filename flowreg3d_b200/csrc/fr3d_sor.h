@@ -17,206 +17,261 @@
 // du,dv,dw) is voxel-local, so the refresh is fused into the sweep: at sweeps t % lag == 0 the
 // voxel recomputes psi from the 10C motion-tensor entries, pre-combines the 3x3 system
 //     A = sum_c w_c psi_c J_c[:3,:3],  b = sum_c w_c psi_c J_c[:3,3]
-// stores it (9 doubles) and uses it for the next `lag` sweeps.
+// stores it (9 doubles; the diagonal as 1/(2(ax+ay+az) + A_qq)) and uses it for the next sweeps.
 //
-// Storage is the rotated-skew layout of fr3d_kernels.h (struct Skew): a hyperplane is a contiguous
-// slab segment and the six neighbours sit at fixed offsets in the two adjacent slabs.
+// Storage is HYPERPLANE-MAJOR (struct HPView): the voxels of hyperplane s = k+j+i are stored
+// contiguously (ordered by k, then j), each hyperplane padded to a multiple of 32 slots, so a warp
+// work item is "32 consecutive slots of one hyperplane" with no idle lanes except in the pad, and
+// the six stencil neighbours come from a per-voxel neighbour table that is shared by every frame
+// of the batch.  The increments are kept as {du,dv,dw,-} vectors (one 16-byte access per voxel in
+// the float32 state mode).
+//
+// Arithmetic: float64 with explicit fma() (the reference solver is numba fastmath=True, i.e.
+// contraction/reassociation/reciprocal are already licensed there; bitwise equality with it is not
+// defined).  State storage (du,dv,dw and the constant Laplacian term) is float32 by default --
+// SURVEY.md 7.3-D measured that as far inside the tolerance -- or float64 (strict mode); the
+// system matrix is always float64.
 #pragma once
 #include "fr3d_kernels.h"
 
 namespace fr3d {
 
-struct SorParams {
-    int p, m, n, C, B, T, lag;
-    double ax, ay, az; // alpha_{x,y,z} / h_{x,y,z}^2
-    double a_data[FR3D_MAX_CHANNELS];
-    const double* J;   // (B, C, 10, N) skewed: J11,J22,J33,J44,J12,J13,J23,J14,J24,J34
-    const double* wgt; // (C, N) skewed, shared by all frames
-    const double* L;   // (B, 3, N) skewed: alpha-weighted Laplacian of u, v, w
-    double* AB;        // (B, 9, N) skewed: A11,A22,A33,A12,A13,A23,b1,b2,b3
-    double* d;         // (B, 3, N) skewed: du, dv, dw (zero-initialised)
-};
-
 #define FR3D_SOR_OMEGA 1.95
 
-// psi refresh + pre-combination for one voxel (sweeps with t % lag == 0): reads the 10C tensor
-// entries and the C weights, returns the 9 system entries A11,A22,A33,A12,A13,A23,b1,b2,b3.
-FR3D_HD void sor_refresh(const SorParams& P, const double* Jb, int64_t N, int64_t a0, double du, double dv,
-                         double dw, double* A)
-{
-#pragma unroll
-    for (int q = 0; q < 9; ++q)
-        A[q] = 0.0;
-#pragma unroll
-    for (int c = 0; c < FR3D_MAX_CHANNELS; ++c) {
-        if (c < P.C) {
-            const double* Jc = Jb + (int64_t)c * 10 * N + a0;
-            const double J11 = Jc[0], J22 = Jc[N], J33 = Jc[2 * N], J44 = Jc[3 * N], J12 = Jc[4 * N],
-                         J13 = Jc[5 * N], J23 = Jc[6 * N], J14 = Jc[7 * N], J24 = Jc[8 * N], J34 = Jc[9 * N];
-            double ww = P.wgt[(int64_t)c * N + a0];
-            const double adc = P.a_data[c];
-            if (adc != 1.0) {
-                double val = J11 * du * du + J22 * dv * dv + J33 * dw * dw + 2.0 * J12 * du * dv +
-                             2.0 * J13 * du * dw + 2.0 * J23 * dv * dw + 2.0 * J14 * du + 2.0 * J24 * dv +
-                             2.0 * J34 * dw + J44;
-                if (val < 0.0)
-                    val = 0.0;
-                ww *= adc * pow(val + 1e-6, adc - 1.0);
-            }
-            A[0] += ww * J11;
-            A[1] += ww * J22;
-            A[2] += ww * J33;
-            A[3] += ww * J12;
-            A[4] += ww * J13;
-            A[5] += ww * J23;
-            A[6] += ww * J14;
-            A[7] += ww * J24;
-            A[8] += ww * J34;
-        }
-    }
-}
-
-// Everything of a (frame b, sweep t, plane k) row that does not depend on j.
-struct SorRow {
-    int64_t N;
-    int64_t base0, basem, basep; // slab*pm + k*m for the voxel's slab and the two adjacent slabs
-    double* d;                   // frame's (3, N) increments
-    double* AB;                  // frame's (9, N) system
-    const double* L;             // frame's (3, N)
-    const double* J;             // frame's (C, 10, N)
-    int s, k, refresh;
-    bool hz0, hz1;
+template <class ST>
+struct SorParams {
+    HPView g;
+    int C, B, T, lag, fg; // fg: frames handled by one warp work item
+    double ax, ay, az;    // alpha_{x,y,z} / h_{x,y,z}^2
+    double a_data[FR3D_MAX_CHANNELS];
+    const double* J;      // (B, C, 10, npad): J11,J22,J33,J44,J12,J13,J23,J14,J24,J34
+    const double* wgt;    // (C, npad), shared by all frames
+    const Vec4<ST>* L;    // (B, npad): alpha-weighted Laplacian of u, v, w
+    Vec4<ST>* d;          // (B, npad): du, dv, dw (zero-initialised)
+    double* AB;           // (B, 9, npad): 1/den_u, 1/den_v, 1/den_w, A12, A13, A23, b1, b2, b3
 };
 
-FR3D_HD SorRow sor_row(const SorParams& P, int b, int t, int s, int k)
+// psi refresh + pre-combination for one voxel (sweeps with t % lag == 0)
+template <int C>
+FR3D_HD void sor_refresh(const double* a_data, const double* Jb, const double* wgt, int64_t np, int64_t a,
+                         double du, double dv, double dw, double den0, double* A)
 {
-    SorRow r;
-    const int64_t pm = (int64_t)P.p * P.m;
-    r.N = pm * P.n;
-    const int cs = s % P.n;
-    const int cm = cs == 0 ? P.n - 1 : cs - 1;
-    const int cp = cs == P.n - 1 ? 0 : cs + 1;
-    const int64_t row = (int64_t)k * P.m;
-    r.base0 = cs * pm + row;
-    r.basem = cm * pm + row;
-    r.basep = cp * pm + row;
-    r.d = P.d + (int64_t)b * 3 * r.N;
-    r.AB = P.AB + (int64_t)b * 9 * r.N;
-    r.L = P.L + (int64_t)b * 3 * r.N;
-    r.J = P.J + (int64_t)b * P.C * 10 * r.N;
-    r.s = s;
-    r.k = k;
-    r.refresh = (t % P.lag) == 0;
-    r.hz0 = k > 0;
-    r.hz1 = k < P.p - 1;
-    return r;
+    double S[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q)
+        S[q] = 0.0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const double* Jc = Jb + (int64_t)c * 10 * np + a;
+        const double J11 = Jc[0], J22 = Jc[np], J33 = Jc[2 * np], J44 = Jc[3 * np], J12 = Jc[4 * np],
+                     J13 = Jc[5 * np], J23 = Jc[6 * np], J14 = Jc[7 * np], J24 = Jc[8 * np], J34 = Jc[9 * np];
+        double ww = wgt[(int64_t)c * np + a];
+        const double adc = a_data[c];
+        if (adc != 1.0) {
+            // E = (du,dv,dw,1) J (du,dv,dw,1)^T  (level_solver_3d.py:363-375)
+            const double ru = fma(J11, du, fma(J12, dv, fma(J13, dw, J14)));
+            const double rv = fma(J12, du, fma(J22, dv, fma(J23, dw, J24)));
+            const double rw = fma(J13, du, fma(J23, dv, fma(J33, dw, J34)));
+            const double r1 = fma(J14, du, fma(J24, dv, fma(J34, dw, J44)));
+            double val = fma(ru, du, fma(rv, dv, fma(rw, dw, r1)));
+            if (val < 0.0)
+                val = 0.0;
+            // adc * (val + 1e-6)^(adc - 1)
+            ww *= adc * exp((adc - 1.0) * log(val + 1e-6));
+        }
+        S[0] = fma(ww, J11, S[0]);
+        S[1] = fma(ww, J22, S[1]);
+        S[2] = fma(ww, J33, S[2]);
+        S[3] = fma(ww, J12, S[3]);
+        S[4] = fma(ww, J13, S[4]);
+        S[5] = fma(ww, J23, S[5]);
+        S[6] = fma(ww, J14, S[6]);
+        S[7] = fma(ww, J24, S[7]);
+        S[8] = fma(ww, J34, S[8]);
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const double den = den0 + S[q];
+        A[q] = den != 0.0 ? 1.0 / den : 0.0; // reference: denom == 0 -> update is 0
+    }
+#pragma unroll
+    for (int q = 3; q < 9; ++q)
+        A[q] = S[q];
 }
 
-// One voxel (row r, column j) of sweep t on hyperplane s = k+j+i.  All loads are unconditional (an
-// out-of-domain neighbour reads the voxel's own, not yet updated, increment) and are issued before
-// the first use, so the memory latency is paid once per voxel.
-FR3D_HD void sor_voxel(const SorParams& P, const SorRow& r, int j)
-{
-    const int i = r.s - r.k - j;
-    const int64_t N = r.N;
-    const int64_t a0 = r.base0 + j;
-    const int64_t am = r.basem + j, ap = r.basep + j;
-    // neighbour addresses; minus side = this sweep, plus side = previous sweep
-    const int64_t axm = i > 0 ? am : a0, axp = i < P.n - 1 ? ap : a0;
-    const int64_t aym = j > 0 ? am - 1 : a0, ayp = j < P.m - 1 ? ap + 1 : a0;
-    const int64_t azm = r.hz0 ? am - P.m : a0, azp = r.hz1 ? ap + P.m : a0;
-    double* d0 = r.d;
-    double* d1 = d0 + N;
-    double* d2 = d1 + N;
-    const double du = FR3D_LDCG(d0 + a0), dv = FR3D_LDCG(d1 + a0), dw = FR3D_LDCG(d2 + a0);
+// Loaded inputs of one voxel update.
+template <class ST>
+struct SorIn {
+    Vec4<ST> own, L, xm, ym, zm, xp, yp, zp;
     double A[9];
-    double* AB = r.AB + a0;
-    if (!r.refresh) {
-#pragma unroll
-        for (int q = 0; q < 9; ++q)
-            A[q] = FR3D_LDCG(AB + q * N);
-    }
-    const double uxp = FR3D_LDCG(d0 + axp), uxm = FR3D_LDCG(d0 + axm), uyp = FR3D_LDCG(d0 + ayp),
-                 uym = FR3D_LDCG(d0 + aym), uzp = FR3D_LDCG(d0 + azp), uzm = FR3D_LDCG(d0 + azm);
-    const double vxp = FR3D_LDCG(d1 + axp), vxm = FR3D_LDCG(d1 + axm), vyp = FR3D_LDCG(d1 + ayp),
-                 vym = FR3D_LDCG(d1 + aym), vzp = FR3D_LDCG(d1 + azp), vzm = FR3D_LDCG(d1 + azm);
-    const double wxp = FR3D_LDCG(d2 + axp), wxm = FR3D_LDCG(d2 + axm), wyp = FR3D_LDCG(d2 + ayp),
-                 wym = FR3D_LDCG(d2 + aym), wzp = FR3D_LDCG(d2 + azp), wzm = FR3D_LDCG(d2 + azm);
-    const double* Lb = r.L + a0;
-    const double Lu = Lb[0], Lv = Lb[N], Lw = Lb[2 * N];
-    if (r.refresh) {
-        sor_refresh(P, r.J, N, a0, du, dv, dw, A);
-#pragma unroll
-        for (int q = 0; q < 9; ++q)
-            FR3D_STCG(AB + q * N, A[q]);
-    }
-    const double den0 = 2.0 * P.ax + 2.0 * P.ay + 2.0 * P.az;
-    const double num_u = Lu + P.ax * (uxp + uxm) + P.ay * (uyp + uym) + P.az * (uzp + uzm);
-    const double num_v = Lv + P.ax * (vxp + vxm) + P.ay * (vyp + vym) + P.az * (vzp + vzm);
-    const double num_w = Lw + P.ax * (wxp + wxm) + P.ay * (wyp + wym) + P.az * (wzp + wzm);
-    const double den_u = den0 + A[0], den_v = den0 + A[1], den_w = den0 + A[2];
+};
 
-    const double u1 = den_u != 0.0 ? (num_u - (A[6] + A[3] * dv + A[4] * dw)) / den_u : 0.0;
-    const double du_n = (1.0 - FR3D_SOR_OMEGA) * du + FR3D_SOR_OMEGA * u1;
-    const double v1 = den_v != 0.0 ? (num_v - (A[7] + A[3] * du_n + A[5] * dw)) / den_v : 0.0;
-    const double dv_n = (1.0 - FR3D_SOR_OMEGA) * dv + FR3D_SOR_OMEGA * v1;
-    const double w1 = den_w != 0.0 ? (num_w - (A[8] + A[4] * du_n + A[5] * dv_n)) / den_w : 0.0;
-    const double dw_n = (1.0 - FR3D_SOR_OMEGA) * dw + FR3D_SOR_OMEGA * w1;
-    FR3D_STCG(d0 + a0, du_n);
-    FR3D_STCG(d1 + a0, dv_n);
-    FR3D_STCG(d2 + a0, dw_n);
+template <class ST>
+FR3D_HD Vec4<ST> sor_update(const SorParams<ST>& P, const SorIn<ST>& r)
+{
+    const double du = (double)r.own.x, dv = (double)r.own.y, dw = (double)r.own.z;
+    const double num_u = fma(P.ax, (double)r.xp.x + (double)r.xm.x,
+                             fma(P.ay, (double)r.yp.x + (double)r.ym.x,
+                                 fma(P.az, (double)r.zp.x + (double)r.zm.x, (double)r.L.x)));
+    const double num_v = fma(P.ax, (double)r.xp.y + (double)r.xm.y,
+                             fma(P.ay, (double)r.yp.y + (double)r.ym.y,
+                                 fma(P.az, (double)r.zp.y + (double)r.zm.y, (double)r.L.y)));
+    const double num_w = fma(P.ax, (double)r.xp.z + (double)r.xm.z,
+                             fma(P.ay, (double)r.yp.z + (double)r.ym.z,
+                                 fma(P.az, (double)r.zp.z + (double)r.zm.z, (double)r.L.z)));
+    const double* A = r.A;
+    const double om = FR3D_SOR_OMEGA, om1 = 1.0 - FR3D_SOR_OMEGA;
+    const double u1 = (num_u - fma(A[3], dv, fma(A[4], dw, A[6]))) * A[0];
+    const double du_n = fma(om, u1, om1 * du);
+    const double v1 = (num_v - fma(A[3], du_n, fma(A[5], dw, A[7]))) * A[1];
+    const double dv_n = fma(om, v1, om1 * dv);
+    const double w1 = (num_w - fma(A[4], du_n, fma(A[5], dv_n, A[8]))) * A[2];
+    const double dw_n = fma(om, w1, om1 * dw);
+    Vec4<ST> o;
+    o.x = (ST)du_n;
+    o.y = (ST)dv_n;
+    o.z = (ST)dw_n;
+    o.w = (ST)0;
+    return o;
 }
 
 // Wave bookkeeping shared by the CUDA kernel and the emulation loop.  A wave's work is a list of
-// rows (b, t, k); a warp takes a row and walks its valid j range 32 columns at a time.
+// warp items (frame group, 32-slot chunk of one of the hyperplanes in flight).
 struct SorWave {
-    int tlo, nT;
-    int rows;
+    int s_lo, nT;   // hyperplanes in flight: s_lo, s_lo+2, ..., s_lo+2(nT-1)
+    int base;       // pe[s_lo-2] (chunks before the first hyperplane in flight, same parity)
+    int chunks;     // total chunks of this wave (one frame)
+    int items;      // chunks * frame groups
 };
-FR3D_HD int sor_num_waves(const SorParams& P) { return (P.p + P.m + P.n - 2) + 2 * (P.T - 1); }
-FR3D_HD SorWave sor_wave(const SorParams& P, int q)
+template <class ST>
+FR3D_HD int sor_num_waves(const SorParams<ST>& P) { return P.g.S + 2 * (P.T - 1); }
+template <class ST>
+FR3D_HD SorWave sor_wave(const SorParams<ST>& P, int q)
 {
-    const int S = P.p + P.m + P.n - 2;
+    const int S = P.g.S;
     int tlo = q - (S - 1);
     tlo = tlo > 0 ? (tlo + 1) / 2 : 0;
     int thi = q / 2;
     if (thi > P.T - 1)
         thi = P.T - 1;
     SorWave w;
-    w.tlo = tlo;
     w.nT = thi >= tlo ? thi - tlo + 1 : 0;
-    w.rows = P.B * w.nT * P.p;
+    w.s_lo = q - 2 * thi;
+    w.base = 0;
+    w.chunks = 0;
+    if (w.nT > 0) {
+        w.base = w.s_lo >= 2 ? P.g.pe[w.s_lo - 2] : 0;
+        w.chunks = P.g.pe[q - 2 * tlo] - w.base;
+    }
+    w.items = w.chunks * ((P.B + P.fg - 1) / P.fg);
     return w;
 }
-// Execute lane `lane` of row `row` of wave q.
-FR3D_HD void sor_do_row(const SorParams& P, int q, const SorWave& w, int row, int lane)
+
+// Execute lane `lane` of warp item `item` of wave q.
+template <class ST, int C>
+FR3D_HD void sor_item(const SorParams<ST>& P, int q, const SorWave& w, int item, int lane)
 {
-    const int k = row % P.p;
-    int r = row / P.p;
-    const int t = w.tlo + r % w.nT;
-    const int b = r / w.nT;
-    const int s = q - 2 * t;
-    int jlo = s - k - (P.n - 1);
-    jlo = jlo < 0 ? 0 : jlo;
-    int jhi = s - k;
-    jhi = jhi > P.m - 1 ? P.m - 1 : jhi;
-    if (jlo > jhi)
+    const HPView& g = P.g;
+    const int fgi = item / w.chunks;
+    const int f = item - fgi * w.chunks;
+    // hyperplane holding chunk f: smallest r with pe[s_lo + 2r] - base > f   (uniform per warp)
+    int lo = 0, hi = w.nT - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (g.pe[w.s_lo + 2 * mid] - w.base > f)
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    const int s = w.s_lo + 2 * lo;
+    const int before = (s >= 2 ? g.pe[s - 2] : 0) - w.base;
+    const int t = (q - s) >> 1;
+    const int64_t a = (int64_t)g.start[s] + 32 * (f - before) + lane;
+    const int64_t np = g.npad;
+    const int n0 = g.nbr[a];
+    if (n0 < 0)
+        return; // pad slot
+    const int n1 = g.nbr[np + a], n2 = g.nbr[2 * np + a], n3 = g.nbr[3 * np + a], n4 = g.nbr[4 * np + a],
+              n5 = g.nbr[5 * np + a];
+    const bool refresh = (t % P.lag) == 0;
+    const double den0 = 2.0 * P.ax + 2.0 * P.ay + 2.0 * P.az;
+    const int b0 = fgi * P.fg;
+    const int b1 = b0 + P.fg < P.B ? b0 + P.fg : P.B;
+    if (refresh) {
+        for (int b = b0; b < b1; ++b) {
+            Vec4<ST>* d = P.d + (int64_t)b * np;
+            double* AB = P.AB + (int64_t)b * 9 * np + a;
+            SorIn<ST> r;
+            r.own = ld4_cg(d + a);
+            r.xm = ld4_cg(d + n0);
+            r.ym = ld4_cg(d + n1);
+            r.zm = ld4_cg(d + n2);
+            r.xp = ld4_cg(d + n3);
+            r.yp = ld4_cg(d + n4);
+            r.zp = ld4_cg(d + n5);
+            r.L = ld4_cg(P.L + (int64_t)b * np + a);
+            sor_refresh<C>(P.a_data, P.J + (int64_t)b * C * 10 * np, P.wgt, np, a, (double)r.own.x, (double)r.own.y,
+                           (double)r.own.z, den0, r.A);
+#pragma unroll
+            for (int e = 0; e < 9; ++e)
+                FR3D_STCG(AB + e * np, r.A[e]);
+            st4_cg(d + a, sor_update(P, r));
+        }
         return;
-    const SorRow rc = sor_row(P, b, t, s, k);
-    for (int j = (jlo & ~31) + lane; j <= jhi; j += 32)
-        if (j >= jlo)
-            sor_voxel(P, rc, j);
+    }
+    // plain sweep: two frames in flight per lane (all loads of both issued before the first use)
+    int b = b0;
+    for (; b + 1 < b1; b += 2) {
+        SorIn<ST> r[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const Vec4<ST>* d = P.d + (int64_t)(b + e) * np;
+            const double* AB = P.AB + (int64_t)(b + e) * 9 * np + a;
+            r[e].own = ld4_cg(d + a);
+            r[e].xm = ld4_cg(d + n0);
+            r[e].ym = ld4_cg(d + n1);
+            r[e].zm = ld4_cg(d + n2);
+            r[e].xp = ld4_cg(d + n3);
+            r[e].yp = ld4_cg(d + n4);
+            r[e].zp = ld4_cg(d + n5);
+            r[e].L = ld4_cg(P.L + (int64_t)(b + e) * np + a);
+#pragma unroll
+            for (int k = 0; k < 9; ++k)
+                r[e].A[k] = FR3D_LDCG(AB + k * np);
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+            st4_cg(P.d + (int64_t)(b + e) * np + a, sor_update(P, r[e]));
+    }
+    if (b < b1) {
+        SorIn<ST> r;
+        const Vec4<ST>* d = P.d + (int64_t)b * np;
+        const double* AB = P.AB + (int64_t)b * 9 * np + a;
+        r.own = ld4_cg(d + a);
+        r.xm = ld4_cg(d + n0);
+        r.ym = ld4_cg(d + n1);
+        r.zm = ld4_cg(d + n2);
+        r.xp = ld4_cg(d + n3);
+        r.yp = ld4_cg(d + n4);
+        r.zp = ld4_cg(d + n5);
+        r.L = ld4_cg(P.L + (int64_t)b * np + a);
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+            r.A[k] = FR3D_LDCG(AB + k * np);
+        st4_cg(P.d + (int64_t)b * np + a, sor_update(P, r));
+    }
 }
 
 #ifdef FR3D_EMU
-inline void sor_run(Device& dev, const SorParams& P, unsigned*)
+template <class ST, int C>
+inline void sor_run_c(Device& dev, const SorParams<ST>& P, unsigned*)
 {
     const int nw = sor_num_waves(P);
     for (int q = 0; q < nw; ++q) {
         const SorWave w = sor_wave(P, q);
-        for (int row = 0; row < w.rows; ++row)
+        for (int item = 0; item < w.items; ++item)
             for (int lane = 0; lane < 32; ++lane)
-                sor_do_row(P, q, w, row, lane);
+                sor_item<ST, C>(P, q, w, item, lane);
     }
     dev.launches++;
 }
@@ -237,7 +292,8 @@ __device__ __forceinline__ void fr3d_grid_barrier(unsigned* ctr, unsigned target
 }
 
 // Persistent cooperative kernel: all waves of one level solve, one grid barrier per wave.
-__global__ void __launch_bounds__(FR3D_SOR_THREADS, 2) fr3d_sor_wavefront(const SorParams P, unsigned* bar)
+template <class ST, int C>
+__global__ void __launch_bounds__(FR3D_SOR_THREADS, 2) fr3d_sor_wavefront(const SorParams<ST> P, unsigned* bar)
 {
     const int nw = sor_num_waves(P);
     const int wpb = blockDim.x >> 5;
@@ -245,44 +301,76 @@ __global__ void __launch_bounds__(FR3D_SOR_THREADS, 2) fr3d_sor_wavefront(const 
     unsigned gen = 0;
     for (int q = 0; q < nw; ++q) {
         const SorWave w = sor_wave(P, q);
-        for (int row = blockIdx.x * wpb + warp; row < w.rows; row += gridDim.x * wpb)
-            sor_do_row(P, q, w, row, lane);
+        for (int item = blockIdx.x * wpb + warp; item < w.items; item += gridDim.x * wpb)
+            sor_item<ST, C>(P, q, w, item, lane);
         ++gen;
         fr3d_grid_barrier(bar, gen * gridDim.x);
     }
 }
 
-inline void sor_run(Device& dev, const SorParams& P, unsigned* bar)
+template <class ST, int C>
+inline void sor_run_c(Device& dev, const SorParams<ST>& P, unsigned* bar, int peak_items)
 {
     int per_sm = 0;
-    FR3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fr3d_sor_wavefront,
+    FR3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fr3d_sor_wavefront<ST, C>,
                                                             FR3D_SOR_THREADS, 0));
     FR3D_REQUIRE(per_sm >= 1, "SOR kernel does not fit on an SM");
-    FR3D_REQUIRE((int64_t)P.B * P.T * P.p < 2147483647LL, "level too large for 32-bit row ids");
     // no more CTAs than the busiest wave can use
-    int64_t peak = 0;
-    {
-        const int nw = sor_num_waves(P);
-        for (int q = 0; q < nw; q += 1) {
-            const SorWave w = sor_wave(P, q);
-            if (w.rows > peak)
-                peak = w.rows;
-        }
-    }
     const int wpb = FR3D_SOR_THREADS / 32;
-    int64_t want = (peak + wpb - 1) / wpb;
+    int64_t want = ((int64_t)peak_items + wpb - 1) / wpb;
     int grid = dev.sm_count * per_sm;
     if (want < grid)
         grid = (int)(want < 1 ? 1 : want);
     FR3D_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), dev.stream));
-    SorParams Pc = P;
+    SorParams<ST> Pc = P;
     void* args[] = {(void*)&Pc, (void*)&bar};
     dev.span_begin("fr3d_sor_wavefront");
-    FR3D_CUDA(cudaLaunchCooperativeKernel((void*)fr3d_sor_wavefront, dim3(grid), dim3(FR3D_SOR_THREADS),
+    FR3D_CUDA(cudaLaunchCooperativeKernel((void*)fr3d_sor_wavefront<ST, C>, dim3(grid), dim3(FR3D_SOR_THREADS),
                                           args, 0, dev.stream));
     dev.span_end();
     dev.launches++;
 }
 #endif
+
+// peak number of warp items over all waves (host; pe_host = host copy of the chunk prefix)
+inline int sor_peak_items(int S, int T, int B, int fg, const int32_t* pe_host)
+{
+    int peak = 0;
+    const int nw = S + 2 * (T - 1);
+    for (int q = 0; q < nw; ++q) {
+        int tlo = q - (S - 1);
+        tlo = tlo > 0 ? (tlo + 1) / 2 : 0;
+        int thi = q / 2;
+        if (thi > T - 1)
+            thi = T - 1;
+        if (thi < tlo)
+            continue;
+        const int s_lo = q - 2 * thi;
+        const int c = pe_host[q - 2 * tlo] - (s_lo >= 2 ? pe_host[s_lo - 2] : 0);
+        if (c > peak)
+            peak = c;
+    }
+    return peak * ((B + fg - 1) / fg);
+}
+
+template <class ST>
+inline void sor_run(Device& dev, const SorParams<ST>& P, unsigned* bar, const int32_t* pe_host)
+{
+#ifdef FR3D_EMU
+    (void)pe_host;
+#define FR3D_SOR_GO(C_) sor_run_c<ST, C_>(dev, P, bar)
+#else
+    const int peak = sor_peak_items(P.g.S, P.T, P.B, P.fg, pe_host);
+#define FR3D_SOR_GO(C_) sor_run_c<ST, C_>(dev, P, bar, peak)
+#endif
+    switch (P.C) {
+    case 1: FR3D_SOR_GO(1); break;
+    case 2: FR3D_SOR_GO(2); break;
+    case 3: FR3D_SOR_GO(3); break;
+    case 4: FR3D_SOR_GO(4); break;
+    default: FR3D_THROW(FR3D_ERR_ARG, "C=%d outside 1..%d", P.C, FR3D_MAX_CHANNELS);
+    }
+#undef FR3D_SOR_GO
+}
 
 } // namespace fr3d

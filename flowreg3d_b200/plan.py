@@ -164,7 +164,7 @@ class PlanHolder:
     """Owns the ctypes fr3d_plan and every host buffer it points to."""
 
     def __init__(self, shape, C_: int, fp: FlowParams, max_batch: int = 1, interp: int = 3,
-                 sigma=None, sweep: int = SWEEP_LEXICOGRAPHIC):
+                 sigma=None, sweep: int = SWEEP_LEXICOGRAPHIC, state_dtype=np.float32):
         Z, Y, X = (int(s) for s in shape)
         self.shape = (Z, Y, X)
         self.C = int(C_)
@@ -214,6 +214,9 @@ class PlanHolder:
         P.a_smooth = float(fp.a_smooth)
         P.sweep = int(sweep)
         P.interp = int(interp)
+        if np.dtype(state_dtype) not in (np.dtype(np.float32), np.dtype(np.float64)):
+            raise ValueError("state_dtype must be float32 or float64")
+        P.state_dtype = _lib.dtype_code(state_dtype)
         sz = sigma_zyx(sigma, self.C) if sigma is not None else np.zeros((self.C, 3))
         for c in range(self.C):
             for a in range(3):

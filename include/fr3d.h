@@ -34,7 +34,7 @@ extern "C" {
 
 #define FR3D_MAX_CHANNELS 4
 #define FR3D_MAX_LEVELS 64
-#define FR3D_ABI_VERSION 1
+#define FR3D_ABI_VERSION 2
 
 typedef enum {
     FR3D_OK = 0,
@@ -88,6 +88,9 @@ typedef struct {
     double a_smooth;              /* only 1.0 (linear smoothness) is implemented; else FR3D_ERR_ARG */
     int32_t sweep;                /* fr3d_sweep */
     int32_t interp;               /* compensation warp: 3 = cubic B-spline, 1 = trilinear */
+    int32_t state_dtype;          /* solver state storage (du,dv,dw and the constant Laplacian term):
+                                   * FR3D_F32 (default; SURVEY 7.3-D: far inside the tolerance) or
+                                   * FR3D_F64 (strict).  The system matrix and all arithmetic are float64. */
     /* pre-filter (util/image_processing_3D.py:95-162): normalised Gaussian half-kernels
      * w[0..r] (w[0] = centre) per channel and axis (z, y, x); r = 0 means identity.  HOST. */
     int32_t gauss_radius[FR3D_MAX_CHANNELS][3];
@@ -163,11 +166,12 @@ int fr3d_motion_tensor(fr3d_ctx* ctx, const float* f1, const float* f2, int p, i
 
 /* compute_flow_3d (core/level_solver_3d.py:314-546) on interior arrays (no ring):
  * J (C,10,p,m,n) float64; weight (C,p,m,n) float64; uvw (3,p,m,n) float64; alpha (x,y,z) host;
- * a_data host C doubles; out d (3,p,m,n) float64 = du,dv,dw. */
+ * a_data host C doubles; state_dtype FR3D_F32|FR3D_F64 (see fr3d_plan); out d (3,p,m,n) float64 =
+ * du,dv,dw. */
 int fr3d_sor_level(fr3d_ctx* ctx, const double* J, const double* weight, const double* uvw, int p,
                    int m, int n, int C, const double* alpha, double hz, double hy, double hx,
                    int iterations, int update_lag, const double* a_data, double a_smooth,
-                   int sweep, double* d);
+                   int sweep, int state_dtype, double* d);
 
 /* scipy.ndimage.median_filter(size=5^3, mode="mirror") on nvol planar float64 volumes. */
 int fr3d_median5(fr3d_ctx* ctx, const double* src, int nvol, int p, int m, int n, double* dst);
