@@ -158,7 +158,15 @@ static void resize3(fr3d_ctx* c, const SrcT* src, View sv, int64_t n0, int64_t n
     float* a = c->t1.ensure(c->dev, (size_t)(n0 * n1) * D * H * ow);
     float* b = c->t2.ensure(c->dev, (size_t)(n0 * n1) * D * oh * ow);
     const View av = planar(n1, D, H, ow), bv = planar(n1, D, oh, ow);
-    {
+    // The item order of a pass is free (ResizePassK takes explicit extents and strides): when the
+    // source / destination is channel-interleaved (stride of the n1 axis == 1) the n1 axis is made the
+    // fastest one so that the interleaved side is accessed contiguously.
+    if (sv.s1 == 1 && n1 > 1) {
+        const int64_t n[5] = {n0, D, H, ow, n1};
+        const int64_t ss[5] = {sv.s0, sv.sz, sv.sy, sv.sx, sv.s1};
+        const int64_t ds[5] = {av.s0, av.sz, av.sy, av.sx, av.s1};
+        resize_pass<SrcT, float>(c, src, ss, a, ds, n, 3, tabs[0]);
+    } else {
         const int64_t n[5] = {n0, n1, D, H, ow};
         const int64_t ss[5] = {sv.s0, sv.s1, sv.sz, sv.sy, sv.sx};
         const int64_t ds[5] = {av.s0, av.s1, av.sz, av.sy, av.sx};
@@ -170,12 +178,54 @@ static void resize3(fr3d_ctx* c, const SrcT* src, View sv, int64_t n0, int64_t n
         const int64_t ds[5] = {bv.s0, bv.s1, bv.sz, bv.sy, bv.sx};
         resize_pass<float, float>(c, a, ss, b, ds, n, 3, tabs[1]);
     }
-    {
+    if (dv.s1 == 1 && n1 > 1) {
+        const int64_t n[5] = {n0, od, oh, ow, n1};
+        const int64_t ss[5] = {bv.s0, bv.sz, bv.sy, bv.sx, bv.s1};
+        const int64_t ds[5] = {dv.s0, dv.sz, dv.sy, dv.sx, dv.s1};
+        resize_pass<float, DstT>(c, b, ss, dst, ds, n, 1, tabs[2]);
+    } else {
         const int64_t n[5] = {n0, n1, od, oh, ow};
         const int64_t ss[5] = {bv.s0, bv.s1, bv.sz, bv.sy, bv.sx};
         const int64_t ds[5] = {dv.s0, dv.s1, dv.sz, dv.sy, dv.sx};
         resize_pass<float, DstT>(c, b, ss, dst, ds, n, 2, tabs[2]);
     }
+}
+
+// One in-place prefilter pass over `nlines` lines of N samples through the shared-memory tiled kernel;
+// lines too long for a tile fall back to the one-thread-per-line kernel.
+template <class Fallback>
+static void spline_tile_pass(fr3d_ctx* c, double* coef, int N, int64_t nlines, int64_t per_group, int64_t group_stride,
+                             int64_t line_stride, int64_t elem_stride, int64_t first, int line_fast,
+                             const Fallback& fallback)
+{
+    const int L3 = N + 3;
+    const int Lv = N + 2 * FR3D_SPLINE_PAD;
+    int nseg = Lv / 48;
+    nseg = nseg < 1 ? 1 : (nseg > 8 ? 8 : nseg);
+    int TL = 256 / nseg;
+    TL = TL > 32 ? 32 : TL;
+    const size_t budget = 72 * 1024; // three resident blocks per SM: staging copies overlap the filter phases
+    while (TL > 1 && (size_t)TL * (L3 + nseg + FR3D_SPLINE_PAD) * sizeof(double) > budget)
+        TL /= 2;
+    if ((size_t)TL * (L3 + nseg + FR3D_SPLINE_PAD) * sizeof(double) > budget || TL < 4) {
+        fallback();
+        return;
+    }
+    SplineTileK k;
+    k.coef = coef;
+    k.N = N;
+    k.TL = TL;
+    k.NSEG = nseg;
+    k.W = 40;
+    k.nlines = nlines;
+    k.per_group = per_group;
+    k.group_stride = group_stride;
+    k.line_stride = line_stride;
+    k.elem_stride = elem_stride;
+    k.first = first;
+    k.line_fast = line_fast;
+    int threads = (TL * nseg + 31) / 32 * 32;
+    launch_tiles(c->dev, k, (nlines + TL - 1) / TL, threads, (size_t)TL * (L3 + nseg + FR3D_SPLINE_PAD) * sizeof(double));
 }
 
 // Cubic B-spline coefficients of B*C volumes (any dtype / strides) -> c->coef.
@@ -186,10 +236,10 @@ static void spline_prefilter(fr3d_ctx* c, const void* src, int dt, int64_t sb, i
     double* coef = c->coef.ensure(c->dev, n);
     SplineZK kz{src, dt, sb, sc, sz, sy, sx, coef, B, C, Z, Y, X};
     launch(c->dev, kz, (int64_t)B * Y * X * C);
-    SplineYK ky{coef, Z, Y, X};
-    launch(c->dev, ky, (int64_t)B * C * (Z + 3) * X);
-    SplineXK kx{coef, X};
-    launch(c->dev, kx, (int64_t)B * C * (Z + 3) * (Y + 3));
+    spline_tile_pass(c, coef, Y, (int64_t)B * C * (Z + 3) * X, X, (int64_t)(Y + 3) * (X + 3), 1, X + 3, 1, 1,
+                     [&] { launch(c->dev, SplineYK{coef, Z, Y, X}, (int64_t)B * C * (Z + 3) * X); });
+    spline_tile_pass(c, coef, X, (int64_t)B * C * (Z + 3) * (Y + 3), (int64_t)1 << 62, 0, X + 3, 1, 0, 0,
+                     [&] { launch(c->dev, SplineXK{coef, X}, (int64_t)B * C * (Z + 3) * (Y + 3)); });
 }
 
 static void check_dtype(int dt)
@@ -432,10 +482,48 @@ int fr3d_preprocess(fr3d_ctx* ctx, const void* raw, int dtype, int B, const doub
     }
     const size_t n = (size_t)B * C * Z * Y * X;
     double* a = _c->g1.ensure(_c->dev, n);
-    double* b = _c->g2.ensure(_c->dev, n);
-    launch(_c->dev, PreZK{raw, dtype, a, B, Z, Y, X, C, g}, (int64_t)n);
-    launch(_c->dev, PreYK{a, b, C, Z, Y, X, g}, (int64_t)n);
-    launch(_c->dev, PreXK{b, out, B, Z, Y, X, C, g}, (int64_t)n);
+    int rz = g.r[0][0];
+    for (int ch = 1; ch < C; ++ch)
+        if (g.r[ch][0] != rz)
+            rz = -1;
+    const int64_t ncol = (int64_t)B * Y * X * C;
+    switch (rz) {
+    case 1: launch(_c->dev, PreZWinK<1>{raw, dtype, a, B, Z, Y, X, C, g}, ncol); break;
+    case 2: launch(_c->dev, PreZWinK<2>{raw, dtype, a, B, Z, Y, X, C, g}, ncol); break;
+    case 3: launch(_c->dev, PreZWinK<3>{raw, dtype, a, B, Z, Y, X, C, g}, ncol); break;
+    case 4: launch(_c->dev, PreZWinK<4>{raw, dtype, a, B, Z, Y, X, C, g}, ncol); break;
+    case 5: launch(_c->dev, PreZWinK<5>{raw, dtype, a, B, Z, Y, X, C, g}, ncol); break;
+    case 6: launch(_c->dev, PreZWinK<6>{raw, dtype, a, B, Z, Y, X, C, g}, ncol); break;
+    default: launch(_c->dev, PreZK{raw, dtype, a, B, Z, Y, X, C, g}, (int64_t)n); break; // mixed / large / zero radii
+    }
+    int RY = 0, RX = 0;
+    for (int ch = 0; ch < C; ++ch) {
+        RY = g.r[ch][1] > RY ? g.r[ch][1] : RY;
+        RX = g.r[ch][2] > RX ? g.r[ch][2] : RX;
+    }
+    if (RY <= 16 && RX <= 16) {
+        PreYXTileK k;
+        k.in = a;
+        k.out = out;
+        k.B = B;
+        k.Z = Z;
+        k.Y = Y;
+        k.X = X;
+        k.C = C;
+        k.RY = RY;
+        k.RX = RX;
+        k.g = g;
+        k.tiles_y = (Y + PreYXTileK::TY - 1) / PreYXTileK::TY;
+        k.tiles_x = (X + PreYXTileK::TX - 1) / PreYXTileK::TX;
+        const int IW = PreYXTileK::TX + 2 * RX, IH = PreYXTileK::TY + 2 * RY;
+        const size_t smem = (size_t)(IH * IW + PreYXTileK::TY * IW) * sizeof(double) +
+                            (size_t)PreYXTileK::TY * PreYXTileK::TX * C * sizeof(float);
+        launch_tiles(_c->dev, k, (int64_t)B * Z * k.tiles_y * k.tiles_x, 256, smem);
+    } else {
+        double* b = _c->g2.ensure(_c->dev, n);
+        launch(_c->dev, PreYK{a, b, C, Z, Y, X, g}, (int64_t)n);
+        launch(_c->dev, PreXK{b, out, B, Z, Y, X, C, g}, (int64_t)n);
+    }
     FR3D_API_END()
 }
 
@@ -557,7 +645,7 @@ int fr3d_get_displacement(fr3d_ctx* ctx, const float* moving, const float* uvw_i
                 L.alpha, _c->iterations, _c->update_lag, _c->a_data, _c->sweep);
         sor_result(_c, _c->state_dtype, L.hp, B, dnat);
         if (L.median)
-            launch(dev, Median5K{dnat, ucur, ucur, p, m, n}, (int64_t)B * 3 * N); // (:517-529)
+            launch(dev, Median5PairK{dnat, ucur, ucur, p, m, n, (n + 1) / 2}, (int64_t)B * 3 * p * m * ((n + 1) / 2)); // (:517-529)
         else
             launch(dev, AddK{ucur, dnat, ucur}, (int64_t)B * 3 * N);
     }
@@ -704,7 +792,7 @@ int fr3d_median5(fr3d_ctx* ctx, const double* src, int nvol, int p, int m, int n
     FR3D_API_BEGIN(ctx)
     FR3D_REQUIRE(src && dst && nvol >= 1 && p > 0 && m > 0 && n > 0, "bad argument");
     FR3D_REQUIRE(src != dst, "fr3d_median5 cannot run in place");
-    launch(_c->dev, Median5K{src, dst, nullptr, p, m, n}, (int64_t)nvol * p * m * n);
+    launch(_c->dev, Median5PairK{src, dst, nullptr, p, m, n, (n + 1) / 2}, (int64_t)nvol * p * m * ((n + 1) / 2));
     FR3D_API_END()
 }
 

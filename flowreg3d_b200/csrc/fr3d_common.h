@@ -327,6 +327,50 @@ FR3D_HD void st4_cg(Vec4<double>* p, const Vec4<double>& v)
 #endif
 }
 
+// ---- block-cooperative launch ---------------------------------------------------------------
+// A "tile kernel" is a functor with  phase(ph, block, tid, nthreads, smem)  executed for
+// ph = 0 .. K::PHASES-1 with a block-wide barrier after every phase; all cross-thread communication
+// goes through `smem` (registers do not survive a phase).  CUDA: one CTA per block, dynamic shared
+// memory.  FR3D_EMU: the phases run as serial loops over the threads of a block.
+#ifndef FR3D_EMU
+template <class K>
+__global__ void __launch_bounds__(256) fr3d_tile_kernel(const K k)
+{
+    extern __shared__ double fr3d_smem[];
+    for (int ph = 0; ph < K::PHASES; ++ph) {
+        k.phase(ph, (int64_t)blockIdx.x, (int)threadIdx.x, (int)blockDim.x, fr3d_smem);
+        __syncthreads();
+    }
+}
+#endif
+
+template <class K>
+void launch_tiles(Device& dev, const K& k, int64_t nblocks, int threads, size_t smem_bytes)
+{
+    if (nblocks <= 0)
+        return;
+#ifdef FR3D_EMU
+    std::vector<double> smem(smem_bytes / sizeof(double) + 1);
+    for (int64_t b = 0; b < nblocks; ++b)
+        for (int ph = 0; ph < K::PHASES; ++ph)
+            for (int t = 0; t < threads; ++t)
+                k.phase(ph, b, t, threads, smem.data());
+#else
+    FR3D_REQUIRE(threads >= 1 && threads <= 256, "tile kernel: %d threads", threads);
+    FR3D_REQUIRE(nblocks < (int64_t)2147483647, "launch too large: %lld blocks", (long long)nblocks);
+    static bool configured = false; // per kernel type
+    if (!configured) {
+        FR3D_CUDA(cudaFuncSetAttribute(fr3d_tile_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    dev.span_begin(typeid(K).name());
+    fr3d_tile_kernel<K><<<(unsigned)nblocks, threads, smem_bytes, dev.stream>>>(k);
+    dev.span_end();
+    FR3D_CUDA(cudaGetLastError());
+#endif
+    dev.launches++;
+}
+
 FR3D_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 FR3D_HD size_t dtype_size(int dt)

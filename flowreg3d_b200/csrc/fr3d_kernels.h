@@ -116,6 +116,52 @@ struct PreZK {
     }
 };
 
+// Z pass, sliding-window form (all channels share the compile-time radius R): one thread walks a
+// whole (b, y, x, c) column keeping the 2R+1 normalised samples in registers, so every raw sample is
+// read and divided once instead of 2R+1 times.  Same summation order as PreZK.
+template <int R>
+struct PreZWinK {
+    const void* raw;
+    int dt;
+    double* out;
+    int B, Z, Y, X, C;
+    PreGauss g;
+    FR3D_HD void operator()(int64_t item) const
+    {
+        const int c = (int)(item % C);
+        item /= C;
+        const int x = (int)(item % X);
+        item /= X;
+        const int y = (int)(item % Y);
+        const int b = (int)(item / Y);
+        const int64_t base = (((int64_t)b * Z * Y + y) * X + x) * C + c;
+        const int64_t zs = (int64_t)Y * X * C;
+        const double lo = g.lo[c], den = g.den[c];
+        double w[R + 1];
+#pragma unroll
+        for (int j = 0; j <= R; ++j)
+            w[j] = g.w[c][0][j];
+        double win[2 * R + 1];
+#pragma unroll
+        for (int j = 0; j <= 2 * R; ++j)
+            win[j] = (load_as_double(raw, dt, base + (int64_t)reflect_idx(j - R, Z) * zs) - lo) / den;
+        double* o = out + (((int64_t)b * C + c) * Z * Y + y) * X + x;
+        const int64_t os = (int64_t)Y * X;
+        for (int z = 0; z < Z; ++z) {
+            double t = win[R] * w[0];
+#pragma unroll
+            for (int j = R; j >= 1; --j)
+                t += (win[R - j] + win[R + j]) * w[j];
+            o[(int64_t)z * os] = t;
+#pragma unroll
+            for (int j = 0; j < 2 * R; ++j)
+                win[j] = win[j + 1];
+            if (z + 1 < Z)
+                win[2 * R] = (load_as_double(raw, dt, base + (int64_t)reflect_idx(z + 1 + R, Z) * zs) - lo) / den;
+        }
+    }
+};
+
 // Y pass: planar float64 -> planar float64; item = (vol, z, y, x).
 struct PreYK {
     const double* in;
@@ -160,6 +206,77 @@ struct PreXK {
         for (int j = r; j >= 1; --j)
             t += (line[reflect_idx(x - j, X)] + line[reflect_idx(x + j, X)]) * w[j];
         out[item] = (float)t;
+    }
+};
+
+// Y and X passes fused through shared memory: a block owns a TY x TX output tile of one (b, z)
+// plane; per channel it stages the (TY+2Ry) x (TX+2Rx) float64 neighbourhood of the Z-pass output
+// (reflect applied on the global coordinates), filters along Y into a second shared buffer (the
+// float64 intermediate scipy would store), filters along X, and finally writes the float32 tile of
+// all channels interleaved.  Summation order per output identical to PreYK / PreXK.
+struct PreYXTileK {
+    static constexpr int PHASES = 3 * FR3D_MAX_CHANNELS + 1;
+    static constexpr int TY = 16, TX = 64;
+    const double* in; // (B, C, Z, Y, X) planar
+    float* out;       // (B, Z, Y, X, C)
+    int B, Z, Y, X, C;
+    int RY, RX;       // halo = max radius over channels
+    PreGauss g;
+    int tiles_y, tiles_x;
+    FR3D_HD void phase(int ph, int64_t blk, int tid, int nthreads, double* sm) const
+    {
+        const int tx = (int)(blk % tiles_x);
+        int64_t q = blk / tiles_x;
+        const int ty = (int)(q % tiles_y);
+        q /= tiles_y; // b*Z + z
+        const int z = (int)(q % Z);
+        const int b = (int)(q / Z);
+        const int y0 = ty * TY, x0 = tx * TX;
+        const int IW = TX + 2 * RX, IH = TY + 2 * RY;
+        double* tin = sm;                       // [IH][IW]
+        double* mid = tin + IH * IW;            // [TY][IW]
+        float* tout = (float*)(mid + TY * IW);  // [TY][TX][C]
+        if (ph == 3 * FR3D_MAX_CHANNELS) {
+            const int ny = Y - y0 < TY ? Y - y0 : TY, nx = X - x0 < TX ? X - x0 : TX;
+            const int rowlen = nx * C;
+            for (int e = tid; e < ny * rowlen; e += nthreads) {
+                const int yy = e / rowlen, r = e - yy * rowlen;
+                out[((((int64_t)b * Z + z) * Y + (y0 + yy)) * X + x0) * C + r] = tout[yy * TX * C + r];
+            }
+            return;
+        }
+        const int c = ph / 3, sub = ph % 3;
+        if (c >= C)
+            return;
+        if (sub == 0) {
+            const double* plane = in + (((int64_t)b * C + c) * Z + z) * Y * X;
+            for (int e = tid; e < IH * IW; e += nthreads) {
+                const int yy = e / IW, xx = e - yy * IW;
+                tin[e] = plane[(int64_t)reflect_idx(y0 - RY + yy, Y) * X + reflect_idx(x0 - RX + xx, X)];
+            }
+        } else if (sub == 1) {
+            const int r = g.r[c][1];
+            const double* w = g.w[c][1];
+            for (int e = tid; e < TY * IW; e += nthreads) {
+                const int yy = e / IW, xx = e - yy * IW;
+                const double* col = tin + (yy + RY) * IW + xx;
+                double t = col[0] * w[0];
+                for (int j = r; j >= 1; --j)
+                    t += (col[-j * IW] + col[j * IW]) * w[j];
+                mid[e] = t;
+            }
+        } else {
+            const int r = g.r[c][2];
+            const double* w = g.w[c][2];
+            for (int e = tid; e < TY * TX; e += nthreads) {
+                const int yy = e / TX, xx = e - yy * TX;
+                const double* row = mid + yy * IW + xx + RX;
+                double t = row[0] * w[0];
+                for (int j = r; j >= 1; --j)
+                    t += (row[-j] + row[j]) * w[j];
+                tout[(yy * TX + xx) * C + c] = (float)t;
+            }
+        }
     }
 };
 
@@ -275,6 +392,201 @@ struct SplineXK {
         spline_line(
             X, [=](int bb) { return 6.0 * base[clampi(bb, 0, XX - 1) + 1]; },
             [=](int bb, double v) { base[bb + 1] = v; }, [=](int bb) { return base[bb + 1]; });
+    }
+};
+
+// Y / X passes, shared-memory tiled.  A block stages TL whole lines in shared memory (coalesced
+// loads), filters them in place and writes them back: one global read and one write per
+// coefficient instead of two each, and coalesced for the X pass too.  Each line is cut into NSEG
+// segments handled by different threads: the recursions  c+[b] = x[b] + z c+[b-1]  and
+// c[b] = z (c[b+1] - c+[b])  forget their start value as |z|^k (|z| = 0.268), so a segment that
+// starts from 0 a warm-up length W = 40 samples early reproduces the sequential result to
+// |z|^40 ~ 1e-23 relative, far below float64 rounding; segments near the line ends use scipy's
+// exact boundary initialisation.  Same recurrences, constants and operation order as spline_line.
+struct SplineTileK {
+    static constexpr int PHASES = 6;
+    double* coef;
+    int N;          // samples per line; N+3 coefficient slots (b = -1 .. N+1 at slot b+1)
+    int TL, NSEG, W;
+    int64_t nlines;
+    // global address of slot p of line l: first + (l / per_group)*group_stride + (l % per_group)*line_stride + p*elem_stride
+    int64_t per_group, group_stride, line_stride, elem_stride, first;
+    int line_fast;  // 1: consecutive threads load consecutive lines (Y pass), 0: consecutive slots (X pass)
+
+    FR3D_HD int64_t gaddr(int64_t l, int p) const
+    {
+        return first + (l / per_group) * group_stride + (l % per_group) * line_stride + (int64_t)p * elem_stride;
+    }
+    FR3D_HD int sidx(int line, int p) const { return line_fast ? p * TL + line : line * (N + 3) + p; }
+    FR3D_HD int seglen() const { return (N + 2 * FR3D_SPLINE_PAD + NSEG - 1) / NSEG; }
+
+    FR3D_HD void phase(int ph, int64_t blk, int tid, int nthreads, double* sm) const
+    {
+        const int L3 = N + 3;
+        const int64_t l0 = blk * TL;
+        int nl = (int)(nlines - l0 < TL ? nlines - l0 : TL);
+        double* prevs = sm + (size_t)TL * L3;              // [TL][NSEG]
+        double* tails = prevs + (size_t)TL * NSEG;         // [TL][PAD]
+        if (ph == 0 || ph == 5) {
+            // staging copy global <-> shared: no per-element division, eight independent accesses in
+            // flight per thread
+            if (line_fast) {
+                // TL is a power of two: element e -> (slot p = e / TL, line = e % TL); consecutive
+                // threads touch consecutive lines (contiguous in memory)
+                int sh = 0;
+                while ((1 << sh) < TL)
+                    ++sh;
+                const int line = tid & (TL - 1);
+                if (line >= nl)
+                    return;
+                double* gp = coef + gaddr(l0 + line, 0);
+                const int pstep = nthreads >> sh;
+                for (int p0 = tid >> sh; p0 < L3; p0 += 8 * pstep) {
+                    double v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int p = p0 + u * pstep;
+                        if (p < L3)
+                            v[u] = ph == 0 ? gp[(int64_t)p * elem_stride] : sm[p * TL + line];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int p = p0 + u * pstep;
+                        if (p < L3) {
+                            if (ph == 0)
+                                sm[p * TL + line] = v[u];
+                            else
+                                gp[(int64_t)p * elem_stride] = v[u];
+                        }
+                    }
+                }
+            } else {
+                // consecutive lanes = consecutive slots of one line, warps stride over lines
+                const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
+                for (int line = warp; line < nl; line += nwarps) {
+                    double* gp = coef + gaddr(l0 + line, 0);
+                    double* sp = sm + line * L3;
+                    for (int p0 = lane; p0 < L3; p0 += 8 * 32) {
+                        double v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int p = p0 + u * 32;
+                            if (p < L3)
+                                v[u] = ph == 0 ? gp[(int64_t)p * elem_stride] : sp[p];
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int p = p0 + u * 32;
+                            if (p < L3) {
+                                if (ph == 0)
+                                    sp[p] = v[u];
+                                else
+                                    gp[(int64_t)p * elem_stride] = v[u];
+                            }
+                        }
+                    }
+                }
+            }
+            return;
+        }
+        if (tid >= TL * NSEG)
+            return;
+        const int line = tid % TL, seg = tid / TL;
+        if (line >= nl)
+            return;
+        const double z = FR3D_SPLINE_POLE;
+        const int blo = -FR3D_SPLINE_PAD, bhi = N + FR3D_SPLINE_PAD - 1;
+        const int sl = seglen();
+        const int bs = blo + seg * sl;
+        int be = bs + sl - 1;
+        be = be > bhi ? bhi : be;
+        if (bs > bhi)
+            return;
+        const int NN = N;
+        auto S = [&](int b) -> double& { return sm[sidx(line, b + 1)]; };
+        auto get = [&](int b) { return 6.0 * sm[sidx(line, clampi(b, 0, NN - 1) + 1)]; };
+        double& slot = prevs[line * NSEG + seg];
+        double* tail = tails + line * FR3D_SPLINE_PAD;
+        if (ph == 1) {
+            // value of c+ just before the segment's first sample
+            double prev;
+            int b;
+            if (seg == 0 || bs - W <= blo) {
+                const int len = N + 2 * FR3D_SPLINE_PAD;
+                const double zn = pow(z, (double)len);
+                const double c0 = get(blo);
+                double acc = c0 + zn * get(bhi);
+                double zi = z;
+                const int K = len - 1 < 48 ? len - 1 : 48;
+                for (int i = 1; i <= K; ++i) {
+                    acc += zi * (get(i - FR3D_SPLINE_PAD) + zn * get(bhi - i));
+                    zi *= z;
+                }
+                acc *= z / (1.0 - zn * zn);
+                acc += c0;
+                prev = acc; // c+[blo]
+                b = blo + 1;
+            } else {
+                prev = 0.0;
+                b = bs - W;
+            }
+            for (; b < bs; ++b)
+                prev = get(b) + z * prev;
+            slot = prev;
+            if (be == bhi)
+                tail[FR3D_SPLINE_PAD - 1] = get(N - 1); // x[N-1], needed after slot N is overwritten
+            return;
+        }
+        if (ph == 2) {
+            double prev = slot;
+            const double xhi = tail[FR3D_SPLINE_PAD - 1];
+            for (int b = (bs > blo + 1 ? bs : blo + 1); b <= be; ++b) {
+                const double cur = (b >= N ? xhi : get(b)) + z * prev;
+                if (b >= -1) {
+                    if (b <= N + 1)
+                        S(b) = cur;
+                    else
+                        tail[b - N - 2] = cur;
+                }
+                prev = cur;
+            }
+            if (be == bhi)
+                tail[FR3D_SPLINE_PAD - 2] = prev; // c+[bhi] (bhi - N - 2 = PAD - 3 is the last tail slot used above)
+            return;
+        }
+        // c+ at position b after phase 2 (b in [-1, bhi - 1])
+        auto cplus = [&](int b) { return b > N + 1 ? tail[b - N - 2] : S(b); };
+        if (ph == 3) {
+            // value of c just above the segment's last sample
+            if (be < -1)
+                return;
+            double cm;
+            int b;
+            if (be == bhi || be + W >= N + 1) {
+                cm = tails[line * FR3D_SPLINE_PAD + FR3D_SPLINE_PAD - 2] * (z / (z - 1.0)); // c[bhi]
+                b = bhi - 1;
+            } else {
+                cm = 0.0;
+                b = be + W;
+            }
+            for (; b > be; --b)
+                cm = z * (cm - cplus(b));
+            slot = cm;
+            return;
+        }
+        if (ph == 4) {
+            if (be < -1)
+                return;
+            double cm = slot;
+            int b = be < bhi - 1 ? be : bhi - 1;
+            const int stop = bs > -1 ? bs : -1;
+            for (; b >= stop; --b) {
+                cm = z * (cm - cplus(b));
+                if (b <= N + 1)
+                    S(b) = cm;
+            }
+            return;
+        }
     }
 };
 
@@ -810,6 +1122,158 @@ struct Median5K {
             res = cur;
         }
         dst[item] = add ? add[item] + res : res;
+    }
+};
+
+// Pair version: one thread produces the medians of two x-adjacent voxels (x = 2*ip, 2*ip + 1).
+// Their windows share 4 of 5 x-columns = 100 samples.  A shared sample with fewer than 37 or more
+// than 62 shared samples below it cannot have exactly 62 of the 125 window samples below it in
+// either window, so the 37 smallest and 37 largest shared keys are discarded ONCE (forgetful
+// min/max elimination, working set 64 -> 28); each output is then the median (rank 25 of 51) of the
+// 26 surviving shared keys and its own 25 keys.  ~3.7k min/max operations per output instead of 6.2k.
+template <int N>
+struct CorePrune {
+    static FR3D_HD void run(float* a, const float* rest)
+    {
+        ForgetStep<N>::minmax(a);
+        a[0] = rest[64 - N]; // the discarded minimum's slot takes the next unseen key; a[N-1] falls off
+        CorePrune<N - 1>::run(a, rest);
+    }
+};
+template <>
+struct CorePrune<28> {
+    static FR3D_HD void run(float* a, const float*) { ForgetStep<28>::minmax(a); } // survivors: a[1..26]
+};
+template <int N>
+struct Forget27 { // median of 51 = 27 in the working set + 24 in rest
+    static FR3D_HD float run(float* a, const float* rest)
+    {
+        ForgetStep<N>::minmax(a);
+        a[0] = rest[27 - N];
+        return Forget27<N - 1>::run(a, rest);
+    }
+};
+template <>
+struct Forget27<3> {
+    static FR3D_HD float run(float* a, const float*)
+    {
+        const float lo = fminf(a[0], a[1]), hi = fmaxf(a[0], a[1]);
+        return fmaxf(lo, fminf(hi, a[2]));
+    }
+};
+
+struct Median5PairK {
+    const double* src; // (nvol, p, m, n)
+    double* dst;       // (nvol, p, m, n): dst = (add ? add : 0) + median
+    const double* add; // optional (nvol, p, m, n)
+    int p, m, n, npair; // npair = (n + 1) / 2
+    // float64 value of rank 62 among the window samples whose float32 key equals med
+    FR3D_HD double recover(const double* f, const int* zi, const int* yi, int i, float med) const
+    {
+        int xi[5];
+#pragma unroll
+        for (int d = 0; d < 5; ++d)
+            xi[d] = mirror_idx(i + d - 2, n);
+        int less = 0, eq = 0;
+        double tmin = 0.0, tmax = 0.0;
+        for (int t = 0; t < 125; ++t) {
+            const double v = f[((int64_t)zi[t / 25] * m + yi[(t / 5) % 5]) * n + xi[t % 5]];
+            const float key = (float)v;
+            less += key < med;
+            if (key == med) {
+                tmin = (eq == 0 || v < tmin) ? v : tmin;
+                tmax = (eq == 0 || v > tmax) ? v : tmax;
+                ++eq;
+            }
+        }
+        if (tmin == tmax)
+            return tmin;
+        int want = 62 - less;
+        double cur = tmin;
+        for (;;) {
+            int mult = 0;
+            double next = tmax;
+            for (int t = 0; t < 125; ++t) {
+                const double v = f[((int64_t)zi[t / 25] * m + yi[(t / 5) % 5]) * n + xi[t % 5]];
+                if ((float)v != med)
+                    continue;
+                mult += v == cur;
+                if (v > cur && v < next)
+                    next = v;
+            }
+            if (want < mult || cur == tmax)
+                break;
+            want -= mult;
+            cur = next;
+        }
+        return cur;
+    }
+    FR3D_HD void operator()(int64_t item) const
+    {
+        const int ip = (int)(item % npair);
+        int64_t q = item / npair;
+        const int j = (int)(q % m);
+        q /= m;
+        const int k = (int)(q % p);
+        const int64_t vol = q / p;
+        const int64_t N = (int64_t)p * m * n;
+        const double* f = src + vol * N;
+        const int i0 = 2 * ip;
+        const bool two = i0 + 1 < n;
+        int zi[5], yi[5], xs[6]; // xs: mirrored x of columns i0-2 .. i0+3
+#pragma unroll
+        for (int d = 0; d < 5; ++d) {
+            zi[d] = mirror_idx(k + d - 2, p);
+            yi[d] = mirror_idx(j + d - 2, m);
+        }
+#pragma unroll
+        for (int d = 0; d < 6; ++d)
+            xs[d] = mirror_idx(i0 + d - 2 < n + 2 ? i0 + d - 2 : n + 1, n); // (clamped only for the unused odd tail)
+        // shared core: columns xs[1..4] x 25 (z,y) positions; key t -> (zy = t / 4, col = 1 + t % 4)
+        float a[64], rest[36];
+#pragma unroll
+        for (int t = 0; t < 100; ++t) {
+            const int zy = t >> 2;
+            const float key = (float)f[((int64_t)zi[zy / 5] * m + yi[zy % 5]) * n + xs[1 + (t & 3)]];
+            if (t < 64)
+                a[t] = key;
+            else
+                rest[t - 64] = key;
+        }
+        CorePrune<64>::run(a, rest);
+        // output A (voxel i0): survivors a[1..26] + own column xs[0]
+        float wa[27], own[24];
+#pragma unroll
+        for (int t = 0; t < 26; ++t)
+            wa[t] = a[1 + t];
+#pragma unroll
+        for (int t = 0; t < 25; ++t) {
+            const float key = (float)f[((int64_t)zi[t / 5] * m + yi[t % 5]) * n + xs[0]];
+            if (t == 0)
+                wa[26] = key;
+            else
+                own[t - 1] = key;
+        }
+        const float medA = Forget27<27>::run(wa, own);
+        const int64_t oA = vol * N + ((int64_t)k * m + j) * n + i0;
+        const double rA = recover(f, zi, yi, i0, medA);
+        dst[oA] = add ? add[oA] + rA : rA;
+        if (!two)
+            return;
+#pragma unroll
+        for (int t = 0; t < 26; ++t)
+            wa[t] = a[1 + t];
+#pragma unroll
+        for (int t = 0; t < 25; ++t) {
+            const float key = (float)f[((int64_t)zi[t / 5] * m + yi[t % 5]) * n + xs[5]];
+            if (t == 0)
+                wa[26] = key;
+            else
+                own[t - 1] = key;
+        }
+        const float medB = Forget27<27>::run(wa, own);
+        const double rB = recover(f, zi, yi, i0 + 1, medB);
+        dst[oA + 1] = add ? add[oA + 1] + rB : rB;
     }
 };
 

@@ -79,6 +79,23 @@ def test_warp_out_of_volume_and_integer_input(backend, golden):
     assert np.array_equal(one, g["linear"][..., 0])
 
 
+def test_warp_long_lines_segmented_prefilter(backend):
+    """Lines long enough for the tiled prefilter to cut them into warm-started segments (Y: 3, X: 8
+    segments) -- same bit-level agreement with scipy as the short golden case."""
+    import flowreg3d_b200 as F
+    from tests_inputs import smooth_flow
+    rng = np.random.default_rng(11)
+    shp = (5, 150, 420)
+    f2 = rng.random(shp + (2,))
+    f2[:, :, :3] *= 50.0                                       # strong edge at a line start
+    f1 = rng.random(shp + (2,))
+    g = smooth_flow(shp, 5, 3.0, 4.0).astype(np.float64)
+    out = F.imregister_wrapper(f2, g[..., 0], g[..., 1], g[..., 2], f1, "cubic")
+    ref = O.imregister_wrapper(f2, g[..., 0], g[..., 1], g[..., 2], f1, "cubic")
+    d = ulp_diff(out, ref)
+    assert d.max() <= 1 and (d > 0).mean() <= 1e-4, (d.max(), (d > 0).mean())
+
+
 def test_motion_tensor(backend, golden):
     from flowreg3d_b200 import core
     g = golden("motion_tensor")
