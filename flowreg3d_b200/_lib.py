@@ -17,6 +17,7 @@ MAX_CHANNELS = 4
 ABI_VERSION = 2
 
 F32, F64, U8, U16, I16, I32 = range(6)
+OPT_SOR_CTAS_PER_SM = 1
 _DTYPES = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.uint8): U8,
            np.dtype(np.uint16): U16, np.dtype(np.int16): I16, np.dtype(np.int32): I32}
 
@@ -83,6 +84,7 @@ def load():
         "fr3d_synchronize": (ci, [vp]),
         "fr3d_launch_count": (i64, [vp]),
         "fr3d_device_bytes": (i64, [vp]),
+        "fr3d_set_option": (ci, [vp, ci, i64]),
         "fr3d_preprocess": (ci, [vp, vp, ci, ci, vp, vp, vp]),
         "fr3d_set_reference": (ci, [vp, vp, vp, vp]),
         "fr3d_get_displacement": (ci, [vp, vp, vp, ci, vp, ci]),
@@ -109,7 +111,7 @@ def load():
 
 EXPORTED_SYMBOLS = [
     "fr3d_abi_version", "fr3d_create", "fr3d_destroy", "fr3d_last_error", "fr3d_synchronize",
-    "fr3d_launch_count", "fr3d_device_bytes", "fr3d_preprocess", "fr3d_set_reference",
+    "fr3d_launch_count", "fr3d_device_bytes", "fr3d_set_option", "fr3d_preprocess", "fr3d_set_reference",
     "fr3d_get_displacement", "fr3d_compensate", "fr3d_resize3d", "fr3d_warp", "fr3d_motion_tensor",
     "fr3d_sor_level", "fr3d_median5", "fr3d_mean_frames", "fr3d_profile_enable",
     "fr3d_profile_report", "fr3d_fill_resize_table",

@@ -26,7 +26,7 @@ import numpy as np
 import torch
 
 from . import device as dev
-from .core import Registration
+from .core import Registration, SplitRegistration
 from .options import OFOptions
 from .plan import FlowParams
 
@@ -70,7 +70,7 @@ class SequenceCorrector:
     """Stateful batch processor: owns the Registration, the fixed volume and the w_init chain."""
 
     def __init__(self, reference_raw: np.ndarray, options, max_batch: Optional[int] = None,
-                 device: Optional[torch.device] = None, group=None):
+                 device: Optional[torch.device] = None, group=None, streams: int = 1):
         if bool(getattr(options, "cc_initialization", False)):
             raise NotImplementedError("cc_initialization is not implemented on the B200 path")
         if bool(getattr(options, "update_reference", False)):
@@ -92,9 +92,11 @@ class SequenceCorrector:
         if fp.a_smooth != 1.0:
             raise NotImplementedError("a_smooth != 1.0 (nonlinear smoothness term) is not implemented on the B200 path")
         mb = int(max_batch or options.buffer_size)
-        self.reg = Registration(self.shape, Cn, fp, max_batch=mb,
-                                interpolation_method=getattr(options, "interpolation_method", "cubic"),
-                                sigma=options.sigma, device=device)
+        kw = dict(interpolation_method=getattr(options, "interpolation_method", "cubic"), sigma=options.sigma)
+        if int(streams) > 1 and mb > 1:
+            self.reg = SplitRegistration(self.shape, Cn, fp, max_batch=mb, n_streams=int(streams), device=device, **kw)
+        else:
+            self.reg = Registration(self.shape, Cn, fp, max_batch=mb, device=device, **kw)
         self.device = self.reg.device
         # weights (compensate_recording_3D.py:211-224)
         wvec = [options.get_weight_at(c, Cn) for c in range(Cn)]
@@ -166,7 +168,10 @@ class SequenceCorrector:
         return reg, flows
 
     def close(self):
-        self.reg.ctx.close()
+        if isinstance(self.reg, SplitRegistration):
+            self.reg.close()
+        else:
+            self.reg.ctx.close()
 
 
 def compensate_arr_3D(c1: np.ndarray, c_ref: np.ndarray, options=None,

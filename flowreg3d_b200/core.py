@@ -10,7 +10,7 @@ context they are built on.  All per-voxel work happens in libfr3d's CUDA kernels
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Sequence
+from typing import List, Optional, Sequence
 
 import numpy as np
 import torch
@@ -260,6 +260,130 @@ class Registration:
     @staticmethod
     def _code(t: torch.Tensor) -> int:
         return _lib.dtype_code(str(t.dtype).replace("torch.", ""))
+
+
+class SplitRegistration:
+    """Registration whose batch is cut into `n_streams` contiguous parts, each owned by its own
+    fr3d context on its own CUDA stream.  Frames are independent in every stage, so the parts only
+    meet at the fork (inputs ready) and the join (outputs ready) of each call.  Purpose: the
+    persistent wavefront solver of one part spends a third of its time in grid barriers and in
+    ramp-up / ramp-down waves; kernels of the other part (ALU-bound median, fp64-bound warp, or its
+    own solver) fill those holes.  Each solver launch claims one CTA per SM so that two can be
+    resident together."""
+
+    def __init__(self, shape, n_channels: int, params: FlowParams, max_batch: int = 2, n_streams: int = 2,
+                 device: Optional[torch.device] = None, **kw):
+        self.device = device if device is not None else dev.default_device()
+        self.n = max(1, min(int(n_streams), int(max_batch)))
+        self.max_batch = int(max_batch)
+        per = -(-self.max_batch // self.n)
+        self.parts: List[Registration] = []
+        self.streams = []
+        for _ in range(self.n):
+            if self.device.type == "cuda":
+                st = torch.cuda.Stream(self.device)
+                with torch.cuda.stream(st):
+                    r = Registration(shape, n_channels, params, max_batch=per, device=self.device, **kw)
+            else:
+                st = None
+                r = Registration(shape, n_channels, params, max_batch=per, device=self.device, **kw)
+            _check(r.ctx.h, r.ctx.lib.fr3d_set_option(r.ctx.h, _lib.OPT_SOR_CTAS_PER_SM, 1))
+            self.parts.append(r)
+            self.streams.append(st)
+        first = self.parts[0]
+        self.shape, self.C, self.plan, self.ctx = first.shape, first.C, first.plan, first.ctx
+
+    # -- fork / join --------------------------------------------------------------------
+    def _bounds(self, B):
+        per = -(-B // self.n)
+        return [(i * per, min(B, (i + 1) * per)) for i in range(self.n) if i * per < B]
+
+    def _run(self, B, fn):
+        """fn(part, lo, hi) on every part's stream; joins back into the caller's stream."""
+        cur = torch.cuda.current_stream(self.device) if self.device.type == "cuda" else None
+        used = []
+        for i, (lo, hi) in enumerate(self._bounds(B)):
+            st = self.streams[i]
+            if st is None:
+                fn(self.parts[i], lo, hi)
+                continue
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                fn(self.parts[i], lo, hi)
+            used.append(st)
+        for st in used:
+            cur.wait_stream(st)
+
+    def _all(self, fn):
+        cur = torch.cuda.current_stream(self.device) if self.device.type == "cuda" else None
+        for r, st in zip(self.parts, self.streams):
+            if st is None:
+                fn(r)
+                continue
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                fn(r)
+            cur.wait_stream(st)
+
+    # -- Registration interface ---------------------------------------------------------
+    def set_reference(self, ref_proc, weight=None, ref_raw=None):
+        self._all(lambda r: r.set_reference(ref_proc, weight=weight, ref_raw=ref_raw))
+
+    def _as_dev(self, a, dtype, shape):
+        return self.parts[0]._as_dev(a, dtype, shape)
+
+    def preprocess(self, raw, lo, den, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        raw_t = self._as_dev(raw, None, None)
+        if raw_t.dim() == 4:
+            raw_t = raw_t[None]
+        B = raw_t.shape[0]
+        if out is None:
+            out = dev.empty((B,) + self.shape + (self.C,), np.float32, self.device)
+        self._run(B, lambda r, a, b: r.preprocess(raw_t[a:b], lo, den, out=out[a:b]))
+        return out
+
+    def get_displacement(self, moving_proc, uvw=None, out_dtype=np.float32,
+                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        mv = self._as_dev(moving_proc, np.float32, None)
+        if mv.dim() == 4:
+            mv = mv[None]
+        B = mv.shape[0]
+        uv = None if uvw is None else self._as_dev(uvw, np.float32, self.shape + (3,))
+        if out is None:
+            out = dev.empty((B,) + self.shape + (3,), out_dtype, self.device)
+        self._run(B, lambda r, a, b: r.get_displacement(mv[a:b], uvw=uv, out=out[a:b]))
+        return out
+
+    def compensate(self, raw, flow, ref_raw=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        raw_t = self._as_dev(raw, None, None)
+        if raw_t.dim() == 4:
+            raw_t = raw_t[None]
+        B = raw_t.shape[0]
+        fl = self._as_dev(flow, np.float32, (B,) + self.shape + (3,))
+        rr = None if ref_raw is None else self._as_dev(ref_raw, None, self.shape + (self.C,))
+        if out is None:
+            out = dev.empty((B,) + self.shape + (self.C,), np.float32, self.device)
+        self._run(B, lambda r, a, b: r.compensate(raw_t[a:b], fl[a:b], ref_raw=rr, out=out[a:b]))
+        return out
+
+    def mean_frames(self, frames: torch.Tensor) -> torch.Tensor:
+        res = []
+        self._run(1, lambda r, a, b: res.append(r.mean_frames(frames)))
+        return res[0]
+
+    def sync(self):
+        for r in self.parts:
+            r.sync()
+        if self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def close(self):
+        for r in self.parts:
+            r.ctx.close()
+
+    @property
+    def launches(self) -> int:
+        return sum(r.ctx.launches for r in self.parts)
 
 
 # --------------------------------------------------------------------------------------------

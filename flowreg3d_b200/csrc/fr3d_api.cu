@@ -130,19 +130,27 @@ template <class SrcT, class DstT>
 static void resize_pass(fr3d_ctx* c, const SrcT* src, const int64_t ss[5], DstT* dst, const int64_t ds[5],
                         const int64_t n[5], int r, const DevTable& t)
 {
-    ResizePassK<SrcT, DstT> k;
-    k.src = src;
-    k.dst = dst;
-    for (int q = 0; q < 5; ++q) {
-        k.n[q] = n[q];
-        k.ss[q] = ss[q];
-        k.ds[q] = ds[q];
+    FR3D_REQUIRE(r != 0, "resize_pass: axis 0 is the batch axis");
+    const int64_t inner = n[1] * n[2] * n[3] * n[4];
+    FR3D_REQUIRE(inner > 0 && inner < (1LL << 31), "resize_pass: one batch entry has %lld outputs", (long long)inner);
+    // items of a launch are decoded with 32-bit fast division: split the batch axis if needed
+    const int64_t per = ((1LL << 31) / inner) < 1 ? 1 : ((1LL << 31) / inner);
+    for (int64_t b0 = 0; b0 < n[0]; b0 += per) {
+        const int64_t nb = n[0] - b0 < per ? n[0] - b0 : per;
+        ResizePassK<SrcT, DstT> k;
+        k.src = src + b0 * ss[0];
+        k.dst = dst + b0 * ds[0];
+        for (int q = 0; q < 5; ++q) {
+            k.ss[q] = ss[q];
+            k.ds[q] = ds[q];
+            k.fd[q] = FastDiv((uint32_t)n[q]);
+        }
+        k.r = r;
+        k.P = t.P;
+        k.idx = t.idx.p;
+        k.wt = t.wt.p;
+        launch(c->dev, k, nb * inner);
     }
-    k.r = r;
-    k.P = t.P;
-    k.idx = t.idx.p;
-    k.wt = t.wt.p;
-    launch(c->dev, k, n[0] * n[1] * n[2] * n[3] * n[4]);
 }
 
 // Separable resize of n0*n1 volumes (D,H,W) -> (od,oh,ow): X, then Y, then Z pass
@@ -248,7 +256,7 @@ static void check_dtype(int dt)
 }
 
 // Frames per warp work item: enough items to balance the busiest wave over the grid.
-static int sor_frame_group(int B) { return B >= 8 ? 4 : (B >= 2 ? 2 : 1); }
+static int sor_frame_group(int B) { return B >= 2 ? 2 : 1; }
 
 // Level solve in solver storage: assembles J (when f1/f2 are given; otherwise Jpre is used as is), the
 // Laplacian term L and zero increments, then runs the wavefront solver.  Result in c->d.
@@ -466,6 +474,19 @@ int fr3d_synchronize(fr3d_ctx* ctx)
     FR3D_API_END()
 }
 
+int fr3d_set_option(fr3d_ctx* ctx, int option, int64_t value)
+{
+    FR3D_API_BEGIN(ctx)
+    switch (option) {
+    case FR3D_OPT_SOR_CTAS_PER_SM:
+        FR3D_REQUIRE(value >= 0 && value <= 32, "FR3D_OPT_SOR_CTAS_PER_SM: %lld", (long long)value);
+        _c->dev.sor_ctas_per_sm = (int)value;
+        break;
+    default: FR3D_THROW(FR3D_ERR_ARG, "unknown option %d", option);
+    }
+    FR3D_API_END()
+}
+
 int fr3d_preprocess(fr3d_ctx* ctx, const void* raw, int dtype, int B, const double* lo, const double* den,
                     float* out)
 {
@@ -645,7 +666,7 @@ int fr3d_get_displacement(fr3d_ctx* ctx, const float* moving, const float* uvw_i
                 L.alpha, _c->iterations, _c->update_lag, _c->a_data, _c->sweep);
         sor_result(_c, _c->state_dtype, L.hp, B, dnat);
         if (L.median)
-            launch(dev, Median5PairK{dnat, ucur, ucur, p, m, n, (n + 1) / 2}, (int64_t)B * 3 * p * m * ((n + 1) / 2)); // (:517-529)
+            launch_occ2(dev, Median5PairK{dnat, ucur, ucur, p, m, n, (n + 1) / 2}, (int64_t)B * 3 * p * m * ((n + 1) / 2)); // (:517-529)
         else
             launch(dev, AddK{ucur, dnat, ucur}, (int64_t)B * 3 * N);
     }
@@ -792,7 +813,7 @@ int fr3d_median5(fr3d_ctx* ctx, const double* src, int nvol, int p, int m, int n
     FR3D_API_BEGIN(ctx)
     FR3D_REQUIRE(src && dst && nvol >= 1 && p > 0 && m > 0 && n > 0, "bad argument");
     FR3D_REQUIRE(src != dst, "fr3d_median5 cannot run in place");
-    launch(_c->dev, Median5PairK{src, dst, nullptr, p, m, n, (n + 1) / 2}, (int64_t)nvol * p * m * ((n + 1) / 2));
+    launch_occ2(_c->dev, Median5PairK{src, dst, nullptr, p, m, n, (n + 1) / 2}, (int64_t)nvol * p * m * ((n + 1) / 2));
     FR3D_API_END()
 }
 

@@ -78,6 +78,7 @@ struct Device {
     int64_t launches = 0;
     int64_t bytes = 0;
     int sm_count = 1;
+    int sor_ctas_per_sm = 0; // 0 = as many as fit
 
     // Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline
     // figures).  Off by default; when on, every launch is bracketed by two event records.
@@ -251,6 +252,70 @@ __global__ void __launch_bounds__(256) fr3d_kernel(const K k, const int64_t n)
         k(i);
 }
 #endif
+
+#ifndef FR3D_EMU
+// Variant that asks ptxas for two resident CTAs per SM (<= 128 registers per thread).
+template <class K>
+__global__ void __launch_bounds__(256, 2) fr3d_kernel_occ2(const K k, const int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        k(i);
+}
+#endif
+
+template <class K>
+void launch_occ2(Device& dev, const K& k, int64_t n)
+{
+    if (n <= 0)
+        return;
+#ifdef FR3D_EMU
+    for (int64_t i = 0; i < n; ++i)
+        k(i);
+#else
+    const int threads = 256;
+    const int64_t blocks = (n + threads - 1) / threads;
+    FR3D_REQUIRE(blocks < (int64_t)2147483647, "launch too large: %lld items", (long long)n);
+    dev.span_begin(typeid(K).name());
+    fr3d_kernel_occ2<K><<<(unsigned)blocks, threads, 0, dev.stream>>>(k, n);
+    dev.span_end();
+    FR3D_CUDA(cudaGetLastError());
+#endif
+    dev.launches++;
+}
+
+// Division of a 32-bit unsigned value by a runtime constant through multiply-high + shift
+// (Granlund-Montgomery); exact for every 32-bit n.  Built on the host.
+struct FastDiv {
+    uint32_t d, mul, sh;
+    FastDiv() : d(1), mul(0), sh(0) {}
+    explicit FastDiv(uint32_t d_) : d(d_), mul(0), sh(0)
+    {
+        if (d <= 1)
+            return;
+        uint32_t l = 0;
+        while (l < 32 && (1ull << l) < d)
+            ++l;
+        sh = l - 1;
+        mul = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+    }
+    FR3D_HD uint32_t div(uint32_t n) const
+    {
+        if (d <= 1)
+            return n;
+#ifdef __CUDA_ARCH__
+        const uint32_t t = __umulhi(mul, n);
+#else
+        const uint32_t t = (uint32_t)(((uint64_t)mul * n) >> 32);
+#endif
+        return (t + ((n - t) >> 1)) >> sh;
+    }
+    FR3D_HD void divmod(uint32_t n, uint32_t& q, uint32_t& r) const
+    {
+        q = div(n);
+        r = n - q * d;
+    }
+};
 
 // One logical thread per item.
 template <class K>

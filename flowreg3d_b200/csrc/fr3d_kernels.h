@@ -39,33 +39,33 @@ template <class SrcT, class DstT>
 struct ResizePassK {
     const SrcT* src;
     DstT* dst;
-    int64_t n[5], ss[5], ds[5];
+    int64_t ss[5], ds[5];
+    FastDiv fd[5]; // divisors n[1..4] at fd[1..4] (item < 2^32)
     int r, P;
     const int32_t* idx;
     const float* wt;
     FR3D_HD void operator()(int64_t item) const
     {
-        int64_t i[5];
-        i[4] = item % n[4];
-        item /= n[4];
-        i[3] = item % n[3];
-        item /= n[3];
-        i[2] = item % n[2];
-        item /= n[2];
-        i[1] = item % n[1];
-        i[0] = item / n[1];
+        uint32_t i[5];
+        uint32_t e = (uint32_t)item;
+        fd[4].divmod(e, e, i[4]);
+        fd[3].divmod(e, e, i[3]);
+        fd[2].divmod(e, e, i[2]);
+        fd[1].divmod(e, i[0], i[1]);
         int64_t so = 0, dof = 0;
+#pragma unroll
         for (int d = 0; d < 5; ++d) {
-            dof += i[d] * ds[d];
+            dof += (int64_t)i[d] * ds[d];
             if (d != r)
-                so += i[d] * ss[d];
+                so += (int64_t)i[d] * ss[d];
         }
-        const int32_t* ix = idx + i[r] * P;
-        const float* w = wt + i[r] * P;
+        const int32_t* ix = idx + (int64_t)i[r] * P;
+        const float* w = wt + (int64_t)i[r] * P;
         const int64_t sr = ss[r];
+        const SrcT* sp = src + so;
         double acc = 0.0;
         for (int p = 0; p < P; ++p) {
-            const float a = (float)src[so + (int64_t)ix[p] * sr];
+            const float a = (float)sp[(int64_t)ix[p] * sr];
             const float prod = a * w[p];
             acc += (double)prod;
         }
@@ -1131,31 +1131,50 @@ struct Median5K {
 // either window, so the 37 smallest and 37 largest shared keys are discarded ONCE (forgetful
 // min/max elimination, working set 64 -> 28); each output is then the median (rank 25 of 51) of the
 // 26 surviving shared keys and its own 25 keys.  ~3.7k min/max operations per output instead of 6.2k.
+// shared-core keys 64..99 and the own-column keys are fetched on demand (they are L1 hits) so that only
+// the 64-entry working set lives in registers
+struct MedianSrc {
+    const double* f;
+    const int* zi;
+    const int* yi;
+    const int* xs;
+    int m, n;
+    template <int T>
+    FR3D_HD float core() const // shared key T in [0, 100): (zy = T / 4, column xs[1 + T % 4])
+    {
+        return (float)f[((int64_t)zi[(T >> 2) / 5] * m + yi[(T >> 2) % 5]) * n + xs[1 + (T & 3)]];
+    }
+    template <int T>
+    FR3D_HD float own(int xo) const // own key T in [0, 25) of the column with mirrored index xo
+    {
+        return (float)f[((int64_t)zi[T / 5] * m + yi[T % 5]) * n + xo];
+    }
+};
 template <int N>
 struct CorePrune {
-    static FR3D_HD void run(float* a, const float* rest)
+    static FR3D_HD void run(float* a, const MedianSrc& s)
     {
         ForgetStep<N>::minmax(a);
-        a[0] = rest[64 - N]; // the discarded minimum's slot takes the next unseen key; a[N-1] falls off
-        CorePrune<N - 1>::run(a, rest);
+        a[0] = s.template core<64 + (64 - N)>(); // the discarded minimum's slot takes the next unseen key
+        CorePrune<N - 1>::run(a, s);
     }
 };
 template <>
 struct CorePrune<28> {
-    static FR3D_HD void run(float* a, const float*) { ForgetStep<28>::minmax(a); } // survivors: a[1..26]
+    static FR3D_HD void run(float* a, const MedianSrc&) { ForgetStep<28>::minmax(a); } // survivors: a[1..26]
 };
 template <int N>
-struct Forget27 { // median of 51 = 27 in the working set + 24 in rest
-    static FR3D_HD float run(float* a, const float* rest)
+struct Forget27 { // median of 51 = 27 in the working set + 24 fetched
+    static FR3D_HD float run(float* a, const MedianSrc& s, int xo)
     {
         ForgetStep<N>::minmax(a);
-        a[0] = rest[27 - N];
-        return Forget27<N - 1>::run(a, rest);
+        a[0] = s.template own<1 + (27 - N)>(xo);
+        return Forget27<N - 1>::run(a, s, xo);
     }
 };
 template <>
 struct Forget27<3> {
-    static FR3D_HD float run(float* a, const float*)
+    static FR3D_HD float run(float* a, const MedianSrc&, int)
     {
         const float lo = fminf(a[0], a[1]), hi = fmaxf(a[0], a[1]);
         return fmaxf(lo, fminf(hi, a[2]));
@@ -1230,50 +1249,32 @@ struct Median5PairK {
         for (int d = 0; d < 6; ++d)
             xs[d] = mirror_idx(i0 + d - 2 < n + 2 ? i0 + d - 2 : n + 1, n); // (clamped only for the unused odd tail)
         // shared core: columns xs[1..4] x 25 (z,y) positions; key t -> (zy = t / 4, col = 1 + t % 4)
-        float a[64], rest[36];
-#pragma unroll
-        for (int t = 0; t < 100; ++t) {
-            const int zy = t >> 2;
-            const float key = (float)f[((int64_t)zi[zy / 5] * m + yi[zy % 5]) * n + xs[1 + (t & 3)]];
-            if (t < 64)
-                a[t] = key;
-            else
-                rest[t - 64] = key;
-        }
-        CorePrune<64>::run(a, rest);
-        // output A (voxel i0): survivors a[1..26] + own column xs[0]
-        float wa[27], own[24];
-#pragma unroll
-        for (int t = 0; t < 26; ++t)
-            wa[t] = a[1 + t];
-#pragma unroll
-        for (int t = 0; t < 25; ++t) {
-            const float key = (float)f[((int64_t)zi[t / 5] * m + yi[t % 5]) * n + xs[0]];
-            if (t == 0)
-                wa[26] = key;
-            else
-                own[t - 1] = key;
-        }
-        const float medA = Forget27<27>::run(wa, own);
+        const MedianSrc ms{f, zi, yi, xs, m, n};
+        float a[64];
+        load_core<0>(a, ms);
+        CorePrune<64>::run(a, ms);
         const int64_t oA = vol * N + ((int64_t)k * m + j) * n + i0;
-        const double rA = recover(f, zi, yi, i0, medA);
-        dst[oA] = add ? add[oA] + rA : rA;
-        if (!two)
-            return;
+#pragma unroll 1
+        for (int o = 0; o < (two ? 2 : 1); ++o) {
+            // output o (voxel i0 + o): survivors a[1..26] + own column xs[0] / xs[5]
+            const int xo = o ? xs[5] : xs[0];
+            float wa[27];
 #pragma unroll
-        for (int t = 0; t < 26; ++t)
-            wa[t] = a[1 + t];
-#pragma unroll
-        for (int t = 0; t < 25; ++t) {
-            const float key = (float)f[((int64_t)zi[t / 5] * m + yi[t % 5]) * n + xs[5]];
-            if (t == 0)
-                wa[26] = key;
-            else
-                own[t - 1] = key;
+            for (int t = 0; t < 26; ++t)
+                wa[t] = a[1 + t];
+            wa[26] = ms.own<0>(xo);
+            const float med = Forget27<27>::run(wa, ms, xo);
+            const double r = recover(f, zi, yi, i0 + o, med);
+            dst[oA + o] = add ? add[oA + o] + r : r;
         }
-        const float medB = Forget27<27>::run(wa, own);
-        const double rB = recover(f, zi, yi, i0 + 1, medB);
-        dst[oA + 1] = add ? add[oA + 1] + rB : rB;
+    }
+    template <int T>
+    static FR3D_HD void load_core(float* a, const MedianSrc& ms)
+    {
+        if constexpr (T < 64) {
+            a[T] = ms.core<T>();
+            load_core<T + 1>(a, ms);
+        }
     }
 };
 

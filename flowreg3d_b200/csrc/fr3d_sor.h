@@ -143,10 +143,15 @@ struct SorWave {
     int chunks;     // total chunks of this wave (one frame)
     int items;      // chunks * frame groups
 };
+// The two small per-hyperplane tables every item consults (shared-memory copies in the CUDA kernel).
+struct SorTabs {
+    const int32_t* pe;
+    const int32_t* start;
+};
 template <class ST>
 FR3D_HD int sor_num_waves(const SorParams<ST>& P) { return P.g.S + 2 * (P.T - 1); }
 template <class ST>
-FR3D_HD SorWave sor_wave(const SorParams<ST>& P, int q)
+FR3D_HD SorWave sor_wave(const SorParams<ST>& P, const SorTabs& tb, int q)
 {
     const int S = P.g.S;
     int tlo = q - (S - 1);
@@ -160,16 +165,25 @@ FR3D_HD SorWave sor_wave(const SorParams<ST>& P, int q)
     w.base = 0;
     w.chunks = 0;
     if (w.nT > 0) {
-        w.base = w.s_lo >= 2 ? P.g.pe[w.s_lo - 2] : 0;
-        w.chunks = P.g.pe[q - 2 * tlo] - w.base;
+        w.base = w.s_lo >= 2 ? tb.pe[w.s_lo - 2] : 0;
+        w.chunks = tb.pe[q - 2 * tlo] - w.base;
     }
     w.items = w.chunks * ((P.B + P.fg - 1) / P.fg);
     return w;
 }
 
-// Execute lane `lane` of warp item `item` of wave q.
-template <class ST, int C>
-FR3D_HD void sor_item(const SorParams<ST>& P, int q, const SorWave& w, int item, int lane)
+// Where a lane works for one warp item: its slot, the six neighbour slots, the frames.
+struct SorLoc {
+    int64_t a;
+    int n0, n1, n2, n3, n4, n5; // n0 < 0: pad slot (nothing to do)
+    int b0, b1;
+    bool refresh;
+};
+
+// Locate lane `lane` of warp item `item` of wave q (table look-ups only; issued one item ahead of
+// the arithmetic so that their latency hides behind the previous item's loads).
+template <class ST>
+FR3D_HD SorLoc sor_locate(const SorParams<ST>& P, const SorTabs& tb, int q, const SorWave& w, int item, int lane)
 {
     const HPView& g = P.g;
     const int fgi = item / w.chunks;
@@ -178,86 +192,87 @@ FR3D_HD void sor_item(const SorParams<ST>& P, int q, const SorWave& w, int item,
     int lo = 0, hi = w.nT - 1;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (g.pe[w.s_lo + 2 * mid] - w.base > f)
+        if (tb.pe[w.s_lo + 2 * mid] - w.base > f)
             hi = mid;
         else
             lo = mid + 1;
     }
     const int s = w.s_lo + 2 * lo;
-    const int before = (s >= 2 ? g.pe[s - 2] : 0) - w.base;
+    const int before = (s >= 2 ? tb.pe[s - 2] : 0) - w.base;
     const int t = (q - s) >> 1;
-    const int64_t a = (int64_t)g.start[s] + 32 * (f - before) + lane;
+    SorLoc L;
+    L.a = (int64_t)tb.start[s] + 32 * (f - before) + lane;
     const int64_t np = g.npad;
-    const int n0 = g.nbr[a];
-    if (n0 < 0)
+    L.n0 = g.nbr[L.a];
+    L.n1 = g.nbr[np + L.a];
+    L.n2 = g.nbr[2 * np + L.a];
+    L.n3 = g.nbr[3 * np + L.a];
+    L.n4 = g.nbr[4 * np + L.a];
+    L.n5 = g.nbr[5 * np + L.a];
+    L.refresh = (t % P.lag) == 0;
+    L.b0 = fgi * P.fg;
+    L.b1 = L.b0 + P.fg < P.B ? L.b0 + P.fg : P.B;
+    return L;
+}
+
+template <class ST>
+FR3D_HD void sor_load(const SorParams<ST>& P, const SorLoc& L, int b, bool with_ab, SorIn<ST>& r)
+{
+    const int64_t np = P.g.npad;
+    const Vec4<ST>* d = P.d + (int64_t)b * np;
+    r.own = ld4_cg(d + L.a);
+    r.xm = ld4_cg(d + L.n0);
+    r.ym = ld4_cg(d + L.n1);
+    r.zm = ld4_cg(d + L.n2);
+    r.xp = ld4_cg(d + L.n3);
+    r.yp = ld4_cg(d + L.n4);
+    r.zp = ld4_cg(d + L.n5);
+    r.L = ld4_cg(P.L + (int64_t)b * np + L.a);
+    if (with_ab) {
+        const double* AB = P.AB + (int64_t)b * 9 * np + L.a;
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+            r.A[k] = FR3D_LDCG(AB + k * np);
+    }
+}
+
+// Update the lane's voxel in every frame of the item.
+template <class ST, int C>
+FR3D_HD void sor_process(const SorParams<ST>& P, const SorLoc& L)
+{
+    if (L.n0 < 0)
         return; // pad slot
-    const int n1 = g.nbr[np + a], n2 = g.nbr[2 * np + a], n3 = g.nbr[3 * np + a], n4 = g.nbr[4 * np + a],
-              n5 = g.nbr[5 * np + a];
-    const bool refresh = (t % P.lag) == 0;
-    const double den0 = 2.0 * P.ax + 2.0 * P.ay + 2.0 * P.az;
-    const int b0 = fgi * P.fg;
-    const int b1 = b0 + P.fg < P.B ? b0 + P.fg : P.B;
-    if (refresh) {
-        for (int b = b0; b < b1; ++b) {
-            Vec4<ST>* d = P.d + (int64_t)b * np;
+    const int64_t np = P.g.npad;
+    const int64_t a = L.a;
+    if (L.refresh) {
+        const double den0 = 2.0 * P.ax + 2.0 * P.ay + 2.0 * P.az;
+        for (int b = L.b0; b < L.b1; ++b) {
             double* AB = P.AB + (int64_t)b * 9 * np + a;
             SorIn<ST> r;
-            r.own = ld4_cg(d + a);
-            r.xm = ld4_cg(d + n0);
-            r.ym = ld4_cg(d + n1);
-            r.zm = ld4_cg(d + n2);
-            r.xp = ld4_cg(d + n3);
-            r.yp = ld4_cg(d + n4);
-            r.zp = ld4_cg(d + n5);
-            r.L = ld4_cg(P.L + (int64_t)b * np + a);
+            sor_load(P, L, b, false, r);
             sor_refresh<C>(P.a_data, P.J + (int64_t)b * C * 10 * np, P.wgt, np, a, (double)r.own.x, (double)r.own.y,
                            (double)r.own.z, den0, r.A);
 #pragma unroll
             for (int e = 0; e < 9; ++e)
                 FR3D_STCG(AB + e * np, r.A[e]);
-            st4_cg(d + a, sor_update(P, r));
+            st4_cg(P.d + (int64_t)b * np + a, sor_update(P, r));
         }
         return;
     }
     // plain sweep: two frames in flight per lane (all loads of both issued before the first use)
-    int b = b0;
-    for (; b + 1 < b1; b += 2) {
+    int b = L.b0;
+    for (; b + 1 < L.b1; b += 2) {
         SorIn<ST> r[2];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const Vec4<ST>* d = P.d + (int64_t)(b + e) * np;
-            const double* AB = P.AB + (int64_t)(b + e) * 9 * np + a;
-            r[e].own = ld4_cg(d + a);
-            r[e].xm = ld4_cg(d + n0);
-            r[e].ym = ld4_cg(d + n1);
-            r[e].zm = ld4_cg(d + n2);
-            r[e].xp = ld4_cg(d + n3);
-            r[e].yp = ld4_cg(d + n4);
-            r[e].zp = ld4_cg(d + n5);
-            r[e].L = ld4_cg(P.L + (int64_t)(b + e) * np + a);
-#pragma unroll
-            for (int k = 0; k < 9; ++k)
-                r[e].A[k] = FR3D_LDCG(AB + k * np);
-        }
+        for (int e = 0; e < 2; ++e)
+            sor_load(P, L, b + e, true, r[e]);
 #pragma unroll
         for (int e = 0; e < 2; ++e)
             st4_cg(P.d + (int64_t)(b + e) * np + a, sor_update(P, r[e]));
     }
-    if (b < b1) {
+    if (b < L.b1) {
         SorIn<ST> r;
-        const Vec4<ST>* d = P.d + (int64_t)b * np;
-        const double* AB = P.AB + (int64_t)b * 9 * np + a;
-        r.own = ld4_cg(d + a);
-        r.xm = ld4_cg(d + n0);
-        r.ym = ld4_cg(d + n1);
-        r.zm = ld4_cg(d + n2);
-        r.xp = ld4_cg(d + n3);
-        r.yp = ld4_cg(d + n4);
-        r.zp = ld4_cg(d + n5);
-        r.L = ld4_cg(P.L + (int64_t)b * np + a);
-#pragma unroll
-        for (int k = 0; k < 9; ++k)
-            r.A[k] = FR3D_LDCG(AB + k * np);
+        sor_load(P, L, b, true, r);
         st4_cg(P.d + (int64_t)b * np + a, sor_update(P, r));
     }
 }
@@ -267,11 +282,12 @@ template <class ST, int C>
 inline void sor_run_c(Device& dev, const SorParams<ST>& P, unsigned*)
 {
     const int nw = sor_num_waves(P);
+    const SorTabs tb{P.g.pe, P.g.start};
     for (int q = 0; q < nw; ++q) {
-        const SorWave w = sor_wave(P, q);
+        const SorWave w = sor_wave(P, tb, q);
         for (int item = 0; item < w.items; ++item)
             for (int lane = 0; lane < 32; ++lane)
-                sor_item<ST, C>(P, q, w, item, lane);
+                sor_process<ST, C>(P, sor_locate(P, tb, q, w, item, lane));
     }
     dev.launches++;
 }
@@ -292,17 +308,47 @@ __device__ __forceinline__ void fr3d_grid_barrier(unsigned* ctr, unsigned target
 }
 
 // Persistent cooperative kernel: all waves of one level solve, one grid barrier per wave.
+// Dynamic shared memory: copies of the pe / start tables (tabs_in_smem) so that locating an item
+// costs shared-memory latency only.
 template <class ST, int C>
-__global__ void __launch_bounds__(FR3D_SOR_THREADS, 2) fr3d_sor_wavefront(const SorParams<ST> P, unsigned* bar)
+__global__ void __launch_bounds__(FR3D_SOR_THREADS, 2)
+fr3d_sor_wavefront(const SorParams<ST> P, unsigned* bar, int tabs_in_smem)
 {
+    extern __shared__ int32_t fr3d_sor_smem[];
+    SorTabs tb{P.g.pe, P.g.start};
+    if (tabs_in_smem) {
+        const int S = P.g.S;
+        for (int i = threadIdx.x; i < S; i += blockDim.x)
+            fr3d_sor_smem[i] = P.g.pe[i];
+        for (int i = threadIdx.x; i <= S; i += blockDim.x)
+            fr3d_sor_smem[S + i] = P.g.start[i];
+        __syncthreads();
+        tb.pe = fr3d_sor_smem;
+        tb.start = fr3d_sor_smem + S;
+    }
     const int nw = sor_num_waves(P);
     const int wpb = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int stride = gridDim.x * wpb;
     unsigned gen = 0;
     for (int q = 0; q < nw; ++q) {
-        const SorWave w = sor_wave(P, q);
-        for (int item = blockIdx.x * wpb + warp; item < w.items; item += gridDim.x * wpb)
-            sor_item<ST, C>(P, q, w, item, lane);
+        const SorWave w = sor_wave(P, tb, q);
+        int item = blockIdx.x * wpb + warp;
+        if (item < w.items) {
+            SorLoc cur = sor_locate(P, tb, q, w, item, lane);
+            for (;;) {
+                const int next = item + stride;
+                const bool more = next < w.items;
+                SorLoc nxt;
+                if (more)
+                    nxt = sor_locate(P, tb, q, w, next, lane); // neighbour-table loads fly during the update below
+                sor_process<ST, C>(P, cur);
+                if (!more)
+                    break;
+                cur = nxt;
+                item = next;
+            }
+        }
         ++gen;
         fr3d_grid_barrier(bar, gen * gridDim.x);
     }
@@ -311,10 +357,15 @@ __global__ void __launch_bounds__(FR3D_SOR_THREADS, 2) fr3d_sor_wavefront(const 
 template <class ST, int C>
 inline void sor_run_c(Device& dev, const SorParams<ST>& P, unsigned* bar, int peak_items)
 {
+    const size_t smem = (size_t)(2 * P.g.S + 1) * sizeof(int32_t);
+    const int tabs_in_smem = smem <= 40 * 1024;
+    const size_t dyn = tabs_in_smem ? smem : 0;
     int per_sm = 0;
     FR3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fr3d_sor_wavefront<ST, C>,
-                                                            FR3D_SOR_THREADS, 0));
+                                                            FR3D_SOR_THREADS, dyn));
     FR3D_REQUIRE(per_sm >= 1, "SOR kernel does not fit on an SM");
+    if (dev.sor_ctas_per_sm > 0 && per_sm > dev.sor_ctas_per_sm)
+        per_sm = dev.sor_ctas_per_sm;
     // no more CTAs than the busiest wave can use
     const int wpb = FR3D_SOR_THREADS / 32;
     int64_t want = ((int64_t)peak_items + wpb - 1) / wpb;
@@ -323,10 +374,11 @@ inline void sor_run_c(Device& dev, const SorParams<ST>& P, unsigned* bar, int pe
         grid = (int)(want < 1 ? 1 : want);
     FR3D_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), dev.stream));
     SorParams<ST> Pc = P;
-    void* args[] = {(void*)&Pc, (void*)&bar};
+    int tis = tabs_in_smem;
+    void* args[] = {(void*)&Pc, (void*)&bar, (void*)&tis};
     dev.span_begin("fr3d_sor_wavefront");
     FR3D_CUDA(cudaLaunchCooperativeKernel((void*)fr3d_sor_wavefront<ST, C>, dim3(grid), dim3(FR3D_SOR_THREADS),
-                                          args, 0, dev.stream));
+                                          args, dyn, dev.stream));
     dev.span_end();
     dev.launches++;
 }

@@ -112,6 +112,13 @@ int64_t fr3d_launch_count(const fr3d_ctx* ctx);
 /* bytes of device memory currently held by the context */
 int64_t fr3d_device_bytes(const fr3d_ctx* ctx);
 
+/* Tuning knobs (do not change results). */
+typedef enum {
+    FR3D_OPT_SOR_CTAS_PER_SM = 1 /* resident CTAs per SM the persistent solver kernel may claim (0 = all it can
+                                  * get; 1 leaves room for a second stream's kernels on every SM) */
+} fr3d_option;
+int fr3d_set_option(fr3d_ctx* ctx, int option, int64_t value);
+
 /* Per-kernel timing with CUDA events on the context's stream (used by bench.py for the roofline
  * figures).  fr3d_profile_report synchronises, writes "name<TAB>launches<TAB>total_ms" lines into buf
  * (host) and clears the record; returns the byte length of the full report or a negative status. */

@@ -143,3 +143,21 @@ def test_config1_default_options(backend, golden):
     mean, mx = epe_stats(flow[::2, ::2, ::2], g["low_flow_s2"])
     assert mean <= 1e-4 and mx <= 5e-3, (mean, mx)              # tolerance: 0.01 / 0.05
     assert rel_l2(reg[::2, ::2, ::2], g["low_reg_s2"]) <= 1e-5   # tolerance: 1e-4
+
+
+def test_split_streams_identical(backend, golden):
+    """The batch split over two contexts / CUDA streams gives bit-identical results (frames are independent)."""
+    import flowreg3d_b200 as F
+    from flowreg3d_b200 import device as dev
+    g = golden("sequence")
+    ml, it, lag, _ = (int(v) for v in g["params"])
+    opts = F.OFOptions(alpha=(0.25, 0.25, 0.25), levels=100, min_level=ml, iterations=it, update_lag=lag,
+                       buffer_size=3, weight=[0.5, 0.5])
+    outs = []
+    for streams in (1, 2):
+        seq = F.SequenceCorrector(g["ref"], opts, max_batch=3, streams=streams)
+        reg, fl = seq.process_batch(g["video"][:3])
+        seq.reg.sync()
+        outs.append((dev.to_host(reg).copy(), dev.to_host(fl).copy()))
+        seq.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
