@@ -25,7 +25,7 @@ from typing import Callable, List, Optional, Tuple
 import numpy as np
 import torch
 
-from . import device as dev
+from . import _lib, device as dev
 from .core import Registration, SplitRegistration
 from .options import OFOptions
 from .plan import FlowParams
@@ -167,6 +167,123 @@ class SequenceCorrector:
             reg = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
         return reg, flows
 
+    # -- host-resident recordings: copy / compute / copy pipeline --------------------------
+    def run_pipelined(self, host_batches, out_reg: Optional[list] = None, out_flow: Optional[list] = None,
+                      global_sizes: Optional[list] = None, local_offsets: Optional[list] = None,
+                      sink: Optional[Callable] = None):
+        """Process a sequence of HOST batches (tensors or arrays (t,Z,Y,X,C); pinned memory makes the
+        copies asynchronous) with the host->device copy of batch k+1 and the device->host copy of
+        batch k-1 running on their own streams under the compute of batch k.  Results land in
+        out_reg[k] (t,Z,Y,X,C) float32 and out_flow[k] (t,Z,Y,X,3) float32 host tensors (allocated
+        pinned when not given).  With `sink`, sink(k, reg_host, flow_host) is called in order as soon
+        as batch k has arrived on the host and only two result buffers are cycled (consume or copy the
+        arrays inside the callback).  Returns (out_reg, out_flow) after everything has completed."""
+        K = len(host_batches)
+        def as_tensor(b):
+            if isinstance(b, torch.Tensor):
+                return b
+            b = np.asarray(b)
+            if b.dtype not in _lib._DTYPES:
+                b = b.astype(np.float64)
+            b = np.ascontiguousarray(b)
+            return torch.from_numpy(b if b.flags.writeable else b.copy())
+        hb = [as_tensor(b) for b in host_batches]
+        Z, Y, X = self.shape
+        if self.device.type != "cuda":  # kernel-logic emulator (tests): plain loop
+            out_reg = list(out_reg) if out_reg is not None else [None] * K
+            out_flow = list(out_flow) if out_flow is not None else [None] * K
+            for k in range(K):
+                g = None if global_sizes is None else global_sizes[k]
+                o = 0 if local_offsets is None else local_offsets[k]
+                reg, fl = self.process_batch(hb[k], global_size=g, local_offset=o)
+                self.reg.sync()
+                t = hb[k].shape[0]
+                r_ = reg if reg is not None else torch.empty((0, Z, Y, X, self.C), dtype=torch.float32)
+                f_ = fl if fl is not None else torch.empty((0, Z, Y, X, 3), dtype=torch.float32)
+                if out_reg[k] is None:
+                    out_reg[k] = r_.clone()
+                else:
+                    out_reg[k][:t].copy_(r_)
+                if out_flow[k] is None:
+                    out_flow[k] = f_.clone()
+                else:
+                    out_flow[k][:t].copy_(f_)
+                if sink is not None:
+                    sink(k, out_reg[k][:t], out_flow[k][:t])
+            return out_reg, out_flow
+        main = torch.cuda.current_stream(self.device)
+        if not hasattr(self, "_s_in"):
+            self._s_in, self._s_out = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
+            self._in_bufs = [None, None]
+        s_in, s_out = self._s_in, self._s_out
+        out_reg = list(out_reg) if out_reg is not None else [None] * K
+        out_flow = list(out_flow) if out_flow is not None else [None] * K
+        tmax = max([b.shape[0] for b in hb], default=0)
+        cyc_reg, cyc_flow = {}, {}
+        for k in range(K):
+            t = hb[k].shape[0]
+            if out_reg[k] is None:
+                if sink is not None:  # two cycling buffers
+                    if k % 2 not in cyc_reg:
+                        cyc_reg[k % 2] = torch.empty((tmax, Z, Y, X, self.C), dtype=torch.float32).pin_memory()
+                    out_reg[k] = cyc_reg[k % 2]
+                else:
+                    out_reg[k] = torch.empty((t, Z, Y, X, self.C), dtype=torch.float32).pin_memory()
+            if out_flow[k] is None:
+                if sink is not None:
+                    if k % 2 not in cyc_flow:
+                        cyc_flow[k % 2] = torch.empty((tmax, Z, Y, X, 3), dtype=torch.float32).pin_memory()
+                    out_flow[k] = cyc_flow[k % 2]
+                else:
+                    out_flow[k] = torch.empty((t, Z, Y, X, 3), dtype=torch.float32).pin_memory()
+        ev_in, ev_done, ev_out = [None] * K, [None] * K, [None] * K
+
+        def drain(k):
+            if sink is not None and k >= 0:
+                if ev_out[k] is not None:
+                    ev_out[k].synchronize()
+                t_ = hb[k].shape[0]
+                sink(k, out_reg[k][:t_], out_flow[k][:t_])
+
+        def stage(k):
+            with torch.cuda.stream(s_in):
+                if k >= 2:
+                    s_in.wait_event(ev_done[k - 2])      # buffer k % 2 is free once batch k-2 was consumed
+                else:
+                    s_in.wait_stream(main)
+                buf = self._in_bufs[k % 2]
+                if buf is None or buf.shape[1:] != hb[k].shape[1:] or buf.shape[0] < hb[k].shape[0] \
+                        or buf.dtype != hb[k].dtype:
+                    buf = self._in_bufs[k % 2] = torch.empty(tuple(hb[k].shape), dtype=hb[k].dtype, device=self.device)
+                buf[:hb[k].shape[0]].copy_(hb[k], non_blocking=True)
+                ev_in[k] = s_in.record_event()
+
+        if K > 0:
+            stage(0)
+        for k in range(K):
+            if k + 1 < K:
+                stage(k + 1)
+            main.wait_event(ev_in[k])
+            t = hb[k].shape[0]
+            g = None if global_sizes is None else global_sizes[k]
+            o = 0 if local_offsets is None else local_offsets[k]
+            reg, fl = self.process_batch(self._in_bufs[k % 2][:t], global_size=g, local_offset=o)
+            ev_done[k] = main.record_event()
+            # host buffer k % 2 must have been consumed (batch k-2 drained below) before it is refilled
+            if t > 0:
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_done[k])
+                    out_reg[k][:t].copy_(reg, non_blocking=True)
+                    out_flow[k][:t].copy_(fl, non_blocking=True)
+                    reg.record_stream(s_out)
+                    fl.record_stream(s_out)
+                    ev_out[k] = s_out.record_event()
+            drain(k - 1)       # blocks the host until batch k-1 is on the host; the GPU keeps computing batch k
+        s_out.synchronize()
+        main.synchronize()
+        drain(K - 1)
+        return out_reg, out_flow
+
     def close(self):
         if isinstance(self.reg, SplitRegistration):
             self.reg.close()
@@ -199,21 +316,24 @@ def compensate_arr_3D(c1: np.ndarray, c_ref: np.ndarray, options=None,
     seq = SequenceCorrector(c_ref, options, device=device)
     registered = np.empty_like(c1)
     w = np.empty((T,) + seq.shape + (3,), np.float32)
-    done = 0
+    bs = int(options.buffer_size)
+    bounds = [(b0, min(T, b0 + bs)) for b0 in range(0, T, bs)]
+    done = [0]
+
+    def sink(k, reg_host, flow_host):
+        b0, b1 = bounds[k]
+        registered[b0:b1] = reg_host.numpy()    # numpy cast to the input dtype, as sequential_3d.py:163-169
+        w[b0:b1] = flow_host.numpy()
+        done[0] += b1 - b0
+        if progress_callback is not None:
+            try:
+                progress_callback(done[0], T)
+            except Exception as e:  # compensate_recording_3D.py:158-162
+                import warnings
+                warnings.warn(f"Progress callback error: {e}")
+
     try:
-        for b0 in range(0, T, int(options.buffer_size)):
-            b1 = min(T, b0 + int(options.buffer_size))
-            reg, flows = seq.process_batch(c1[b0:b1])
-            seq.reg.sync()
-            registered[b0:b1] = dev.to_host(reg)
-            w[b0:b1] = dev.to_host(flows)
-            done += b1 - b0
-            if progress_callback is not None:
-                try:
-                    progress_callback(done, T)
-                except Exception as e:  # compensate_recording_3D.py:158-162
-                    import warnings
-                    warnings.warn(f"Progress callback error: {e}")
+        seq.run_pipelined([c1[b0:b1] for b0, b1 in bounds], sink=sink)
     finally:
         seq.close()
     tn = getattr(options, "output_typename", None)
