@@ -60,7 +60,7 @@ _lib = None
 
 
 def library_path() -> Path:
-    ov = os.environ.get("FR3D_LIBRARY_OVERRIDE")
+    ov = os.environ.get("FR3D_LIBRARY_OVERRIDE") or os.environ.get("FR3D_LIBRARY_VARIANT")
     return Path(ov) if ov else HERE / "libfr3d.so"
 
 

@@ -374,6 +374,37 @@ FR3D_HD Vec4<double> ld4_cg(const Vec4<double>* p)
     return *p;
 #endif
 }
+// L1-cached vector loads (neighbour increments: hyperplanes that are not written during the current wave;
+// every CTA invalidates its SM's L1 at the wave barrier -- see fr3d_sor.h)
+FR3D_HD Vec4<float> ld4_ca(const Vec4<float>* p)
+{
+#ifdef __CUDA_ARCH__
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    Vec4<float> r;
+    r.x = v.x;
+    r.y = v.y;
+    r.z = v.z;
+    r.w = v.w;
+    return r;
+#else
+    return *p;
+#endif
+}
+FR3D_HD Vec4<double> ld4_ca(const Vec4<double>* p)
+{
+#ifdef __CUDA_ARCH__
+    const double2 a = *reinterpret_cast<const double2*>(p);
+    const double2 b = *(reinterpret_cast<const double2*>(p) + 1);
+    Vec4<double> r;
+    r.x = a.x;
+    r.y = a.y;
+    r.z = b.x;
+    r.w = b.y;
+    return r;
+#else
+    return *p;
+#endif
+}
 FR3D_HD void st4_cg(Vec4<float>* p, const Vec4<float>& v)
 {
 #ifdef __CUDA_ARCH__

@@ -38,6 +38,23 @@ namespace fr3d {
 
 #define FR3D_SOR_OMEGA 1.95
 
+// Per-state-dtype tuning (measured on B200, config 2, B = 16; profiles/r01_sor_variants.txt):
+//   float64 state: two frames in flight per lane, 2 CTAs/SM (128 registers), neighbour increments via L1
+//   float32 state: one frame in flight per lane, 3 CTAs/SM (80 registers)
+// Neighbour loads through L1 are safe because (i) a wave only writes hyperplanes of its own parity
+// while neighbours live on hyperplanes of the other parity, (ii) the voxel's own value bypasses L1,
+// and (iii) every CTA executes a gpu-scope fence (which invalidates its SM's L1) at the wave barrier.
+template <class ST>
+struct SorTune;
+template <>
+struct SorTune<double> {
+    static constexpr int kPair = 1, kMinBlocks = 2, kNbrCa = 1;
+};
+template <>
+struct SorTune<float> {
+    static constexpr int kPair = 0, kMinBlocks = 3, kNbrCa = 0;
+};
+
 template <class ST>
 struct SorParams {
     HPView g;
@@ -221,12 +238,21 @@ FR3D_HD void sor_load(const SorParams<ST>& P, const SorLoc& L, int b, bool with_
     const int64_t np = P.g.npad;
     const Vec4<ST>* d = P.d + (int64_t)b * np;
     r.own = ld4_cg(d + L.a);
-    r.xm = ld4_cg(d + L.n0);
-    r.ym = ld4_cg(d + L.n1);
-    r.zm = ld4_cg(d + L.n2);
-    r.xp = ld4_cg(d + L.n3);
-    r.yp = ld4_cg(d + L.n4);
-    r.zp = ld4_cg(d + L.n5);
+    if (SorTune<ST>::kNbrCa) {
+        r.xm = ld4_ca(d + L.n0);
+        r.ym = ld4_ca(d + L.n1);
+        r.zm = ld4_ca(d + L.n2);
+        r.xp = ld4_ca(d + L.n3);
+        r.yp = ld4_ca(d + L.n4);
+        r.zp = ld4_ca(d + L.n5);
+    } else {
+        r.xm = ld4_cg(d + L.n0);
+        r.ym = ld4_cg(d + L.n1);
+        r.zm = ld4_cg(d + L.n2);
+        r.xp = ld4_cg(d + L.n3);
+        r.yp = ld4_cg(d + L.n4);
+        r.zp = ld4_cg(d + L.n5);
+    }
     r.L = ld4_cg(P.L + (int64_t)b * np + L.a);
     if (with_ab) {
         const double* AB = P.AB + (int64_t)b * 9 * np + L.a;
@@ -261,7 +287,7 @@ FR3D_HD void sor_process(const SorParams<ST>& P, const SorLoc& L)
     }
     // plain sweep: two frames in flight per lane (all loads of both issued before the first use)
     int b = L.b0;
-    for (; b + 1 < L.b1; b += 2) {
+    for (; SorTune<ST>::kPair && b + 1 < L.b1; b += 2) {
         SorIn<ST> r[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e)
@@ -270,7 +296,7 @@ FR3D_HD void sor_process(const SorParams<ST>& P, const SorLoc& L)
         for (int e = 0; e < 2; ++e)
             st4_cg(P.d + (int64_t)(b + e) * np + a, sor_update(P, r[e]));
     }
-    if (b < L.b1) {
+    for (; b < L.b1; ++b) {
         SorIn<ST> r;
         sor_load(P, L, b, true, r);
         st4_cg(P.d + (int64_t)b * np + a, sor_update(P, r));
@@ -311,7 +337,7 @@ __device__ __forceinline__ void fr3d_grid_barrier(unsigned* ctr, unsigned target
 // Dynamic shared memory: copies of the pe / start tables (tabs_in_smem) so that locating an item
 // costs shared-memory latency only.
 template <class ST, int C>
-__global__ void __launch_bounds__(FR3D_SOR_THREADS, 2)
+__global__ void __launch_bounds__(FR3D_SOR_THREADS, SorTune<ST>::kMinBlocks)
 fr3d_sor_wavefront(const SorParams<ST> P, unsigned* bar, int tabs_in_smem)
 {
     extern __shared__ int32_t fr3d_sor_smem[];
