@@ -126,12 +126,16 @@ struct fr3d_ctx {
 static thread_local std::string g_create_err;
 
 // ---- building blocks -------------------------------------------------------------------------
+// One resampling pass.  n[], ss[], ds[]: extents and element strides of the 5-D item space, axis r
+// (1..3) is the resampled one.  inner4: the thread walks axis 4 itself (short interleaved axis whose tap
+// table look-ups and index arithmetic are then shared); otherwise axis 4 must have been folded away
+// (n[4] == 1).
 template <class SrcT, class DstT>
 static void resize_pass(fr3d_ctx* c, const SrcT* src, const int64_t ss[5], DstT* dst, const int64_t ds[5],
                         const int64_t n[5], int r, const DevTable& t)
 {
-    FR3D_REQUIRE(r != 0, "resize_pass: axis 0 is the batch axis");
-    const int64_t inner = n[1] * n[2] * n[3] * n[4];
+    FR3D_REQUIRE(r >= 1 && r <= 3, "resize_pass: resampled axis must be 1..3");
+    const int64_t inner = n[1] * n[2] * n[3];
     FR3D_REQUIRE(inner > 0 && inner < (1LL << 31), "resize_pass: one batch entry has %lld outputs", (long long)inner);
     // items of a launch are decoded with 32-bit fast division: split the batch axis if needed
     const int64_t per = ((1LL << 31) / inner) < 1 ? 1 : ((1LL << 31) / inner);
@@ -147,6 +151,7 @@ static void resize_pass(fr3d_ctx* c, const SrcT* src, const int64_t ss[5], DstT*
         }
         k.r = r;
         k.P = t.P;
+        k.n4 = (int)n[4];
         k.idx = t.idx.p;
         k.wt = t.wt.p;
         launch(c->dev, k, nb * inner);
@@ -160,6 +165,10 @@ static void resize3(fr3d_ctx* c, const SrcT* src, View sv, int64_t n0, int64_t n
                     DstT* dst, View dv, const DevTable tabs[3])
 {
     const int ow = tabs[0].out_len, oh = tabs[1].out_len, od = tabs[2].out_len;
+    if (n1 == 1) { // a single-entry axis carries no stride of its own
+        sv.s1 = sv.s0;
+        dv.s1 = dv.s0;
+    }
     FR3D_REQUIRE(tabs[0].in_len == W && tabs[1].in_len == H && tabs[2].in_len == D,
                  "resize tables (%d,%d,%d) do not match volume (%d,%d,%d)", tabs[2].in_len, tabs[1].in_len,
                  tabs[0].in_len, D, H, W);
@@ -169,33 +178,41 @@ static void resize3(fr3d_ctx* c, const SrcT* src, View sv, int64_t n0, int64_t n
     // The item order of a pass is free (ResizePassK takes explicit extents and strides): when the
     // source / destination is channel-interleaved (stride of the n1 axis == 1) the n1 axis is made the
     // fastest one so that the interleaved side is accessed contiguously.
-    if (sv.s1 == 1 && n1 > 1) {
+    // Item space (n0, A, B, C | inner): when the source / destination is channel-interleaved (stride of the
+    // n1 axis == 1) and short, the thread walks the n1 axis itself (axis 4) so that the interleaved side
+    // is accessed contiguously and the tap look-ups are shared; otherwise n0 and n1 are folded into
+    // axis 0 (planar views: s0 == n1 * s1).
+    const bool src_il = sv.s1 == 1 && n1 > 1 && n1 <= 4;
+    const bool dst_il = dv.s1 == 1 && n1 > 1 && n1 <= 4;
+    const bool src_fold = sv.s0 == n1 * sv.s1 || n0 == 1, dst_fold = dv.s0 == n1 * dv.s1 || n0 == 1;
+    FR3D_REQUIRE((src_il || src_fold) && (dst_il || dst_fold), "resize3: unsupported view");
+    if (src_il) {
         const int64_t n[5] = {n0, D, H, ow, n1};
         const int64_t ss[5] = {sv.s0, sv.sz, sv.sy, sv.sx, sv.s1};
         const int64_t ds[5] = {av.s0, av.sz, av.sy, av.sx, av.s1};
         resize_pass<SrcT, float>(c, src, ss, a, ds, n, 3, tabs[0]);
     } else {
-        const int64_t n[5] = {n0, n1, D, H, ow};
-        const int64_t ss[5] = {sv.s0, sv.s1, sv.sz, sv.sy, sv.sx};
-        const int64_t ds[5] = {av.s0, av.s1, av.sz, av.sy, av.sx};
-        resize_pass<SrcT, float>(c, src, ss, a, ds, n, 4, tabs[0]);
+        const int64_t n[5] = {n0 * n1, D, H, ow, 1};
+        const int64_t ss[5] = {sv.s1, sv.sz, sv.sy, sv.sx, 0};
+        const int64_t ds[5] = {av.s1, av.sz, av.sy, av.sx, 0};
+        resize_pass<SrcT, float>(c, src, ss, a, ds, n, 3, tabs[0]);
     }
     {
-        const int64_t n[5] = {n0, n1, D, oh, ow};
-        const int64_t ss[5] = {av.s0, av.s1, av.sz, av.sy, av.sx};
-        const int64_t ds[5] = {bv.s0, bv.s1, bv.sz, bv.sy, bv.sx};
-        resize_pass<float, float>(c, a, ss, b, ds, n, 3, tabs[1]);
+        const int64_t n[5] = {n0 * n1, D, oh, ow, 1};
+        const int64_t ss[5] = {av.s1, av.sz, av.sy, av.sx, 0};
+        const int64_t ds[5] = {bv.s1, bv.sz, bv.sy, bv.sx, 0};
+        resize_pass<float, float>(c, a, ss, b, ds, n, 2, tabs[1]);
     }
-    if (dv.s1 == 1 && n1 > 1) {
+    if (dst_il) {
         const int64_t n[5] = {n0, od, oh, ow, n1};
         const int64_t ss[5] = {bv.s0, bv.sz, bv.sy, bv.sx, bv.s1};
         const int64_t ds[5] = {dv.s0, dv.sz, dv.sy, dv.sx, dv.s1};
         resize_pass<float, DstT>(c, b, ss, dst, ds, n, 1, tabs[2]);
     } else {
-        const int64_t n[5] = {n0, n1, od, oh, ow};
-        const int64_t ss[5] = {bv.s0, bv.s1, bv.sz, bv.sy, bv.sx};
-        const int64_t ds[5] = {dv.s0, dv.s1, dv.sz, dv.sy, dv.sx};
-        resize_pass<float, DstT>(c, b, ss, dst, ds, n, 2, tabs[2]);
+        const int64_t n[5] = {n0 * n1, od, oh, ow, 1};
+        const int64_t ss[5] = {bv.s1, bv.sz, bv.sy, bv.sx, 0};
+        const int64_t ds[5] = {dv.s1, dv.sz, dv.sy, dv.sx, 0};
+        resize_pass<float, DstT>(c, b, ss, dst, ds, n, 1, tabs[2]);
     }
 }
 
@@ -301,7 +318,7 @@ static void run_sor_t(fr3d_ctx* c, const HPGeom& hp, int B, int C, const float* 
     as.ax = P.ax;
     as.ay = P.ay;
     as.az = P.az;
-    launch(dev, as, (int64_t)B * np);
+    launch_occ2(dev, as, (int64_t)B * np);
     sor_run(dev, P, c->bar.ensure(dev, 4), hp.pe_host.data());
 }
 

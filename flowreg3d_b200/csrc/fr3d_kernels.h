@@ -40,36 +40,40 @@ struct ResizePassK {
     const SrcT* src;
     DstT* dst;
     int64_t ss[5], ds[5];
-    FastDiv fd[5]; // divisors n[1..4] at fd[1..4] (item < 2^32)
-    int r, P;
+    FastDiv fd[5]; // divisors n[1..3] at fd[1..3] (item < 2^32); axis 4 is walked inside the thread
+    int r, P, n4;  // n4 = extent of axis 4 (1 unless the innermost axis is a short interleaved one)
     const int32_t* idx;
     const float* wt;
     FR3D_HD void operator()(int64_t item) const
     {
-        uint32_t i[5];
+        uint32_t i[4];
         uint32_t e = (uint32_t)item;
-        fd[4].divmod(e, e, i[4]);
         fd[3].divmod(e, e, i[3]);
         fd[2].divmod(e, e, i[2]);
         fd[1].divmod(e, i[0], i[1]);
         int64_t so = 0, dof = 0;
+        uint32_t ir = 0;
 #pragma unroll
-        for (int d = 0; d < 5; ++d) {
+        for (int d = 0; d < 4; ++d) {
             dof += (int64_t)i[d] * ds[d];
             if (d != r)
                 so += (int64_t)i[d] * ss[d];
+            else
+                ir = i[d];
         }
-        const int32_t* ix = idx + (int64_t)i[r] * P;
-        const float* w = wt + (int64_t)i[r] * P;
+        const int32_t* ix = idx + (int64_t)ir * P;
+        const float* w = wt + (int64_t)ir * P;
         const int64_t sr = ss[r];
-        const SrcT* sp = src + so;
-        double acc = 0.0;
-        for (int p = 0; p < P; ++p) {
-            const float a = (float)sp[(int64_t)ix[p] * sr];
-            const float prod = a * w[p];
-            acc += (double)prod;
+        for (int q = 0; q < n4; ++q) {
+            const SrcT* sp = src + so + q * ss[4];
+            double acc = 0.0;
+            for (int p = 0; p < P; ++p) {
+                const float a = (float)sp[(int64_t)ix[p] * sr];
+                const float prod = a * w[p];
+                acc += (double)prod;
+            }
+            dst[dof + q * ds[4]] = (DstT)(float)acc;
         }
-        dst[dof] = (DstT)(float)acc;
     }
 };
 

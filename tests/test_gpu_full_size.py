@@ -93,3 +93,55 @@ def test_sor_many_ctas_and_batches(cuda_backend, golden):
                           pad(uvw[1]), pad(uvw[2]), (0.3, 0.4, 0.5), 12, 5, np.full(C, 0.45), 1.0, 1.1, 1.2, 1.5)
     inner = (slice(1, -1),) * 3
     assert np.abs(d - np.moveaxis(o[inner], -1, 0)).max() <= 1e-9
+
+
+def _recoil_jitter_frames(ref, T):
+    """BASELINE config 3 style motion: injection every few frames with exponential
+    recoil (expansion about the volume centre) plus a scanning jitter, deterministic in t."""
+    import flowreg3d_b200 as F
+    Z, Y, X, C = ref.shape
+    zz, yy, xx = np.meshgrid(np.arange(Z) - Z / 2, np.arange(Y) - Y / 2, np.arange(X) - X / 2, indexing="ij")
+    frames = []
+    r64 = ref.astype(np.float64)
+    for t in range(T):
+        mag = 0.04 * np.exp(-(t % 5) / 2.0)
+        jit = 1.0 * np.sin(2 * np.pi * t / 17.0)
+        u = xx * mag + jit * np.sin(2 * np.pi * yy / Y)
+        v = yy * mag
+        w = zz * mag * 0.5
+        frames.append(O.imregister_wrapper(r64, -u, -v, -w, r64, "linear"))
+    return np.stack(frames, 0).astype(np.float32)
+
+
+def test_config3_sequence_cuda_vs_oracle(cuda_backend):
+    """Config 3 (injection / recoil + jitter) at a size the oracle finishes in seconds: the whole
+    sequence path (GPU pre-filter, w_init bootstrap + chaining over three batches, ragged last batch,
+    pipelined host streaming) against the oracle's restatement of BatchMotionCorrector."""
+    import flowreg3d_b200 as F
+    Z, Y, X = 24, 64, 72
+    ref = np.stack([synth_volume((Z, Y, X), 70 + c) for c in range(2)], -1)
+    video = _recoil_jitter_frames(ref, 7)
+    opts = F.OFOptions(min_level=2, iterations=40, update_lag=5, buffer_size=3, weight=[0.5, 0.5])
+    reg, w = F.compensate_arr_3D(video, ref, opts)
+    oreg, ow = O.compensate_arr(video, ref, min_level=2, iterations=40, update_lag=5, buffer_size=3,
+                                weight=[0.5, 0.5])
+    mean, mx = epe_stats(w, ow)
+    assert mean <= 1e-4 and mx <= 5e-3, (mean, mx)              # tolerance: 0.01 / 0.05
+    assert rel_l2(reg, oreg) <= 1e-5                            # tolerance: 1e-4
+
+
+@pytest.mark.parametrize("min_level,alpha,iters", [(3, 0.1, 20), (3, 2.0, 50), (0, 0.25, 50), (0, 1.0, 20)])
+def test_config5_solver_sweep_cuda_vs_oracle(cuda_backend, min_level, alpha, iters):
+    """Config 5 (pyramid depth / alpha / iteration sweep) cells on a 1-channel 20x72x80 pair."""
+    import flowreg3d_b200 as F
+    Z, Y, X = 20, 72, 80
+    fixed = synth_volume((Z, Y, X), 90)
+    g = smooth_flow((Z, Y, X), 4, 1.5, 7.0)
+    f64 = fixed.astype(np.float64)
+    moving = O.imregister_wrapper(f64, -g[..., 0], -g[..., 1], -g[..., 2], f64, "linear")
+    kw = dict(alpha=(alpha,) * 3, update_lag=5, iterations=iters, min_level=min_level, levels=100, eta=0.8,
+              a_smooth=1.0, a_data=0.45)
+    flow = F.get_displacement(fixed, moving, **kw)
+    ref = O.get_displacement(fixed, moving, **kw)
+    mean, mx = epe_stats(flow, ref)
+    assert mean <= 1e-4 and mx <= 5e-3, (min_level, alpha, iters, mean, mx)   # tolerance: 0.01 / 0.05
