@@ -24,6 +24,9 @@ from .plan import FlowParams, PlanHolder, SWEEP_LEXICOGRAPHIC, TableSet, make_ta
 # reduced-traffic mode: measured 1e-5 / 4e-4 voxel mean / max EPE against the reference at
 # min_level 2 and 1e-4 / 1.1e-2 at min_level 0 (tolerance 0.01 / 0.05).
 STATE_DTYPE = np.float64
+# Sweep order of the level solver used when a caller does not choose: SWEEP_LEXICOGRAPHIC (wavefront
+# schedule, reproduces the reference) or plan.SWEEP_REDBLACK (checkerboard; opt-in, not reference-exact).
+SWEEP = SWEEP_LEXICOGRAPHIC
 
 
 def _check(ctx, rc):
@@ -112,7 +115,7 @@ class Registration:
     """
 
     def __init__(self, shape, n_channels: int, params: FlowParams, max_batch: int = 1,
-                 interpolation_method: str = "cubic", sigma=None, sweep: int = SWEEP_LEXICOGRAPHIC,
+                 interpolation_method: str = "cubic", sigma=None, sweep: Optional[int] = None,
                  device: Optional[torch.device] = None, state_dtype=None):
         meth = str(getattr(interpolation_method, "value", interpolation_method)).lower()
         if meth not in ("cubic", "linear"):
@@ -121,7 +124,8 @@ class Registration:
         self.C = int(n_channels)
         self.max_batch = int(max_batch)
         self.plan = PlanHolder(self.shape, self.C, params, max_batch=max_batch,
-                               interp=3 if meth == "cubic" else 1, sigma=sigma, sweep=sweep,
+                               interp=3 if meth == "cubic" else 1, sigma=sigma,
+                               sweep=SWEEP if sweep is None else sweep,
                                state_dtype=STATE_DTYPE if state_dtype is None else state_dtype)
         self.ctx = Context(self.plan, device)
         self.device = self.ctx.device

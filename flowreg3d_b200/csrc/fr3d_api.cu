@@ -280,7 +280,7 @@ static int sor_frame_group(int B) { return B >= 2 ? 2 : 1; }
 template <class ST>
 static void run_sor_t(fr3d_ctx* c, const HPGeom& hp, int B, int C, const float* f1, const float* f2, int f2f32,
                       const double* Jpre, const double* uvw, const double* whp, double hz, double hy, double hx,
-                      const double* alpha, int T, int lag, const double* a_data)
+                      const double* alpha, int T, int lag, const double* a_data, int sweep)
 {
     Device& dev = c->dev;
     const int64_t np = hp.npad;
@@ -291,6 +291,7 @@ static void run_sor_t(fr3d_ctx* c, const HPGeom& hp, int B, int C, const float* 
     P.T = T;
     P.lag = lag;
     P.fg = sor_frame_group(B);
+    P.redblack = sweep == FR3D_SWEEP_REDBLACK;
     P.ax = alpha[0] / (hx * hx);
     P.ay = alpha[1] / (hy * hy);
     P.az = alpha[2] / (hz * hz);
@@ -326,11 +327,11 @@ static void run_sor(fr3d_ctx* c, int state_dtype, const HPGeom& hp, int B, int C
                     int f2f32, const double* Jpre, const double* uvw, const double* whp, double hz, double hy,
                     double hx, const double* alpha, int T, int lag, const double* a_data, int sweep)
 {
-    FR3D_REQUIRE(sweep == FR3D_SWEEP_LEXICOGRAPHIC, "sweep order %d is not implemented", sweep);
+    FR3D_REQUIRE(sweep == FR3D_SWEEP_LEXICOGRAPHIC || sweep == FR3D_SWEEP_REDBLACK, "unknown sweep order %d", sweep);
     if (state_dtype == FR3D_F64)
-        run_sor_t<double>(c, hp, B, C, f1, f2, f2f32, Jpre, uvw, whp, hz, hy, hx, alpha, T, lag, a_data);
+        run_sor_t<double>(c, hp, B, C, f1, f2, f2f32, Jpre, uvw, whp, hz, hy, hx, alpha, T, lag, a_data, sweep);
     else
-        run_sor_t<float>(c, hp, B, C, f1, f2, f2f32, Jpre, uvw, whp, hz, hy, hx, alpha, T, lag, a_data);
+        run_sor_t<float>(c, hp, B, C, f1, f2, f2f32, Jpre, uvw, whp, hz, hy, hx, alpha, T, lag, a_data, sweep);
 }
 
 // increments in solver storage -> natural planar float64 (B, 3, N)
@@ -404,7 +405,8 @@ int fr3d_create(fr3d_ctx** out, int device, const fr3d_plan* plan, void* stream)
             FR3D_REQUIRE(plan->a_smooth == 1.0,
                          "a_smooth != 1 (nonlinear smoothness) is not implemented in libfr3d");
             FR3D_REQUIRE(plan->interp == 3 || plan->interp == 1, "interp must be 3 (cubic) or 1 (linear)");
-            FR3D_REQUIRE(plan->sweep == FR3D_SWEEP_LEXICOGRAPHIC, "sweep order %d is not implemented", plan->sweep);
+            FR3D_REQUIRE(plan->sweep == FR3D_SWEEP_LEXICOGRAPHIC || plan->sweep == FR3D_SWEEP_REDBLACK,
+                         "unknown sweep order %d", plan->sweep);
             c->Z = plan->Z;
             c->Y = plan->Y;
             c->X = plan->X;

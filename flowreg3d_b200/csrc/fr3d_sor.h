@@ -59,6 +59,7 @@ template <class ST>
 struct SorParams {
     HPView g;
     int C, B, T, lag, fg; // fg: frames handled by one warp work item
+    int redblack;         // 0: waves q = s + 2t (lexicographic order); 1: waves q = 2t + colour (checkerboard)
     double ax, ay, az;    // alpha_{x,y,z} / h_{x,y,z}^2
     double a_data[FR3D_MAX_CHANNELS];
     const double* J;      // (B, C, 10, npad): J11,J22,J33,J44,J12,J13,J23,J14,J24,J34
@@ -166,17 +167,30 @@ struct SorTabs {
     const int32_t* start;
 };
 template <class ST>
-FR3D_HD int sor_num_waves(const SorParams<ST>& P) { return P.g.S + 2 * (P.T - 1); }
+FR3D_HD int sor_num_waves(const SorParams<ST>& P)
+{
+    return P.redblack ? 2 * P.T : P.g.S + 2 * (P.T - 1);
+}
 template <class ST>
 FR3D_HD SorWave sor_wave(const SorParams<ST>& P, const SorTabs& tb, int q)
 {
     const int S = P.g.S;
+    SorWave w;
+    if (P.redblack) {
+        // half-sweep q: every hyperplane of parity q & 1 (a voxel's six neighbours have the other parity)
+        const int c = q & 1;
+        w.s_lo = c;
+        w.nT = c < S ? (S - 1 - c) / 2 + 1 : 0;
+        w.base = 0;
+        w.chunks = w.nT > 0 ? tb.pe[c + 2 * (w.nT - 1)] : 0;
+        w.items = w.chunks * ((P.B + P.fg - 1) / P.fg);
+        return w;
+    }
     int tlo = q - (S - 1);
     tlo = tlo > 0 ? (tlo + 1) / 2 : 0;
     int thi = q / 2;
     if (thi > P.T - 1)
         thi = P.T - 1;
-    SorWave w;
     w.nT = thi >= tlo ? thi - tlo + 1 : 0;
     w.s_lo = q - 2 * thi;
     w.base = 0;
@@ -216,7 +230,7 @@ FR3D_HD SorLoc sor_locate(const SorParams<ST>& P, const SorTabs& tb, int q, cons
     }
     const int s = w.s_lo + 2 * lo;
     const int before = (s >= 2 ? tb.pe[s - 2] : 0) - w.base;
-    const int t = (q - s) >> 1;
+    const int t = P.redblack ? (q >> 1) : ((q - s) >> 1);
     SorLoc L;
     L.a = (int64_t)tb.start[s] + 32 * (f - before) + lane;
     const int64_t np = g.npad;
@@ -411,9 +425,16 @@ inline void sor_run_c(Device& dev, const SorParams<ST>& P, unsigned* bar, int pe
 #endif
 
 // peak number of warp items over all waves (host; pe_host = host copy of the chunk prefix)
-inline int sor_peak_items(int S, int T, int B, int fg, const int32_t* pe_host)
+inline int sor_peak_items(int S, int T, int B, int fg, const int32_t* pe_host, int redblack)
 {
     int peak = 0;
+    if (redblack) {
+        for (int c = 0; c < 2 && c < S; ++c) {
+            const int last = c + 2 * ((S - 1 - c) / 2);
+            peak = pe_host[last] > peak ? pe_host[last] : peak;
+        }
+        return peak * ((B + fg - 1) / fg);
+    }
     const int nw = S + 2 * (T - 1);
     for (int q = 0; q < nw; ++q) {
         int tlo = q - (S - 1);
@@ -438,7 +459,7 @@ inline void sor_run(Device& dev, const SorParams<ST>& P, unsigned* bar, const in
     (void)pe_host;
 #define FR3D_SOR_GO(C_) sor_run_c<ST, C_>(dev, P, bar)
 #else
-    const int peak = sor_peak_items(P.g.S, P.T, P.B, P.fg, pe_host);
+    const int peak = sor_peak_items(P.g.S, P.T, P.B, P.fg, pe_host, P.redblack);
 #define FR3D_SOR_GO(C_) sor_run_c<ST, C_>(dev, P, bar, peak)
 #endif
     switch (P.C) {

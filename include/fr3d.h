@@ -55,7 +55,9 @@ typedef enum {
 
 typedef enum {
     FR3D_SWEEP_LEXICOGRAPHIC = 0, /* hyperplane wavefront: reproduces the reference's sweep order */
-    FR3D_SWEEP_REDBLACK = 1       /* checkerboard; faster, outside the parity tolerance */
+    FR3D_SWEEP_REDBLACK = 1       /* checkerboard half-sweeps (even k+j+i first), du->dv->dw sequential inside a
+                                   * voxel; opt-in throughput mode: it does NOT reproduce the reference's
+                                   * lexicographic result (mean 0.015, max 0.4 voxel apart) */
 } fr3d_sweep;
 
 /* Per-axis resampling table of the fused Gauss (x) Keys-cubic resize

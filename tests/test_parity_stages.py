@@ -134,6 +134,25 @@ def test_solver_wavefront_reproduces_lexicographic_order(backend, golden):
         assert np.abs(d - np.moveaxis(o[INNER], -1, 0)).max() <= 1e-10
 
 
+def test_solver_redblack_mode_matches_redblack_restatement(backend, golden):
+    """The opt-in checkerboard sweep equals a CPU restatement with the same (non-reference) order, and
+    differs from the lexicographic result (which is why it is not the default)."""
+    from flowreg3d_b200 import core
+    from flowreg3d_b200.plan import SWEEP_REDBLACK
+    g = golden("solver")
+    J, wgt, uvw, ref, it, lag, _ = _solver_case(g, "c2")
+    d = core.sor_level(J, wgt, uvw, g["c2_alpha"], g["c2_h"], it, lag, g["c2_a_data"], sweep=SWEEP_REDBLACK)
+    Jr = [np.pad(np.moveaxis(J[:, q], 0, -1), ((1, 1), (1, 1), (1, 1), (0, 0))) for q in range(10)]
+    O.set_sweep_order(1)
+    try:
+        o = O.compute_flow_3d(Jr, g["c2_weight"], g["c2_u"], g["c2_v"], g["c2_w"], g["c2_alpha"], it, lag,
+                              g["c2_a_data"], 1.0, g["c2_h"][2], g["c2_h"][1], g["c2_h"][0])
+    finally:
+        O.set_sweep_order(0)
+    assert np.abs(d - np.moveaxis(o[INNER], -1, 0)).max() <= 1e-10
+    assert np.abs(d - ref).max() > 1e-6      # a different iteration, not the reference's
+
+
 def test_solver_rejects_nonlinear_smoothness(backend, golden):
     from flowreg3d_b200 import core, _lib
     g = golden("solver")
