@@ -89,8 +89,6 @@ class SequenceCorrector:
             self.world = torch.distributed.get_world_size(group)
             self.rank = torch.distributed.get_rank(group)
         fp = flow_params_from_options(options)
-        if fp.a_smooth != 1.0:
-            raise NotImplementedError("a_smooth != 1.0 (nonlinear smoothness term) is not implemented on the B200 path")
         mb = int(max_batch or options.buffer_size)
         kw = dict(interpolation_method=getattr(options, "interpolation_method", "cubic"), sigma=options.sigma)
         if int(streams) > 1 and mb > 1:

@@ -398,7 +398,7 @@ def get_displacement(fixed, moving, alpha=(2, 2, 2), update_lag=10, iterations=2
     """Drop-in for flowreg3d.core.optical_flow_3d.get_displacement (:319-542): dense 3-D flow of
     `moving` towards `fixed`, (Z,Y,X[,C]) arrays in, (Z,Y,X,3) float64 out, [...,0]=dx.
     `const_assumption` is accepted and ignored exactly as in the reference (gradient constancy is
-    hard-wired, :457).  a_smooth must be 1.0 on this path (nonlinear smoothness: NotImplementedError)."""
+    hard-wired, :457).  a_smooth != 1 selects the nonlinear smoothness term (psi_s recomputed every sweep)."""
     fixed = np.asarray(fixed)
     moving = np.asarray(moving)
     if fixed.ndim == 3:
@@ -406,8 +406,6 @@ def get_displacement(fixed, moving, alpha=(2, 2, 2), update_lag=10, iterations=2
         moving = moving[..., None]
     if fixed.ndim != 4 or fixed.shape != moving.shape:
         raise ValueError(f"fixed/moving must be (Z,Y,X) or (Z,Y,X,C) of equal shape, got {fixed.shape} / {moving.shape}")
-    if float(a_smooth) != 1.0:
-        raise NotImplementedError("a_smooth != 1.0 (nonlinear smoothness term) is not implemented on the B200 path")
     if isinstance(alpha, (int, float)):
         alpha = (alpha,) * 3
     Z, Y, X, Cn = fixed.shape

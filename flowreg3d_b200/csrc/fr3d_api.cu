@@ -36,7 +36,7 @@ struct HPGeom {
     int p = 0, m = 0, n = 0, S = 0;
     int32_t npad = 0;
     std::vector<int32_t> pe_host;
-    Buf<int32_t> rowbase, start, pe, nbr, perm;
+    Buf<int32_t> rowbase, start, pe, pe4, nbr, perm;
     HPView view() const
     {
         return HPView{p, m, n, S, npad, rowbase.p, start.p, pe.p, nbr.p, perm.p};
@@ -72,6 +72,10 @@ struct HPGeom {
         rowbase.upload(dev, rb.data(), rb.size());
         start.upload(dev, st.data(), st.size());
         pe.upload(dev, pe_host.data(), pe_host.size());
+        std::vector<int32_t> p4(S);
+        for (int s = 0; s < S; ++s)
+            p4[s] = (st[s + 1] - st[s]) / 32 + (s >= 4 ? p4[s - 4] : 0);
+        pe4.upload(dev, p4.data(), p4.size());
         nbr.ensure(dev, (size_t)6 * npad);
         perm.ensure(dev, (size_t)npad);
         launch(dev, HPFillK{nbr.p, perm.p, npad}, npad);
@@ -117,7 +121,8 @@ struct fr3d_ctx {
     // workspaces (grow-only)
     Buf<float> t1, t2, f2, tmp, fscr;
     Buf<double> uvw_a, uvw_b, coef, J, AB, dnat, g1, g2, wnat;
-    Buf<char> L, d; // (B, npad) Vec4 of the state dtype
+    Buf<char> L, d, U, dold; // (B, npad) Vec4 of the state dtype
+    Buf<double> psi_c, psi_r;
     Buf<unsigned> bar;
     DevTable stage_tab[3];
     std::unique_ptr<HPGeom> stage_hp; // geometry cache of fr3d_sor_level
@@ -280,7 +285,7 @@ static int sor_frame_group(int B) { return B >= 2 ? 2 : 1; }
 template <class ST>
 static void run_sor_t(fr3d_ctx* c, const HPGeom& hp, int B, int C, const float* f1, const float* f2, int f2f32,
                       const double* Jpre, const double* uvw, const double* whp, double hz, double hy, double hx,
-                      const double* alpha, int T, int lag, const double* a_data, int sweep)
+                      const double* alpha, int T, int lag, const double* a_data, int sweep, double a_smooth)
 {
     Device& dev = c->dev;
     const int64_t np = hp.npad;
@@ -305,6 +310,22 @@ static void run_sor_t(fr3d_ctx* c, const HPGeom& hp, int B, int C, const float* 
     P.L = (Vec4<ST>*)c->L.ensure(dev, (size_t)B * np * sizeof(Vec4<ST>));
     P.d = (Vec4<ST>*)c->d.ensure(dev, (size_t)B * np * sizeof(Vec4<ST>));
     P.AB = c->AB.ensure(dev, (size_t)B * 9 * np);
+    P.a_smooth = a_smooth;
+    P.hx = hx;
+    P.hy = hy;
+    P.hz = hz;
+    P.pe4 = hp.pe4.p;
+    P.U = nullptr;
+    P.dold = nullptr;
+    P.psi_c = nullptr;
+    P.psi_r = nullptr;
+    if (a_smooth != 1.0) {
+        FR3D_REQUIRE(sweep == FR3D_SWEEP_LEXICOGRAPHIC, "the red-black sweep is only implemented for a_smooth == 1");
+        P.U = (Vec4<ST>*)c->U.ensure(dev, (size_t)B * np * sizeof(Vec4<ST>));
+        P.dold = (Vec4<ST>*)c->dold.ensure(dev, (size_t)B * np * sizeof(Vec4<ST>));
+        P.psi_c = c->psi_c.ensure(dev, (size_t)B * np);
+        P.psi_r = c->psi_r.ensure(dev, (size_t)B * 3 * np);
+    }
     AssembleK<ST> as;
     as.f1 = f1;
     as.f2 = f2;
@@ -312,6 +333,8 @@ static void run_sor_t(fr3d_ctx* c, const HPGeom& hp, int B, int C, const float* 
     as.J = Jpre ? nullptr : J;
     as.L = const_cast<Vec4<ST>*>(P.L);
     as.d = P.d;
+    as.U = const_cast<Vec4<ST>*>(P.U);
+    as.dold = P.dold;
     as.hp = P.g;
     as.g = MTGeom{hp.p, hp.m, hp.n, hz, hy, hx, f2f32};
     as.B = B;
@@ -325,13 +348,13 @@ static void run_sor_t(fr3d_ctx* c, const HPGeom& hp, int B, int C, const float* 
 
 static void run_sor(fr3d_ctx* c, int state_dtype, const HPGeom& hp, int B, int C, const float* f1, const float* f2,
                     int f2f32, const double* Jpre, const double* uvw, const double* whp, double hz, double hy,
-                    double hx, const double* alpha, int T, int lag, const double* a_data, int sweep)
+                    double hx, const double* alpha, int T, int lag, const double* a_data, int sweep, double a_smooth)
 {
     FR3D_REQUIRE(sweep == FR3D_SWEEP_LEXICOGRAPHIC || sweep == FR3D_SWEEP_REDBLACK, "unknown sweep order %d", sweep);
     if (state_dtype == FR3D_F64)
-        run_sor_t<double>(c, hp, B, C, f1, f2, f2f32, Jpre, uvw, whp, hz, hy, hx, alpha, T, lag, a_data, sweep);
+        run_sor_t<double>(c, hp, B, C, f1, f2, f2f32, Jpre, uvw, whp, hz, hy, hx, alpha, T, lag, a_data, sweep, a_smooth);
     else
-        run_sor_t<float>(c, hp, B, C, f1, f2, f2f32, Jpre, uvw, whp, hz, hy, hx, alpha, T, lag, a_data, sweep);
+        run_sor_t<float>(c, hp, B, C, f1, f2, f2f32, Jpre, uvw, whp, hz, hy, hx, alpha, T, lag, a_data, sweep, a_smooth);
 }
 
 // increments in solver storage -> natural planar float64 (B, 3, N)
@@ -402,8 +425,9 @@ int fr3d_create(fr3d_ctx** out, int device, const fr3d_plan* plan, void* stream)
             FR3D_REQUIRE(plan->max_batch >= 1, "max_batch must be >= 1");
             FR3D_REQUIRE(plan->n_levels >= 1 && plan->n_levels <= FR3D_MAX_LEVELS && plan->levels, "bad level list");
             FR3D_REQUIRE(plan->iterations >= 1 && plan->update_lag >= 1, "iterations/update_lag must be >= 1");
-            FR3D_REQUIRE(plan->a_smooth == 1.0,
-                         "a_smooth != 1 (nonlinear smoothness) is not implemented in libfr3d");
+            FR3D_REQUIRE(plan->a_smooth > 0.0, "a_smooth must be positive");
+            FR3D_REQUIRE(plan->a_smooth == 1.0 || plan->sweep == FR3D_SWEEP_LEXICOGRAPHIC,
+                         "the red-black sweep is only implemented for a_smooth == 1");
             FR3D_REQUIRE(plan->interp == 3 || plan->interp == 1, "interp must be 3 (cubic) or 1 (linear)");
             FR3D_REQUIRE(plan->sweep == FR3D_SWEEP_LEXICOGRAPHIC || plan->sweep == FR3D_SWEEP_REDBLACK,
                          "unknown sweep order %d", plan->sweep);
@@ -682,7 +706,7 @@ int fr3d_get_displacement(fr3d_ctx* ctx, const float* moving, const float* uvw_i
             f2f32 = 1; // numpy keeps the float32 warp output in float32 through its derivatives
         }
         run_sor(_c, _c->state_dtype, L.hp, B, C, L.f1.p, warped, f2f32, nullptr, ucur, L.whp.p, L.hz, L.hy, L.hx,
-                L.alpha, _c->iterations, _c->update_lag, _c->a_data, _c->sweep);
+                L.alpha, _c->iterations, _c->update_lag, _c->a_data, _c->sweep, _c->a_smooth);
         sor_result(_c, _c->state_dtype, L.hp, B, dnat);
         if (L.median)
             launch_occ2(dev, Median5PairK{dnat, ucur, ucur, p, m, n, (n + 1) / 2}, (int64_t)B * 3 * p * m * ((n + 1) / 2)); // (:517-529)
@@ -809,7 +833,7 @@ int fr3d_sor_level(fr3d_ctx* ctx, const double* J, const double* weight, const d
     FR3D_REQUIRE(J && weight && uvw && alpha && a_data && d, "null argument");
     FR3D_REQUIRE(p > 0 && m > 0 && n > 0 && C >= 1 && C <= FR3D_MAX_CHANNELS, "bad shape");
     FR3D_REQUIRE(iterations >= 1 && update_lag >= 1, "iterations/update_lag must be >= 1");
-    FR3D_REQUIRE(a_smooth == 1.0, "a_smooth != 1 (nonlinear smoothness) is not implemented in libfr3d");
+    FR3D_REQUIRE(a_smooth > 0.0, "a_smooth must be positive");
     FR3D_REQUIRE(state_dtype == FR3D_F32 || state_dtype == FR3D_F64, "state_dtype must be FR3D_F32 or FR3D_F64");
     if (!_c->stage_hp || _c->stage_hp->p != p || _c->stage_hp->m != m || _c->stage_hp->n != n) {
         _c->stage_hp.reset(new HPGeom());
@@ -822,7 +846,7 @@ int fr3d_sor_level(fr3d_ctx* ctx, const double* J, const double* weight, const d
     launch(_c->dev, ToHPK<double>{J, Js, hp.view()}, (int64_t)C * 10 * np);
     launch(_c->dev, ToHPK<double>{weight, ws, hp.view()}, (int64_t)C * np);
     run_sor(_c, state_dtype, hp, 1, C, nullptr, nullptr, 0, Js, uvw, ws, hz, hy, hx, alpha, iterations, update_lag,
-            a_data, sweep);
+            a_data, sweep, a_smooth);
     sor_result(_c, state_dtype, hp, 1, d);
     FR3D_API_END()
 }

@@ -900,6 +900,8 @@ struct AssembleK {
     double* J;         // (B, C, 10, npad) or null
     Vec4<ST>* L;       // (B, npad)
     Vec4<ST>* d;       // (B, npad)
+    Vec4<ST>* U;       // (B, npad) u, v, w in solver storage, or null (nonlinear smoothness only)
+    Vec4<ST>* dold;    // (B, npad) zero-initialised, or null
     HPView hp;
     MTGeom g;
     int B, C;
@@ -912,9 +914,13 @@ struct AssembleK {
         Vec4<ST> zero;
         zero.x = zero.y = zero.z = zero.w = (ST)0;
         d[(int64_t)b * np + a] = zero;
+        if (dold)
+            dold[(int64_t)b * np + a] = zero;
         const int32_t nat = hp.perm[a];
         if (nat < 0) {
             L[(int64_t)b * np + a] = zero;
+            if (U)
+                U[(int64_t)b * np + a] = zero;
             return;
         }
         const int i = nat % g.n;
@@ -933,10 +939,11 @@ struct AssembleK {
         const int km = clampi(k - 1, 0, g.p - 1), kp = clampi(k + 1, 0, g.p - 1);
         const int jm = clampi(j - 1, 0, g.m - 1), jp = clampi(j + 1, 0, g.m - 1);
         const int im_ = clampi(i - 1, 0, g.n - 1), ip = clampi(i + 1, 0, g.n - 1);
-        double Lq[3];
+        double Lq[3], Uq[3];
         for (int q = 0; q < 3; ++q) {
             const double* f = uvw + ((int64_t)b * 3 + q) * N;
             const double c0 = f[((int64_t)k * g.m + j) * g.n + i];
+            Uq[q] = c0;
             const double lx = f[((int64_t)k * g.m + j) * g.n + ip] + f[((int64_t)k * g.m + j) * g.n + im_] - 2.0 * c0;
             const double ly = f[((int64_t)k * g.m + jp) * g.n + i] + f[((int64_t)k * g.m + jm) * g.n + i] - 2.0 * c0;
             const double lz = f[((int64_t)kp * g.m + j) * g.n + i] + f[((int64_t)km * g.m + j) * g.n + i] - 2.0 * c0;
@@ -948,6 +955,14 @@ struct AssembleK {
         Lv.z = (ST)Lq[2];
         Lv.w = (ST)0;
         L[(int64_t)b * np + a] = Lv;
+        if (U) {
+            Vec4<ST> Uv;
+            Uv.x = (ST)Uq[0];
+            Uv.y = (ST)Uq[1];
+            Uv.z = (ST)Uq[2];
+            Uv.w = (ST)0;
+            U[(int64_t)b * np + a] = Uv;
+        }
     }
 };
 

@@ -67,12 +67,20 @@ struct SorParams {
     const Vec4<ST>* L;    // (B, npad): alpha-weighted Laplacian of u, v, w
     Vec4<ST>* d;          // (B, npad): du, dv, dw (zero-initialised)
     double* AB;           // (B, 9, npad): 1/den_u, 1/den_v, 1/den_w, A12, A13, A23, b1, b2, b3
+                          // (nonlinear smoothness: A11, A22, A33 themselves -- the denominator changes per sweep)
+    // nonlinear smoothness term (a_smooth != 1), see "Nonlinear smoothness" below
+    double a_smooth, hx, hy, hz;
+    const int32_t* pe4;   // (S): chunks in hyperplanes s, s-4, s-8, ...
+    const Vec4<ST>* U;    // (B, npad): u, v, w
+    Vec4<ST>* dold;       // (B, npad): increments before the voxel's latest update
+    double* psi_c;        // (B, npad): psi_s at the voxel
+    double* psi_r;        // (B, 3, npad): psi_s at the ring voxel next to a boundary voxel along x / y / z
 };
 
 // psi refresh + pre-combination for one voxel (sweeps with t % lag == 0)
 template <int C>
 FR3D_HD void sor_refresh(const double* a_data, const double* Jb, const double* wgt, int64_t np, int64_t a,
-                         double du, double dv, double dw, double den0, double* A)
+                         double du, double dv, double dw, double den0, double* A, bool inv_diag = true)
 {
     double S[9];
 #pragma unroll
@@ -110,7 +118,7 @@ FR3D_HD void sor_refresh(const double* a_data, const double* Jb, const double* w
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
         const double den = den0 + S[q];
-        A[q] = den != 0.0 ? 1.0 / den : 0.0; // reference: denom == 0 -> update is 0
+        A[q] = inv_diag ? (den != 0.0 ? 1.0 / den : 0.0) : S[q]; // reference: denom == 0 -> update is 0
     }
 #pragma unroll
     for (int q = 3; q < 9; ++q)
@@ -317,10 +325,230 @@ FR3D_HD void sor_process(const SorParams<ST>& P, const SorLoc& L)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Nonlinear smoothness (a_smooth != 1; level_solver_3d.py:262-311, 352-355, 400-493).
+// The reference recomputes psi_s = a (|grad(u+du)|^2 + 1e-5)^(a-1) over the whole ring-padded field at
+// the start of EVERY sweep t from the increments after sweep t-1 -- and, because set_boundary_3d runs
+// after it, from ring values that still hold the state after sweep t-2 -- and weights each face by
+// 0.5 (psi_s[c] + psi_s[nb]) alpha / h^2.  psi_s of a voxel therefore depends on its six neighbours'
+// previous-sweep values, which stretches the wave schedule to
+//      psi task (voxel on hyperplane s, sweep t)   -> wave s + 4t
+//      sweep task (same voxel, sweep t)            -> wave s + 4t + 2
+// (every input of either task is final at least one wave earlier, and nothing it reads is overwritten
+// before it ran).  `dold` keeps each voxel's increments from before its latest update = the stale ring
+// values the reference sees.
+struct SorSet {       // hyperplanes s_lo, s_lo+4, ... of one task kind in one wave
+    int s_lo, nT, base, chunks;
+};
+template <class ST>
+FR3D_HD int sor_nl_num_waves(const SorParams<ST>& P) { return P.g.S + 4 * (P.T - 1) + 2; }
+template <class ST>
+FR3D_HD SorSet sor_nl_set(const SorParams<ST>& P, int qq) // tasks with s + 4t == qq
+{
+    SorSet w{0, 0, 0, 0};
+    if (qq < 0)
+        return w;
+    const int S = P.g.S;
+    int tlo = qq - (S - 1);
+    tlo = tlo > 0 ? (tlo + 3) / 4 : 0;
+    int thi = qq / 4;
+    if (thi > P.T - 1)
+        thi = P.T - 1;
+    if (thi < tlo)
+        return w;
+    w.nT = thi - tlo + 1;
+    w.s_lo = qq - 4 * thi;
+    w.base = w.s_lo >= 4 ? P.pe4[w.s_lo - 4] : 0;
+    w.chunks = P.pe4[qq - 4 * tlo] - w.base;
+    return w;
+}
+// slot of lane `lane` of chunk f of the set; returns the hyperplane through s
+template <class ST>
+FR3D_HD int64_t sor_nl_slot(const SorParams<ST>& P, const SorSet& w, int f, int lane, int& s)
+{
+    int lo = 0, hi = w.nT - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (P.pe4[w.s_lo + 4 * mid] - w.base > f)
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    s = w.s_lo + 4 * lo;
+    const int before = (s >= 4 ? P.pe4[s - 4] : 0) - w.base;
+    return (int64_t)P.g.start[s] + 32 * (f - before) + lane;
+}
+
+template <class ST>
+struct V3 {
+    double x, y, z;
+};
+template <class ST>
+FR3D_HD V3<ST> v3add(const Vec4<ST>& a, const Vec4<ST>& b)
+{
+    return V3<ST>{(double)a.x + (double)b.x, (double)a.y + (double)b.y, (double)a.z + (double)b.z};
+}
+
+// psi_s at voxel a and at the ring voxels next to it, frame b.
+template <class ST>
+FR3D_HD void sor_nl_psi(const SorParams<ST>& P, int64_t a, int b)
+{
+    const int64_t np = P.g.npad;
+    const int nb[6] = {P.g.nbr[a], P.g.nbr[np + a], P.g.nbr[2 * np + a], P.g.nbr[3 * np + a], P.g.nbr[4 * np + a],
+                       P.g.nbr[5 * np + a]};
+    if (nb[0] < 0)
+        return; // pad slot
+    const Vec4<ST>* d = P.d + (int64_t)b * np;
+    const Vec4<ST>* dold = P.dold + (int64_t)b * np;
+    const Vec4<ST>* U = P.U + (int64_t)b * np;
+    const Vec4<ST> Uc = ld4_cg(U + a);
+    const V3<ST> cur = v3add(Uc, ld4_cg(d + a));       // u + du after sweep t-1
+    const V3<ST> ring = v3add(Uc, ld4_cg(dold + a));   // what a ring copy of this voxel holds: state after sweep t-2
+    V3<ST> uu[6], ro[6]; // neighbour values as the interior sees them / as the ring holds them (state t-2)
+    bool in[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        in[q] = nb[q] != (int)a;
+        if (in[q]) {
+            const Vec4<ST> Un = ld4_cg(U + nb[q]);
+            uu[q] = v3add(Un, ld4_cg(d + nb[q]));
+            ro[q] = v3add(Un, ld4_cg(dold + nb[q]));
+        } else {
+            uu[q] = ring;
+            ro[q] = ring;
+        }
+    }
+    const double h2[3] = {2.0 * P.hx, 2.0 * P.hy, 2.0 * P.hz};
+    double g = 0.0;
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+        const double dx = (uu[ax + 3].x - uu[ax].x) / h2[ax], dy = (uu[ax + 3].y - uu[ax].y) / h2[ax],
+                     dz = (uu[ax + 3].z - uu[ax].z) / h2[ax];
+        g = fma(dx, dx, fma(dy, dy, fma(dz, dz, g)));
+    }
+    if (g < 0.0)
+        g = 0.0;
+    const double am1 = P.a_smooth - 1.0;
+    P.psi_c[(int64_t)b * np + a] = P.a_smooth * exp(am1 * log(g + 1e-5));
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+        if (in[ax] && in[ax + 3])
+            continue;
+        // ring voxel beyond this voxel along ax: one-sided difference along ax (this voxel's current value
+        // against the ring's stale copy), central differences of stale ring copies along the other two axes
+        double gr = 0.0;
+        {
+            const double dx = (cur.x - ring.x) / h2[ax], dy = (cur.y - ring.y) / h2[ax], dz = (cur.z - ring.z) / h2[ax];
+            gr = fma(dx, dx, fma(dy, dy, fma(dz, dz, gr)));
+        }
+#pragma unroll
+        for (int bx = 0; bx < 3; ++bx) {
+            if (bx == ax)
+                continue;
+            const double dx = (ro[bx + 3].x - ro[bx].x) / h2[bx], dy = (ro[bx + 3].y - ro[bx].y) / h2[bx],
+                         dz = (ro[bx + 3].z - ro[bx].z) / h2[bx];
+            gr = fma(dx, dx, fma(dy, dy, fma(dz, dz, gr)));
+        }
+        if (gr < 0.0)
+            gr = 0.0;
+        P.psi_r[((int64_t)b * 3 + ax) * np + a] = P.a_smooth * exp(am1 * log(gr + 1e-5));
+    }
+}
+
+// One sweep update of voxel a, frame b, sweep t (nonlinear smoothness).
+template <class ST, int C>
+FR3D_HD void sor_nl_update(const SorParams<ST>& P, int64_t a, int b, int t)
+{
+    const int64_t np = P.g.npad;
+    const int nb[6] = {P.g.nbr[a], P.g.nbr[np + a], P.g.nbr[2 * np + a], P.g.nbr[3 * np + a], P.g.nbr[4 * np + a],
+                       P.g.nbr[5 * np + a]};
+    if (nb[0] < 0)
+        return;
+    Vec4<ST>* d = P.d + (int64_t)b * np;
+    const Vec4<ST>* U = P.U + (int64_t)b * np;
+    const double* pc = P.psi_c + (int64_t)b * np;
+    const double* pr = P.psi_r + (int64_t)b * 3 * np;
+    const Vec4<ST> own = ld4_cg(d + a);
+    const Vec4<ST> Uc = ld4_cg(U + a);
+    const double psc = FR3D_LDCG(pc + a);
+    const double aw[3] = {P.ax, P.ay, P.az};
+    double num[3] = {0.0, 0.0, 0.0}, den = 0.0;
+    const int order[6] = {2, 5, 1, 4, 0, 3}; // z-, z+, y-, y+, x-, x+ (level_solver_3d.py:400-493)
+#pragma unroll
+    for (int o = 0; o < 6; ++o) {
+        const int q = order[o], ax = q % 3;
+        const bool in = nb[q] != (int)a;
+        const double psn = in ? FR3D_LDCG(pc + nb[q]) : FR3D_LDCG(pr + (int64_t)ax * np + a);
+        const double tmp = 0.5 * (psc + psn) * aw[ax];
+        const Vec4<ST> dn = in ? ld4_cg(d + nb[q]) : own;
+        const Vec4<ST> Un = in ? ld4_cg(U + nb[q]) : Uc;
+        num[0] = fma(tmp, ((double)Un.x + (double)dn.x) - (double)Uc.x, num[0]);
+        num[1] = fma(tmp, ((double)Un.y + (double)dn.y) - (double)Uc.y, num[1]);
+        num[2] = fma(tmp, ((double)Un.z + (double)dn.z) - (double)Uc.z, num[2]);
+        den += tmp;
+    }
+    double A[9];
+    double* AB = P.AB + (int64_t)b * 9 * np + a;
+    const double du = (double)own.x, dv = (double)own.y, dw = (double)own.z;
+    if ((t % P.lag) == 0) {
+        sor_refresh<C>(P.a_data, P.J + (int64_t)b * C * 10 * np, P.wgt, np, a, du, dv, dw, 0.0, A, false);
+#pragma unroll
+        for (int e = 0; e < 9; ++e)
+            FR3D_STCG(AB + e * np, A[e]);
+    } else {
+#pragma unroll
+        for (int e = 0; e < 9; ++e)
+            A[e] = FR3D_LDCG(AB + e * np);
+    }
+    const double om = FR3D_SOR_OMEGA, om1 = 1.0 - FR3D_SOR_OMEGA;
+    const double den_u = den + A[0], den_v = den + A[1], den_w = den + A[2];
+    const double u1 = den_u != 0.0 ? (num[0] - fma(A[3], dv, fma(A[4], dw, A[6]))) / den_u : 0.0;
+    const double du_n = fma(om, u1, om1 * du);
+    const double v1 = den_v != 0.0 ? (num[1] - fma(A[3], du_n, fma(A[5], dw, A[7]))) / den_v : 0.0;
+    const double dv_n = fma(om, v1, om1 * dv);
+    const double w1 = den_w != 0.0 ? (num[2] - fma(A[4], du_n, fma(A[5], dv_n, A[8]))) / den_w : 0.0;
+    const double dw_n = fma(om, w1, om1 * dw);
+    Vec4<ST> o;
+    o.x = (ST)du_n;
+    o.y = (ST)dv_n;
+    o.z = (ST)dw_n;
+    o.w = (ST)0;
+    st4_cg(P.dold + (int64_t)b * np + a, own);
+    st4_cg(d + a, o);
+}
+
+// Warp item `item` of wave q: psi items first, then sweep items; each for all frames.
+template <class ST, int C>
+FR3D_HD void sor_nl_item(const SorParams<ST>& P, int q, const SorSet& wp, const SorSet& ws, int item, int lane)
+{
+    int s;
+    if (item < wp.chunks) {
+        const int64_t a = sor_nl_slot(P, wp, item, lane, s);
+        for (int b = 0; b < P.B; ++b)
+            sor_nl_psi(P, a, b);
+    } else {
+        const int64_t a = sor_nl_slot(P, ws, item - wp.chunks, lane, s);
+        const int t = (q - 2 - s) >> 2;
+        for (int b = 0; b < P.B; ++b)
+            sor_nl_update<ST, C>(P, a, b, t);
+    }
+}
+
 #ifdef FR3D_EMU
 template <class ST, int C>
 inline void sor_run_c(Device& dev, const SorParams<ST>& P, unsigned*)
 {
+    if (P.a_smooth != 1.0) {
+        const int nw = sor_nl_num_waves(P);
+        for (int q = 0; q < nw; ++q) {
+            const SorSet wp = sor_nl_set(P, q), ws = sor_nl_set(P, q - 2);
+            for (int item = 0; item < wp.chunks + ws.chunks; ++item)
+                for (int lane = 0; lane < 32; ++lane)
+                    sor_nl_item<ST, C>(P, q, wp, ws, item, lane);
+        }
+        dev.launches++;
+        return;
+    }
     const int nw = sor_num_waves(P);
     const SorTabs tb{P.g.pe, P.g.start};
     for (int q = 0; q < nw; ++q) {
@@ -394,9 +622,54 @@ fr3d_sor_wavefront(const SorParams<ST> P, unsigned* bar, int tabs_in_smem)
     }
 }
 
+// Nonlinear-smoothness variant: psi and sweep tasks of a wave, one grid barrier per wave.
+template <class ST, int C>
+__global__ void __launch_bounds__(FR3D_SOR_THREADS, 2) fr3d_sor_wavefront_nl(const SorParams<ST> P, unsigned* bar)
+{
+    const int nw = sor_nl_num_waves(P);
+    const int wpb = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned gen = 0;
+    for (int q = 0; q < nw; ++q) {
+        const SorSet wp = sor_nl_set(P, q), ws = sor_nl_set(P, q - 2);
+        const int items = wp.chunks + ws.chunks;
+        for (int item = blockIdx.x * wpb + warp; item < items; item += gridDim.x * wpb)
+            sor_nl_item<ST, C>(P, q, wp, ws, item, lane);
+        ++gen;
+        fr3d_grid_barrier(bar, gen * gridDim.x);
+    }
+}
+
+template <class ST, int C>
+inline void sor_run_nl(Device& dev, const SorParams<ST>& P, unsigned* bar)
+{
+    int per_sm = 0;
+    FR3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fr3d_sor_wavefront_nl<ST, C>,
+                                                            FR3D_SOR_THREADS, 0));
+    FR3D_REQUIRE(per_sm >= 1, "SOR kernel does not fit on an SM");
+    const int wpb = FR3D_SOR_THREADS / 32;
+    // an upper bound of the busiest wave: every chunk of one residue class mod 4, twice
+    int64_t want = ((int64_t)P.g.npad / 32 / 2 + wpb) / wpb;
+    int grid = dev.sm_count * per_sm;
+    if (want < grid)
+        grid = (int)(want < 1 ? 1 : want);
+    FR3D_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), dev.stream));
+    SorParams<ST> Pc = P;
+    void* args[] = {(void*)&Pc, (void*)&bar};
+    dev.span_begin("fr3d_sor_wavefront_nl");
+    FR3D_CUDA(cudaLaunchCooperativeKernel((void*)fr3d_sor_wavefront_nl<ST, C>, dim3(grid), dim3(FR3D_SOR_THREADS),
+                                          args, 0, dev.stream));
+    dev.span_end();
+    dev.launches++;
+}
+
 template <class ST, int C>
 inline void sor_run_c(Device& dev, const SorParams<ST>& P, unsigned* bar, int peak_items)
 {
+    if (P.a_smooth != 1.0) {
+        sor_run_nl<ST, C>(dev, P, bar);
+        return;
+    }
     const size_t smem = (size_t)(2 * P.g.S + 1) * sizeof(int32_t);
     const int tabs_in_smem = smem <= 40 * 1024;
     const size_t dyn = tabs_in_smem ? smem : 0;

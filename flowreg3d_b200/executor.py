@@ -93,8 +93,6 @@ class B200Executor3D(_Base):
             raise NotImplementedError("cc_initialization (rigid cross-correlation pre-alignment) is not "
                                       "implemented on the B200 path")
         fp, weight = flow_params_from_dict(fp_all)
-        if fp.a_smooth != 1.0:
-            raise NotImplementedError("a_smooth != 1.0 (nonlinear smoothness term) is not implemented on the B200 path")
         reg = self._registration((Z, Y, X), Cn, fp, interpolation_method)
         self._ensure_reference(reg, reference_proc, reference_raw, weight)
         registered = np.empty_like(batch)

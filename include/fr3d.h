@@ -87,7 +87,8 @@ typedef struct {
     fr3d_axis_table to_full[3];   /* (x, y, z) finest solved level -> full resolution; P = 0 if min_level == 0 */
     int32_t iterations, update_lag;
     double a_data[FR3D_MAX_CHANNELS];
-    double a_smooth;              /* only 1.0 (linear smoothness) is implemented; else FR3D_ERR_ARG */
+    double a_smooth;              /* 1.0: linear smoothness; otherwise the nonlinear term psi_s = a (|grad|^2 + 1e-5)^(a-1),
+                                   * recomputed every sweep (level_solver_3d.py:262-311); lexicographic sweep only */
     int32_t sweep;                /* fr3d_sweep */
     int32_t interp;               /* compensation warp: 3 = cubic B-spline, 1 = trilinear */
     int32_t state_dtype;          /* solver state storage (du,dv,dw and the constant Laplacian term):

@@ -51,8 +51,10 @@ def test_get_displacement_argument_handling(backend, golden):
     assert np.array_equal(f3, f4)                              # const_assumption is ignored, like the reference
     o = O.get_displacement(fx, mv, **{**kw, "alpha": (0.3,) * 3})
     assert epe_stats(f3, o)[1] <= 1e-6
-    with pytest.raises(NotImplementedError):
-        F.get_displacement(fx, mv, a_smooth=0.5)
+    # the reference's own defaults (alpha 2, 20 iterations, lag 10, a_smooth 0.5 = nonlinear smoothness)
+    fd = F.get_displacement(fx, mv)
+    mean, mx = epe_stats(fd, O.get_displacement(fx, mv))
+    assert mean <= 1e-6 and mx <= 1e-4, (mean, mx)
     with pytest.raises(ValueError):
         F.get_displacement(fx, mv[:-1], **kw)
 
