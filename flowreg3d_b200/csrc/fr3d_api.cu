@@ -126,6 +126,13 @@ struct fr3d_ctx {
     Buf<unsigned> bar;
     DevTable stage_tab[3];
     std::unique_ptr<HPGeom> stage_hp; // geometry cache of fr3d_sor_level
+    // level-by-level execution state (fr3d_level_begin / _sweeps / _end / fr3d_flow_finish)
+    int run_B = 0, run_level = -1;    // frames of the run, level whose solve is open (-1: none)
+    int run_done = -1;                // last level completed
+    bool run_flip = false;            // which of uvw_a / uvw_b holds the current flow
+    SorParams<float> spf;
+    SorParams<double> spd;
+    const HPGeom* sp_hp = nullptr;
 };
 
 static thread_local std::string g_create_err;
@@ -283,13 +290,22 @@ static int sor_frame_group(int B) { return B >= 2 ? 2 : 1; }
 // Level solve in solver storage: assembles J (when f1/f2 are given; otherwise Jpre is used as is), the
 // Laplacian term L and zero increments, then runs the wavefront solver.  Result in c->d.
 template <class ST>
-static void run_sor_t(fr3d_ctx* c, const HPGeom& hp, int B, int C, const float* f1, const float* f2, int f2f32,
-                      const double* Jpre, const double* uvw, const double* whp, double hz, double hy, double hx,
-                      const double* alpha, int T, int lag, const double* a_data, int sweep, double a_smooth)
+static SorParams<ST>& sor_params(fr3d_ctx* c);
+template <>
+SorParams<float>& sor_params<float>(fr3d_ctx* c) { return c->spf; }
+template <>
+SorParams<double>& sor_params<double>(fr3d_ctx* c) { return c->spd; }
+
+// Prepare a level solve in solver storage: assembles J (when f1/f2 are given; otherwise Jpre is used as
+// is), the Laplacian term L and zero increments; the parameters are kept in the context.
+template <class ST>
+static void sor_prepare_t(fr3d_ctx* c, const HPGeom& hp, int B, int C, const float* f1, const float* f2, int f2f32,
+                          const double* Jpre, const double* uvw, const double* whp, double hz, double hy, double hx,
+                          const double* alpha, int T, int lag, const double* a_data, int sweep, double a_smooth)
 {
     Device& dev = c->dev;
     const int64_t np = hp.npad;
-    SorParams<ST> P;
+    SorParams<ST>& P = sor_params<ST>(c);
     P.g = hp.view();
     P.C = C;
     P.B = B;
@@ -297,6 +313,10 @@ static void run_sor_t(fr3d_ctx* c, const HPGeom& hp, int B, int C, const float* 
     P.lag = lag;
     P.fg = sor_frame_group(B);
     P.redblack = sweep == FR3D_SWEEP_REDBLACK;
+    P.t_begin = 0;
+    P.t_end = T;
+    P.q_begin = 0;
+    P.q_end = sor_num_waves(P);
     P.ax = alpha[0] / (hx * hx);
     P.ay = alpha[1] / (hy * hy);
     P.az = alpha[2] / (hz * hz);
@@ -343,18 +363,57 @@ static void run_sor_t(fr3d_ctx* c, const HPGeom& hp, int B, int C, const float* 
     as.ay = P.ay;
     as.az = P.az;
     launch_occ2(dev, as, (int64_t)B * np);
-    sor_run(dev, P, c->bar.ensure(dev, 4), hp.pe_host.data());
+    c->sp_hp = &hp;
+}
+
+static void sor_prepare(fr3d_ctx* c, int state_dtype, const HPGeom& hp, int B, int C, const float* f1, const float* f2,
+                        int f2f32, const double* Jpre, const double* uvw, const double* whp, double hz, double hy,
+                        double hx, const double* alpha, int T, int lag, const double* a_data, int sweep, double a_smooth)
+{
+    FR3D_REQUIRE(sweep == FR3D_SWEEP_LEXICOGRAPHIC || sweep == FR3D_SWEEP_REDBLACK, "unknown sweep order %d", sweep);
+    if (state_dtype == FR3D_F64)
+        sor_prepare_t<double>(c, hp, B, C, f1, f2, f2f32, Jpre, uvw, whp, hz, hy, hx, alpha, T, lag, a_data, sweep, a_smooth);
+    else
+        sor_prepare_t<float>(c, hp, B, C, f1, f2, f2f32, Jpre, uvw, whp, hz, hy, hx, alpha, T, lag, a_data, sweep, a_smooth);
+}
+
+// Run sweeps [t0,t1) x waves [q0,q1) of the prepared solve (negative bounds: the whole range).
+template <class ST>
+static void sor_launch_t(fr3d_ctx* c, int t0, int t1, int q0, int q1)
+{
+    SorParams<ST> P = sor_params<ST>(c);
+    const int nw = sor_num_waves(P);
+    const bool partial = !(t0 <= 0 && (t1 < 0 || t1 >= P.T) && q0 <= 0 && (q1 < 0 || q1 >= nw));
+    if (partial) {
+        FR3D_REQUIRE(!P.redblack && P.a_smooth == 1.0,
+                     "partial sweep ranges need the lexicographic sweep with a_smooth == 1");
+        FR3D_REQUIRE(t0 >= 0 && t1 <= P.T && t0 < t1 && q0 >= 0 && q1 <= nw && q0 <= q1, "bad sweep / wave range");
+        FR3D_REQUIRE(t0 % P.lag == 0, "a partial solve must start at a multiple of update_lag (psi refresh)");
+        P.t_begin = t0;
+        P.t_end = t1;
+        P.q_begin = q0;
+        P.q_end = q1;
+        if (q0 == q1)
+            return;
+    }
+    sor_run(c->dev, P, c->bar.ensure(c->dev, 4), c->sp_hp->pe_host.data());
+}
+
+static void sor_launch(fr3d_ctx* c, int state_dtype, int t0 = -1, int t1 = -1, int q0 = -1, int q1 = -1)
+{
+    FR3D_REQUIRE(c->sp_hp != nullptr, "no level solve has been prepared");
+    if (state_dtype == FR3D_F64)
+        sor_launch_t<double>(c, t0, t1, q0, q1);
+    else
+        sor_launch_t<float>(c, t0, t1, q0, q1);
 }
 
 static void run_sor(fr3d_ctx* c, int state_dtype, const HPGeom& hp, int B, int C, const float* f1, const float* f2,
                     int f2f32, const double* Jpre, const double* uvw, const double* whp, double hz, double hy,
                     double hx, const double* alpha, int T, int lag, const double* a_data, int sweep, double a_smooth)
 {
-    FR3D_REQUIRE(sweep == FR3D_SWEEP_LEXICOGRAPHIC || sweep == FR3D_SWEEP_REDBLACK, "unknown sweep order %d", sweep);
-    if (state_dtype == FR3D_F64)
-        run_sor_t<double>(c, hp, B, C, f1, f2, f2f32, Jpre, uvw, whp, hz, hy, hx, alpha, T, lag, a_data, sweep, a_smooth);
-    else
-        run_sor_t<float>(c, hp, B, C, f1, f2, f2f32, Jpre, uvw, whp, hz, hy, hx, alpha, T, lag, a_data, sweep, a_smooth);
+    sor_prepare(c, state_dtype, hp, B, C, f1, f2, f2f32, Jpre, uvw, whp, hz, hy, hx, alpha, T, lag, a_data, sweep, a_smooth);
+    sor_launch(c, state_dtype);
 }
 
 // increments in solver storage -> natural planar float64 (B, 3, N)
@@ -623,106 +682,153 @@ int fr3d_set_reference(fr3d_ctx* ctx, const float* ref_proc, const float* weight
     FR3D_API_END()
 }
 
-int fr3d_get_displacement(fr3d_ctx* ctx, const float* moving, const float* uvw_init, int B, void* flow_out,
-                          int out_dtype)
+// ---- coarse-to-fine driver, one level at a time (core/optical_flow_3d.py:403-541) -----------------
+static void run_buffers(fr3d_ctx* c, int B, double*& ucur, double*& uprev)
 {
-    FR3D_API_BEGIN(ctx)
-    FR3D_REQUIRE(_c->has_plan, "fr3d_get_displacement needs a context created with a plan");
-    if (!_c->ref_set)
+    int64_t Nmax = 0;
+    for (const auto& L : c->levels)
+        Nmax = L->N > Nmax ? L->N : Nmax;
+    double* a = c->uvw_a.ensure(c->dev, (size_t)B * 3 * Nmax);
+    double* b = c->uvw_b.ensure(c->dev, (size_t)B * 3 * Nmax);
+    ucur = c->run_flip ? b : a;
+    uprev = c->run_flip ? a : b;
+}
+
+// Everything of level li that precedes its solve: moving image of the level, flow from the coarser
+// level, cubic warp, system assembly.
+static void level_begin(fr3d_ctx* c, int li, const float* moving, const float* uvw_init, int B)
+{
+    FR3D_REQUIRE(c->has_plan, "needs a context created with a plan");
+    if (!c->ref_set)
         FR3D_THROW(FR3D_ERR_STATE, "fr3d_set_reference has not been called");
-    FR3D_REQUIRE(moving && flow_out, "null argument");
-    FR3D_REQUIRE(B >= 1 && B <= _c->max_batch, "B=%d outside 1..max_batch=%d", B, _c->max_batch);
-    FR3D_REQUIRE(out_dtype == FR3D_F32 || out_dtype == FR3D_F64, "flow_out dtype must be F32 or F64");
-    Device& dev = _c->dev;
-    const int Z = _c->Z, Y = _c->Y, X = _c->X, C = _c->C;
+    FR3D_REQUIRE(moving, "null argument");
+    FR3D_REQUIRE(B >= 1 && B <= c->max_batch, "B=%d outside 1..max_batch=%d", B, c->max_batch);
+    FR3D_REQUIRE(li >= 0 && li < (int)c->levels.size(), "level %d outside 0..%d", li, (int)c->levels.size() - 1);
+    if (li == 0) {
+        c->run_B = B;
+        c->run_done = -1;
+        c->run_flip = false;
+    } else if (c->run_done != li - 1 || c->run_B != B || c->run_level != -1) {
+        FR3D_THROW(FR3D_ERR_STATE, "levels must be processed in order, coarse to fine, one at a time");
+    }
+    Device& dev = c->dev;
+    const int Z = c->Z, Y = c->Y, X = c->X, C = c->C;
     const int64_t NF = (int64_t)Z * Y * X;
     int64_t Nmax = 0;
-    for (const auto& L : _c->levels)
+    for (const auto& L : c->levels)
         Nmax = L->N > Nmax ? L->N : Nmax;
-    float* f2 = _c->f2.ensure(dev, (size_t)B * C * Nmax);
-    float* tmp = _c->tmp.ensure(dev, (size_t)B * C * Nmax);
-    double* ucur = _c->uvw_a.ensure(dev, (size_t)B * 3 * Nmax);
-    double* uprev = _c->uvw_b.ensure(dev, (size_t)B * 3 * Nmax);
-    double* dnat = _c->dnat.ensure(dev, (size_t)B * 3 * Nmax);
+    float* f2 = c->f2.ensure(dev, (size_t)B * C * Nmax);
+    float* tmp = c->tmp.ensure(dev, (size_t)B * C * Nmax);
+    if (li > 0)
+        c->run_flip = !c->run_flip;
+    double *ucur, *uprev;
+    run_buffers(c, B, ucur, uprev);
     const View mov_cl{NF * C, 1, (int64_t)Y * X * C, (int64_t)X * C, C};
-
-    for (size_t li = 0; li < _c->levels.size(); ++li) {
-        LevelDev& L = *_c->levels[li];
-        const int p = L.pz, m = L.py, n = L.px;
-        const int64_t N = L.N;
-        // moving image at this level: always resampled from full resolution (:409-410)
-        resize3<float, float>(_c, moving, mov_cl, B, C, Z, Y, X, f2, planar(C, p, m, n), L.full);
-        const float* warped = f2;
-        int f2f32 = 0;
-        if (li == 0) {
-            if (uvw_init) {
-                // (:417-420) the initial field is shared by the batch: resample once, broadcast
-                float* u0 = _c->fscr.ensure(dev, (size_t)3 * N);
-                const View uv{0, 1, (int64_t)Y * X * 3, (int64_t)X * 3, 3};
-                resize3<float, float>(_c, uvw_init, uv, 1, 3, Z, Y, X, u0, planar(3, p, m, n), L.full);
-                launch(dev, BroadcastF32toF64K{u0, ucur, 3 * N}, (int64_t)B * 3 * N);
-            } else {
-                dev.zero(ucur, (size_t)B * 3 * N * sizeof(double));
-            }
+    LevelDev& L = *c->levels[li];
+    const int p = L.pz, m = L.py, n = L.px;
+    const int64_t N = L.N;
+    // moving image at this level: always resampled from full resolution (:409-410)
+    resize3<float, float>(c, moving, mov_cl, B, C, Z, Y, X, f2, planar(C, p, m, n), L.full);
+    const float* warped = f2;
+    int f2f32 = 0;
+    if (li == 0) {
+        if (uvw_init) {
+            // (:417-420) the initial field is shared by the batch: resample once, broadcast
+            float* u0 = c->fscr.ensure(dev, (size_t)3 * N);
+            const View uv{0, 1, (int64_t)Y * X * 3, (int64_t)X * 3, 3};
+            resize3<float, float>(c, uvw_init, uv, 1, 3, Z, Y, X, u0, planar(3, p, m, n), L.full);
+            launch(dev, BroadcastF32toF64K{u0, ucur, 3 * N}, (int64_t)B * 3 * N);
         } else {
-            // (:424-434) upsample the flow from the coarser level, then warp the moving image
-            const LevelDev& Lp = *_c->levels[li - 1];
-            double* t = ucur;
-            ucur = uprev;
-            uprev = t;
-            resize3<double, double>(_c, uprev, planar(3, Lp.pz, Lp.py, Lp.px), B, 3, Lp.pz, Lp.py, Lp.px, ucur,
-                                    planar(3, p, m, n), L.prev);
-            spline_prefilter(_c, f2, FR3D_F32, C * N, N, (int64_t)m * n, n, 1, B, C, p, m, n);
-            WarpGatherK g;
-            g.order = 3;
-            g.coef = _c->coef.p;
-            g.src = nullptr;
-            g.sdt = FR3D_F32;
-            g.sb = g.sc = g.sz = g.sy = g.sx = 0;
-            g.disp64 = ucur;
-            g.disp32 = nullptr;
-            g.hx = L.hx;
-            g.hy = L.hy;
-            g.hz = L.hz;
-            g.ref = L.f1.p;
-            g.rdt = FR3D_F32;
-            g.rc = N;
-            g.rz = (int64_t)m * n;
-            g.ry = n;
-            g.rx = 1;
-            g.out = tmp;
-            g.ob = C * N;
-            g.oc = N;
-            g.oz = (int64_t)m * n;
-            g.oy = n;
-            g.ox = 1;
-            g.B = B;
-            g.C = C;
-            g.Z = p;
-            g.Y = m;
-            g.X = n;
-            launch(dev, g, (int64_t)B * N);
-            warped = tmp;
-            f2f32 = 1; // numpy keeps the float32 warp output in float32 through its derivatives
+            dev.zero(ucur, (size_t)B * 3 * N * sizeof(double));
         }
-        run_sor(_c, _c->state_dtype, L.hp, B, C, L.f1.p, warped, f2f32, nullptr, ucur, L.whp.p, L.hz, L.hy, L.hx,
-                L.alpha, _c->iterations, _c->update_lag, _c->a_data, _c->sweep, _c->a_smooth);
-        sor_result(_c, _c->state_dtype, L.hp, B, dnat);
-        if (L.median)
-            launch_occ2(dev, Median5PairK{dnat, ucur, ucur, p, m, n, (n + 1) / 2}, (int64_t)B * 3 * p * m * ((n + 1) / 2)); // (:517-529)
-        else
-            launch(dev, AddK{ucur, dnat, ucur}, (int64_t)B * 3 * N);
+    } else {
+        // (:424-434) upsample the flow from the coarser level, then warp the moving image
+        const LevelDev& Lp = *c->levels[li - 1];
+        resize3<double, double>(c, uprev, planar(3, Lp.pz, Lp.py, Lp.px), B, 3, Lp.pz, Lp.py, Lp.px, ucur,
+                                planar(3, p, m, n), L.prev);
+        spline_prefilter(c, f2, FR3D_F32, C * N, N, (int64_t)m * n, n, 1, B, C, p, m, n);
+        WarpGatherK g;
+        g.order = 3;
+        g.coef = c->coef.p;
+        g.src = nullptr;
+        g.sdt = FR3D_F32;
+        g.sb = g.sc = g.sz = g.sy = g.sx = 0;
+        g.disp64 = ucur;
+        g.disp32 = nullptr;
+        g.hx = L.hx;
+        g.hy = L.hy;
+        g.hz = L.hz;
+        g.ref = L.f1.p;
+        g.rdt = FR3D_F32;
+        g.rc = N;
+        g.rz = (int64_t)m * n;
+        g.ry = n;
+        g.rx = 1;
+        g.out = tmp;
+        g.ob = C * N;
+        g.oc = N;
+        g.oz = (int64_t)m * n;
+        g.oy = n;
+        g.ox = 1;
+        g.B = B;
+        g.C = C;
+        g.Z = p;
+        g.Y = m;
+        g.X = n;
+        launch(dev, g, (int64_t)B * N);
+        warped = tmp;
+        f2f32 = 1; // numpy keeps the float32 warp output in float32 through its derivatives
     }
-    const LevelDev& Lf = *_c->levels.back();
-    if (_c->to_full[0].P > 0) {
-        // (:536-541) resample the flow to full resolution; values are not rescaled
+    sor_prepare(c, c->state_dtype, L.hp, B, C, L.f1.p, warped, f2f32, nullptr, ucur, L.whp.p, L.hz, L.hy, L.hx,
+                L.alpha, c->iterations, c->update_lag, c->a_data, c->sweep, c->a_smooth);
+    c->run_level = li;
+}
+
+// Increments of the open level -> natural layout, 5^3 median, accumulation into the flow (:517-529).
+static void level_end(fr3d_ctx* c, int li)
+{
+    FR3D_REQUIRE(c->run_level == li, "level %d is not open", li);
+    Device& dev = c->dev;
+    const int B = c->run_B;
+    LevelDev& L = *c->levels[li];
+    const int p = L.pz, m = L.py, n = L.px;
+    int64_t Nmax = 0;
+    for (const auto& Lq : c->levels)
+        Nmax = Lq->N > Nmax ? Lq->N : Nmax;
+    double* dnat = c->dnat.ensure(dev, (size_t)B * 3 * Nmax);
+    double *ucur, *uprev;
+    run_buffers(c, B, ucur, uprev);
+    sor_result(c, c->state_dtype, L.hp, B, dnat);
+    if (L.median)
+        launch_occ2(dev, Median5PairK{dnat, ucur, ucur, p, m, n, (n + 1) / 2}, (int64_t)B * 3 * p * m * ((n + 1) / 2));
+    else
+        launch(dev, AddK{ucur, dnat, ucur}, (int64_t)B * 3 * L.N);
+    c->run_level = -1;
+    c->run_done = li;
+}
+
+// (:530-541) flow of the finest solved level -> full resolution, interleaved (B,Z,Y,X,3).
+static void flow_finish(fr3d_ctx* c, void* flow_out, int out_dtype)
+{
+    FR3D_REQUIRE(flow_out, "null argument");
+    FR3D_REQUIRE(out_dtype == FR3D_F32 || out_dtype == FR3D_F64, "flow_out dtype must be F32 or F64");
+    FR3D_REQUIRE(c->run_done == (int)c->levels.size() - 1 && c->run_level == -1, "the finest level has not been solved");
+    Device& dev = c->dev;
+    const int B = c->run_B;
+    const int Z = c->Z, Y = c->Y, X = c->X;
+    const int64_t NF = (int64_t)Z * Y * X;
+    double *ucur, *uprev;
+    run_buffers(c, B, ucur, uprev);
+    const LevelDev& Lf = *c->levels.back();
+    if (c->to_full[0].P > 0) {
+        // resample the flow to full resolution; values are not rescaled
         const View fo{NF * 3, 1, (int64_t)Y * X * 3, (int64_t)X * 3, 3};
         if (out_dtype == FR3D_F32)
-            resize3<double, float>(_c, ucur, planar(3, Lf.pz, Lf.py, Lf.px), B, 3, Lf.pz, Lf.py, Lf.px,
-                                   (float*)flow_out, fo, _c->to_full);
+            resize3<double, float>(c, ucur, planar(3, Lf.pz, Lf.py, Lf.px), B, 3, Lf.pz, Lf.py, Lf.px,
+                                   (float*)flow_out, fo, c->to_full);
         else
-            resize3<double, double>(_c, ucur, planar(3, Lf.pz, Lf.py, Lf.px), B, 3, Lf.pz, Lf.py, Lf.px,
-                                    (double*)flow_out, fo, _c->to_full);
+            resize3<double, double>(c, ucur, planar(3, Lf.pz, Lf.py, Lf.px), B, 3, Lf.pz, Lf.py, Lf.px,
+                                    (double*)flow_out, fo, c->to_full);
     } else {
         FR3D_REQUIRE(Lf.pz == Z && Lf.py == Y && Lf.px == X, "finest level is not full resolution but to_full is empty");
         if (out_dtype == FR3D_F32)
@@ -730,6 +836,101 @@ int fr3d_get_displacement(fr3d_ctx* ctx, const float* moving, const float* uvw_i
         else
             launch(dev, InterleaveFlowK<double>{ucur, (double*)flow_out, NF}, (int64_t)B * NF * 3);
     }
+}
+
+int fr3d_get_displacement(fr3d_ctx* ctx, const float* moving, const float* uvw_init, int B, void* flow_out,
+                          int out_dtype)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(moving && flow_out, "null argument");
+    FR3D_REQUIRE(out_dtype == FR3D_F32 || out_dtype == FR3D_F64, "flow_out dtype must be F32 or F64");
+    _c->run_level = -1;
+    for (int li = 0; li < (int)_c->levels.size(); ++li) {
+        level_begin(_c, li, moving, uvw_init, B);
+        sor_launch(_c, _c->state_dtype);
+        level_end(_c, li);
+    }
+    flow_finish(_c, flow_out, out_dtype);
+    FR3D_API_END()
+}
+
+int fr3d_level_count(const fr3d_ctx* ctx) { return ctx ? (int)ctx->levels.size() : 0; }
+
+int fr3d_level_info(const fr3d_ctx* ctx, int level, int32_t size[3], int32_t* n_hyperplanes, int64_t* n_slots,
+                    int32_t* hyperplane_start)
+{
+    if (!ctx || level < 0 || level >= (int)ctx->levels.size())
+        return FR3D_ERR_ARG;
+    const LevelDev& L = *ctx->levels[level];
+    if (size) {
+        size[0] = L.pz;
+        size[1] = L.py;
+        size[2] = L.px;
+    }
+    if (n_hyperplanes)
+        *n_hyperplanes = L.hp.S;
+    if (n_slots)
+        *n_slots = L.hp.npad;
+    if (hyperplane_start) {
+        // start[s] = 32 * (chunks of hyperplanes < s); rebuilt from the parity prefix kept on the host
+        int64_t at = 0;
+        for (int s = 0; s < L.hp.S; ++s) {
+            hyperplane_start[s] = (int32_t)at;
+            at += 32LL * (L.hp.pe_host[s] - (s >= 2 ? L.hp.pe_host[s - 2] : 0));
+        }
+        hyperplane_start[L.hp.S] = (int32_t)at;
+    }
+    return FR3D_OK;
+}
+
+int fr3d_level_begin(fr3d_ctx* ctx, int level, const float* moving_proc, const float* uvw_init, int B)
+{
+    FR3D_API_BEGIN(ctx)
+    if (level == 0)
+        _c->run_level = -1;
+    level_begin(_c, level, moving_proc, uvw_init, B);
+    FR3D_API_END()
+}
+
+int fr3d_level_sweeps(fr3d_ctx* ctx, int level, int t_begin, int t_end, int q_begin, int q_end)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(_c->run_level == level, "level %d is not open", level);
+    sor_launch(_c, _c->state_dtype, t_begin, t_end, q_begin, q_end);
+    FR3D_API_END()
+}
+
+int fr3d_level_state(fr3d_ctx* ctx, int level, int direction, void* ext, int64_t slot_begin, int64_t slot_end)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(_c->run_level == level, "level %d is not open", level);
+    FR3D_REQUIRE(ext && (direction == 0 || direction == 1), "bad argument");
+    const HPGeom& hp = _c->levels[level]->hp;
+    FR3D_REQUIRE(slot_begin >= 0 && slot_begin <= slot_end && slot_end <= hp.npad, "bad slot range");
+    const size_t esz = _c->state_dtype == FR3D_F64 ? sizeof(Vec4<double>) : sizeof(Vec4<float>);
+    const size_t n = (size_t)(slot_end - slot_begin) * esz;
+    for (int b = 0; b < _c->run_B; ++b) {
+        char* in = _c->d.p + ((size_t)b * hp.npad + slot_begin) * esz;
+        char* ex = (char*)ext + (size_t)b * n;
+        if (direction == 0)
+            _c->dev.d2d(ex, in, n);
+        else
+            _c->dev.d2d(in, ex, n);
+    }
+    FR3D_API_END()
+}
+
+int fr3d_level_end(fr3d_ctx* ctx, int level)
+{
+    FR3D_API_BEGIN(ctx)
+    level_end(_c, level);
+    FR3D_API_END()
+}
+
+int fr3d_flow_finish(fr3d_ctx* ctx, void* flow_out, int out_dtype)
+{
+    FR3D_API_BEGIN(ctx)
+    flow_finish(_c, flow_out, out_dtype);
     FR3D_API_END()
 }
 

@@ -60,6 +60,9 @@ struct SorParams {
     HPView g;
     int C, B, T, lag, fg; // fg: frames handled by one warp work item
     int redblack;         // 0: waves q = s + 2t (lexicographic order); 1: waves q = 2t + colour (checkerboard)
+    // partial execution (sweep-pipelined multi-GPU solve): only sweeps t_begin <= t < t_end and waves
+    // q_begin <= q < q_end of the global schedule q = s + 2t; the full solve is [0,T) x [0,num_waves)
+    int t_begin, t_end, q_begin, q_end;
     double ax, ay, az;    // alpha_{x,y,z} / h_{x,y,z}^2
     double a_data[FR3D_MAX_CHANNELS];
     const double* J;      // (B, C, 10, npad): J11,J22,J33,J44,J12,J13,J23,J14,J24,J34
@@ -196,9 +199,10 @@ FR3D_HD SorWave sor_wave(const SorParams<ST>& P, const SorTabs& tb, int q)
     }
     int tlo = q - (S - 1);
     tlo = tlo > 0 ? (tlo + 1) / 2 : 0;
+    tlo = tlo < P.t_begin ? P.t_begin : tlo;
     int thi = q / 2;
-    if (thi > P.T - 1)
-        thi = P.T - 1;
+    if (thi > P.t_end - 1)
+        thi = P.t_end - 1;
     w.nT = thi >= tlo ? thi - tlo + 1 : 0;
     w.s_lo = q - 2 * thi;
     w.base = 0;
@@ -549,9 +553,8 @@ inline void sor_run_c(Device& dev, const SorParams<ST>& P, unsigned*)
         dev.launches++;
         return;
     }
-    const int nw = sor_num_waves(P);
     const SorTabs tb{P.g.pe, P.g.start};
-    for (int q = 0; q < nw; ++q) {
+    for (int q = P.q_begin; q < P.q_end; ++q) {
         const SorWave w = sor_wave(P, tb, q);
         for (int item = 0; item < w.items; ++item)
             for (int lane = 0; lane < 32; ++lane)
@@ -594,12 +597,11 @@ fr3d_sor_wavefront(const SorParams<ST> P, unsigned* bar, int tabs_in_smem)
         tb.pe = fr3d_sor_smem;
         tb.start = fr3d_sor_smem + S;
     }
-    const int nw = sor_num_waves(P);
     const int wpb = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int stride = gridDim.x * wpb;
     unsigned gen = 0;
-    for (int q = 0; q < nw; ++q) {
+    for (int q = P.q_begin; q < P.q_end; ++q) {
         const SorWave w = sor_wave(P, tb, q);
         int item = blockIdx.x * wpb + warp;
         if (item < w.items) {

@@ -1,0 +1,161 @@
+"""Single large volume on several GPUs: the sweep-pipelined level solve.
+
+Frames of a recording shard trivially (compensate.py).  ONE volume that is too slow on one GPU does
+not: the reference's solver is a lexicographic Gauss-Seidel sweep, so a z-slab decomposition has to
+exchange the slab faces after EVERY wave of the wavefront schedule, in both directions.
+The dependency structure offers something cheaper: sweep t+1 of a hyperplane needs nothing but sweep t
+of that hyperplane and of its two neighbours.  So the T sweeps are split over the ranks instead of the
+space: rank r runs sweeps [t_r, t_{r+1}) of the global schedule  q = (k+j+i) + 2t  over the WHOLE level,
+and the increments stream rank r -> r+1 as contiguous hyperplane blocks (solver storage is
+hyperplane-major) while both keep sweeping -- a one-directional NVLink pipeline with a handful of
+NCCL send/recv per level, no per-wave synchronisation between GPUs, and exactly the reference's
+update order (the result is bit-identical to the single-GPU solve).
+
+Everything around the solve (pyramid, warp, assembly, median) is computed redundantly on every rank
+from the same inputs -- it is deterministic, so all ranks stay identical without communication; only
+levels large enough to be bandwidth-bound are pipelined, small ones are solved redundantly too.
+
+    reg  = Registration(shape, C, params, max_batch=1)        # on every rank, same arguments
+    reg.set_reference(fixed_proc)
+    flow = get_displacement_pipelined(reg, moving_proc)        # (B,Z,Y,X,3) device tensor on every rank
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib, device as dev
+from .core import Registration, _check
+
+
+def sweep_partition(T: int, lag: int, world: int) -> List[Tuple[int, int]]:
+    """Split sweeps [0,T) into <= world contiguous ranges whose starts are multiples of `lag`
+    (a range must begin with a psi refresh).  Ranks beyond the number of lag blocks get (T, T)."""
+    blocks = -(-T // lag)
+    base, rem = divmod(blocks, world)
+    out, at = [], 0
+    for r in range(world):
+        nb = base + (1 if r < rem else 0)
+        t0, t1 = min(T, at * lag), min(T, (at + nb) * lag)
+        out.append((t0, t1))
+        at += nb
+    return out
+
+
+def pipeline_schedule(S: int, T: int, parts: List[Tuple[int, int]], n_chunks: int):
+    """Stages of every active rank: list (per rank) of (recv (h0,h1) | None, q_begin, q_end, send (h0,h1) | None),
+    hyperplane ranges.  Rank r's receives are rank r-1's sends, in order."""
+    active = [r for r, (a, b) in enumerate(parts) if b > a]
+    sched = {}
+    prev_sends: Optional[list] = None
+    for idx, r in enumerate(active):
+        t0, t1 = parts[r]
+        last = idx == len(active) - 1
+        q_first, q_last_end = 2 * t0, (S - 1) + 2 * (t1 - 1) + 1
+        stages, q_done, sent = [], q_first, 0
+        if prev_sends is None:
+            ends = sorted({max(1, min(S, round(c * S / n_chunks))) for c in range(1, n_chunks + 1)})
+            inputs = [(None, h) for h in ends]           # no receive; stage boundary = hyperplanes final after it
+        else:
+            inputs = [((a, b), b) for (a, b) in prev_sends]
+        for k, (rcv, h_in) in enumerate(inputs):
+            final_stage = k == len(inputs) - 1
+            if prev_sends is None:
+                q_end = h_in - 1 + 2 * (t1 - 1) + 1
+            else:
+                q_end = h_in + 2 * t0 - 1              # waves that only touch hyperplanes < h_in (and read < h_in)
+            q_end = q_last_end if final_stage else max(q_done, min(q_last_end, q_end))
+            fin = max(0, min(S, q_end - 2 * (t1 - 1)))   # hyperplanes final after waves < q_end
+            if final_stage:
+                fin = S
+            snd = None
+            if not last and fin > sent:
+                snd = (sent, fin)
+                sent = fin
+            stages.append((rcv, q_done, q_end, snd))
+            q_done = q_end
+        sched[r] = stages
+        prev_sends = [s[3] for s in stages if s[3] is not None]
+    return active, sched
+
+
+def _level_info(reg: Registration, li: int):
+    lib, h = reg.ctx.lib, reg.ctx.h
+    size = (C.c_int32 * 3)()
+    S = C.c_int32()
+    nslots = C.c_int64()
+    _check(h, lib.fr3d_level_info(h, li, size, C.byref(S), C.byref(nslots), None))
+    start = np.empty(S.value + 1, np.int32)
+    _check(h, lib.fr3d_level_info(h, li, size, C.byref(S), C.byref(nslots), start.ctypes.data))
+    return tuple(size), int(S.value), int(nslots.value), start
+
+
+def get_displacement_pipelined(reg: Registration, moving_proc, uvw=None, group=None, out_dtype=np.float32,
+                               min_slots: int = 1 << 21, n_chunks: int = 8,
+                               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """get_displacement for B frames with the level solves pipelined over the ranks of `group`.
+    Every rank must call with identical arguments; every rank returns the full result.
+    min_slots: levels with fewer solver slots (x frames) are solved redundantly without communication."""
+    lib, h = reg.ctx.lib, reg.ctx.h
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    mv = reg._as_dev(moving_proc, np.float32, None)
+    if mv.dim() == 4:
+        mv = mv[None]
+    B = mv.shape[0]
+    uv = None if uvw is None else reg._as_dev(uvw, np.float32, reg.shape + (3,))
+    if out is None:
+        out = dev.empty((B,) + reg.shape + (3,), out_dtype, reg.device)
+    T, lag = int(reg.plan.plan.iterations), int(reg.plan.plan.update_lag)
+    state_dt = np.float64 if reg.plan.plan.state_dtype == _lib.F64 else np.float32
+    pipelinable = reg.plan.plan.sweep == 0 and float(reg.plan.plan.a_smooth) == 1.0
+    nl = lib.fr3d_level_count(h)
+    keep = []
+    for li in range(nl):
+        _check(h, lib.fr3d_level_begin(h, li, dev.ptr(mv), dev.ptr(uv), B))
+        _, S, nslots, start = _level_info(reg, li)
+        parts = sweep_partition(T, lag, world)
+        active = [r for r, (a, b) in enumerate(parts) if b > a]
+        if world == 1 or not pipelinable or len(active) < 2 or nslots * B < min_slots:
+            _check(h, lib.fr3d_level_sweeps(h, li, -1, -1, -1, -1))      # redundant on every rank, no exchange
+        else:
+            active, sched = pipeline_schedule(S, T, parts, n_chunks)
+            if rank in sched:
+                t0, t1 = parts[rank]
+                pos = active.index(rank)
+                src = active[pos - 1] if pos > 0 else None
+                dst = active[pos + 1] if pos + 1 < len(active) else None
+                for rcv, q0, q1, snd in sched[rank]:
+                    if rcv is not None:
+                        a, b = int(start[rcv[0]]), int(start[rcv[1]])
+                        buf = dev.empty((B, b - a, 4), state_dt, reg.device)
+                        dist.recv(buf, src=_global_rank(group, src), group=group)
+                        _check(h, lib.fr3d_level_state(h, li, 1, dev.ptr(buf), a, b))
+                        keep.append(buf)
+                    _check(h, lib.fr3d_level_sweeps(h, li, t0, t1, q0, q1))
+                    if snd is not None:
+                        a, b = int(start[snd[0]]), int(start[snd[1]])
+                        buf = dev.empty((B, b - a, 4), state_dt, reg.device)
+                        _check(h, lib.fr3d_level_state(h, li, 0, dev.ptr(buf), a, b))
+                        dist.send(buf, dst=_global_rank(group, dst), group=group)
+                        keep.append(buf)
+            # the last active rank holds the finished increments: hand them to everybody
+            full = dev.empty((B, nslots, 4), state_dt, reg.device)
+            if rank == active[-1]:
+                _check(h, lib.fr3d_level_state(h, li, 0, dev.ptr(full), 0, nslots))
+            dist.broadcast(full, src=_global_rank(group, active[-1]), group=group)
+            if rank != active[-1]:
+                _check(h, lib.fr3d_level_state(h, li, 1, dev.ptr(full), 0, nslots))
+            keep.append(full)
+        _check(h, lib.fr3d_level_end(h, li))
+    _check(h, lib.fr3d_flow_finish(h, dev.ptr(out), reg._code(out)))
+    reg._keep = [mv, uv, keep]
+    return out
+
+
+def _global_rank(group, r: int) -> int:
+    return r if group is None else dist.get_global_rank(group, r)

@@ -147,6 +147,33 @@ int fr3d_set_reference(fr3d_ctx* ctx, const float* ref_proc, const float* weight
 int fr3d_get_displacement(fr3d_ctx* ctx, const float* moving_proc, const float* uvw_init, int B,
                           void* flow_out, int out_dtype);
 
+/* The same computation one pyramid level at a time (levels 0 .. fr3d_level_count()-1, coarse to fine):
+ *   fr3d_level_begin   everything before the solve (level image, flow from the coarser level, warp, assembly)
+ *   fr3d_level_sweeps  sweeps t_begin <= t < t_end restricted to waves q_begin <= q < q_end of the global
+ *                      wavefront schedule q = (k+j+i) + 2t (negative bounds = everything).  t_begin must be a
+ *                      multiple of update_lag.  Lexicographic sweep, a_smooth == 1 only for partial ranges.
+ *   fr3d_level_state   copy the increments of solver-storage slots [slot_begin, slot_end) of all B frames
+ *                      out of (direction 0) or into (direction 1) `ext` (device, B x (slot_end-slot_begin)
+ *                      4-vectors {du,dv,dw,-} of the state dtype).  Hyperplane s = k+j+i occupies the slots
+ *                      hyperplane_start[s] .. hyperplane_start[s+1] reported by fr3d_level_info, so a range of
+ *                      hyperplanes is one contiguous block per frame.
+ *   fr3d_level_end     increments -> 5^3 median -> accumulate into the flow
+ *   fr3d_flow_finish   flow of the finest level -> (B,Z,Y,X,3) full resolution
+ * This is the seam of the sweep-pipelined multi-GPU solve of a single large volume
+ * (flowreg3d_b200/multigpu.py): rank r runs the sweeps [t_r, t_{r+1}) of every level; the increments
+ * stream rank r -> r+1 hyperplane block by hyperplane block over NVLink (one direction only, because sweep
+ * t+1 of a hyperplane needs nothing but sweep t of itself and its two neighbours). */
+int fr3d_level_count(const fr3d_ctx* ctx);
+/* size: (pz,py,px); hyperplane_start: host, n_hyperplanes+1 entries (may be NULL). */
+int fr3d_level_info(const fr3d_ctx* ctx, int level, int32_t size[3], int32_t* n_hyperplanes,
+                    int64_t* n_slots, int32_t* hyperplane_start);
+int fr3d_level_begin(fr3d_ctx* ctx, int level, const float* moving_proc, const float* uvw_init, int B);
+int fr3d_level_sweeps(fr3d_ctx* ctx, int level, int t_begin, int t_end, int q_begin, int q_end);
+int fr3d_level_state(fr3d_ctx* ctx, int level, int direction, void* ext, int64_t slot_begin,
+                     int64_t slot_end);
+int fr3d_level_end(fr3d_ctx* ctx, int level);
+int fr3d_flow_finish(fr3d_ctx* ctx, void* flow_out, int out_dtype);
+
 /* Compensation warp of B raw frames (parallelization/sequential_3d.py:153-160):
  * out(x) = vol(x + flow(x)), plan.interp interpolation, out-of-volume voxels take ref's value.
  * vol: (B,Z,Y,X,C) of vol_dtype; flow: (B,Z,Y,X,3) float32; ref: (Z,Y,X,C) of ref_dtype;

@@ -61,3 +61,71 @@ def test_two_rank_sharding_matches_single_process(emu_backend, tmp_path):
     assert sorted(seen) == list(range(v.shape[0]))   # every frame processed exactly once
     # batches of 5 and 2 frames over 2 ranks: 3+2 and 1+1
     assert len(np.load(tmp_path / "r0.npz")["idx"]) == 4 and len(np.load(tmp_path / "r1.npz")["idx"]) == 3
+
+
+def _pipeline_worker(rank, world, port, emu_path, tmp):
+    os.environ["FR3D_LIBRARY_OVERRIDE"] = emu_path
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    import torch.distributed as dist
+    import flowreg3d_b200 as F
+    from flowreg3d_b200 import device as dev
+    from flowreg3d_b200.multigpu import get_displacement_pipelined
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = np.load(ROOT / "tests" / "golden" / "flow_small.npz")
+    fixed, moving = g["fixed"][:16, :28, :32].astype(np.float32), g["moving"][:16, :28, :32].astype(np.float32)
+    fp = F.FlowParams(alpha=(0.25, 0.3, 0.2), update_lag=3, iterations=14, min_level=0, levels=100, eta=0.8,
+                      a_smooth=1.0, a_data=0.45)
+    reg = F.Registration(fixed.shape[:3], fixed.shape[3], fp, max_batch=2)
+    reg.set_reference(fixed)
+    mv = np.stack([moving, np.roll(moving, 1, 2)], 0)
+    flow = get_displacement_pipelined(reg, mv, min_slots=0, n_chunks=5)      # pipeline every level
+    reg.sync()
+    np.save(os.path.join(tmp, f"p{rank}.npy"), dev.to_host(flow))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sweep_pipelined_solve_is_bit_identical(emu_backend, tmp_path, world):
+    """One volume on several ranks: sweeps split over the ranks, increments streamed rank -> rank+1 in
+    hyperplane blocks.  Every rank ends with exactly the single-process flow (iterations 14 / lag 3 gives
+    uneven sweep ranges: 2 ranks -> [0,9) [9,14); 3 ranks -> [0,6) [6,12) [12,14))."""
+    from emu.build_emu import build
+    import flowreg3d_b200 as F
+    from flowreg3d_b200 import device as dev
+    from flowreg3d_b200.multigpu import pipeline_schedule, sweep_partition
+    assert sweep_partition(14, 3, 2) == [(0, 9), (9, 14)]
+    assert sweep_partition(14, 3, 3) == [(0, 6), (6, 12), (12, 14)]
+    assert sweep_partition(10, 5, 4) == [(0, 5), (5, 10), (10, 10), (10, 10)]
+    # schedule invariants: every rank runs each of its waves exactly once, in order; receives of rank r are
+    # the sends of rank r-1; a wave never runs before the hyperplanes it reads have arrived
+    S, T = 40, 14
+    parts = sweep_partition(T, 3, 3)
+    active, sched = pipeline_schedule(S, T, parts, 5)
+    for i, r in enumerate(active):
+        t0, t1 = parts[r]
+        st = sched[r]
+        assert st[0][1] == 2 * t0 and st[-1][2] == S - 1 + 2 * (t1 - 1) + 1
+        assert all(a[2] == b[1] for a, b in zip(st, st[1:]))
+        got = 0 if i else S
+        for rcv, q0, q1, snd in st:
+            if rcv is not None:
+                assert rcv[0] == got
+                got = rcv[1]
+            assert q1 <= got + 2 * t0 - 1 or got == S
+        if i:
+            assert [s[0] for s in st if s[0]] == [s[3] for s in sched[active[i - 1]] if s[3]]
+    emu = str(build())
+    mp.spawn(_pipeline_worker, args=(world, _free_port(), emu, str(tmp_path)), nprocs=world, join=True)
+    g = np.load(ROOT / "tests" / "golden" / "flow_small.npz")
+    fixed, moving = g["fixed"][:16, :28, :32].astype(np.float32), g["moving"][:16, :28, :32].astype(np.float32)
+    fp = F.FlowParams(alpha=(0.25, 0.3, 0.2), update_lag=3, iterations=14, min_level=0, levels=100, eta=0.8,
+                      a_smooth=1.0, a_data=0.45)
+    reg = F.Registration(fixed.shape[:3], fixed.shape[3], fp, max_batch=2)
+    reg.set_reference(fixed)
+    ref = dev.to_host(reg.get_displacement(np.stack([moving, np.roll(moving, 1, 2)], 0)))
+    for rank in range(world):
+        assert np.array_equal(np.load(tmp_path / f"p{rank}.npy"), ref), rank
