@@ -624,7 +624,27 @@ int fr3d_preprocess(fr3d_ctx* ctx, const void* raw, int dtype, int B, const doub
         RY = g.r[ch][1] > RY ? g.r[ch][1] : RY;
         RX = g.r[ch][2] > RX ? g.r[ch][2] : RX;
     }
-    if (RY <= 16 && RX <= 16) {
+    bool uniform = RY == RX && RY >= 1 && RY <= 6;
+    for (int ch = 0; ch < C; ++ch)
+        uniform = uniform && g.r[ch][1] == RY && g.r[ch][2] == RY;
+    if (uniform) {
+        const int ty = (Y + 15) / 16, tx = (X + 63) / 64;
+        const int64_t nblk = (int64_t)B * Z * ty * tx;
+#define FR3D_PRE_WIN(R_)                                                                                   \
+    case R_:                                                                                               \
+        launch_tiles(_c->dev, PreYXWinK<R_>{a, out, B, Z, Y, X, C, g, ty, tx}, nblk, 256,                   \
+                     PreYXWinK<R_>::smem_bytes(C));                                                        \
+        break;
+        switch (RY) {
+            FR3D_PRE_WIN(1)
+            FR3D_PRE_WIN(2)
+            FR3D_PRE_WIN(3)
+            FR3D_PRE_WIN(4)
+            FR3D_PRE_WIN(5)
+            FR3D_PRE_WIN(6)
+        }
+#undef FR3D_PRE_WIN
+    } else if (RY <= 16 && RX <= 16) {
         PreYXTileK k;
         k.in = a;
         k.out = out;

@@ -284,6 +284,98 @@ struct PreYXTileK {
     }
 };
 
+// Register-window variant of PreYXTileK for the common case that every channel uses the same radius R
+// along Y and X: a thread produces a run of 8 outputs from 8 + 2R staged samples held in registers
+// (2 shared-memory reads per output instead of 2R + 1).  Same summation order per output.
+template <int R>
+struct PreYXWinK {
+    static constexpr int PHASES = 3 * FR3D_MAX_CHANNELS + 1;
+    static constexpr int TY = 16, TX = 64, RUN = 8;
+    static constexpr int IW = TX + 2 * R, IH = TY + 2 * R, MW = IW + 1; // MW: padded row of the Y-pass buffer
+    const double* in; // (B, C, Z, Y, X) planar
+    float* out;       // (B, Z, Y, X, C)
+    int B, Z, Y, X, C;
+    PreGauss g;
+    int tiles_y, tiles_x;
+    static size_t smem_bytes(int C_) { return (size_t)(IH * IW + TY * MW) * sizeof(double) + (size_t)TY * TX * C_ * sizeof(float); }
+    FR3D_HD void phase(int ph, int64_t blk, int tid, int nthreads, double* sm) const
+    {
+        const int tx = (int)(blk % tiles_x);
+        int64_t q = blk / tiles_x;
+        const int ty = (int)(q % tiles_y);
+        q /= tiles_y; // b*Z + z
+        const int z = (int)(q % Z);
+        const int b = (int)(q / Z);
+        const int y0 = ty * TY, x0 = tx * TX;
+        double* tin = sm;                       // [IH][IW]
+        double* mid = tin + IH * IW;            // [TY][MW]
+        float* tout = (float*)(mid + TY * MW);  // [TY][TX][C]
+        if (ph == 3 * FR3D_MAX_CHANNELS) {
+            const int ny = Y - y0 < TY ? Y - y0 : TY, nx = X - x0 < TX ? X - x0 : TX;
+            const int rowlen = nx * C;
+            const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
+            for (int yy = warp; yy < ny; yy += nwarps) {
+                float* o = out + ((((int64_t)b * Z + z) * Y + (y0 + yy)) * X + x0) * C;
+                for (int r = lane; r < rowlen; r += 32)
+                    o[r] = tout[yy * TX * C + r];
+            }
+            return;
+        }
+        const int c = ph / 3, sub = ph % 3;
+        if (c >= C)
+            return;
+        if (sub == 0) {
+            const double* plane = in + (((int64_t)b * C + c) * Z + z) * Y * X;
+            const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
+            for (int yy = warp; yy < IH; yy += nwarps) {
+                const double* row = plane + (int64_t)reflect_idx(y0 - R + yy, Y) * X;
+                for (int xx = lane; xx < IW; xx += 32)
+                    tin[yy * IW + xx] = row[reflect_idx(x0 - R + xx, X)];
+            }
+        } else if (sub == 1) {
+            // task = (column xx, run of 8 rows)
+            for (int task = tid; task < IW * (TY / RUN); task += nthreads) {
+                const int xx = task % IW, run = task / IW;
+                double w[R + 1], win[RUN + 2 * R];
+#pragma unroll
+                for (int j = 0; j <= R; ++j)
+                    w[j] = g.w[c][1][j];
+#pragma unroll
+                for (int k = 0; k < RUN + 2 * R; ++k)
+                    win[k] = tin[(run * RUN + k) * IW + xx];
+#pragma unroll
+                for (int o = 0; o < RUN; ++o) {
+                    double t = win[o + R] * w[0];
+#pragma unroll
+                    for (int j = R; j >= 1; --j)
+                        t += (win[o + R - j] + win[o + R + j]) * w[j];
+                    mid[(run * RUN + o) * MW + xx] = t;
+                }
+            }
+        } else {
+            // task = (row yy, run of 8 columns); consecutive threads take consecutive rows (bank spread)
+            for (int task = tid; task < TY * (TX / RUN); task += nthreads) {
+                const int yy = task % TY, run = task / TY;
+                double w[R + 1], win[RUN + 2 * R];
+#pragma unroll
+                for (int j = 0; j <= R; ++j)
+                    w[j] = g.w[c][2][j];
+#pragma unroll
+                for (int k = 0; k < RUN + 2 * R; ++k)
+                    win[k] = mid[yy * MW + run * RUN + k];
+#pragma unroll
+                for (int o = 0; o < RUN; ++o) {
+                    double t = win[o + R] * w[0];
+#pragma unroll
+                    for (int j = R; j >= 1; --j)
+                        t += (win[o + R - j] + win[o + R + j]) * w[j];
+                    tout[(yy * TX + run * RUN + o) * C + c] = (float)t;
+                }
+            }
+        }
+    }
+};
+
 // ------------------------------------------------------------------------------------------
 // Cubic B-spline prefilter = scipy.ndimage.spline_filter(order=3, mode="nearest") applied to the
 // volume edge-padded by 12 (scipy/ndimage/_interpolation.py:212-225, ni_splines.c).  One thread per
