@@ -194,6 +194,13 @@ def algorithmic_bytes(name, plan_levels, B, C, iters, lag):
     return None
 
 
+# ncu `dram__bytes_read.sum + dram__bytes_write.sum` of ONE fr3d_sor_wavefront<double,2> launch on the 10x168x168
+# level at B = 16 (profiles/r01_ncu_full_step_b16_f64.txt: 82.370 + 20.494 GB), per frame and level voxel.  The
+# other launch of a step (8x134x134 level) is scaled by its voxel count.  Valid for the default solver
+# (100 sweeps, lag 5, float64 state, lexicographic order) only.
+SOR_NCU_DRAM_BYTES_PER_FRAME_VOXEL = (82.370e9 + 20.494e9) / (16 * 10 * 168 * 168)
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -369,7 +376,11 @@ def run_gpu(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": top["kernel"], "achieved": None if ach is None else round(ach, 1),
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                         "frac": None if ach is None else round(ach / peak, 4), "traffic": None,
+                         "frac": None if ach is None else round(ach / peak, 4),
+                         "traffic": (round(SOR_NCU_DRAM_BYTES_PER_FRAME_VOXEL * B * float(np.mean(level_n)))
+                                     if top["kernel"].startswith("fr3d_sor_wavefront") and args.state == "f64"
+                                     and args.sweep == "lexicographic" and opts.iterations == 100 else None),
+                         "traffic_source": "ncu dram bytes per launch (profiles/r01_ncu_full_step_b16_f64.txt), mean of the two levels",
                          "share_of_step": top["share"]},
             "kernels": table[:8],
             "cpu_baseline": cpu,
