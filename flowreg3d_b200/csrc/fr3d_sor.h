@@ -69,7 +69,7 @@ struct SorParams {
     const double* wgt;    // (C, npad), shared by all frames
     const Vec4<ST>* L;    // (B, npad): alpha-weighted Laplacian of u, v, w
     Vec4<ST>* d;          // (B, npad): du, dv, dw (zero-initialised)
-    double* AB;           // (B, 9, npad): 1/den_u, 1/den_v, 1/den_w, A12, A13, A23, b1, b2, b3
+    double* AB;           // (B, 9, npad): 1/den_u, 1/den_v, 1/den_w, A12, A13, A23, b1-Lu, b2-Lv, b3-Lw
                           // (nonlinear smoothness: A11, A22, A33 themselves -- the denominator changes per sweep)
     // nonlinear smoothness term (a_smooth != 1), see "Nonlinear smoothness" below
     double a_smooth, hx, hy, hz;
@@ -279,12 +279,15 @@ FR3D_HD void sor_load(const SorParams<ST>& P, const SorLoc& L, int b, bool with_
         r.yp = ld4_cg(d + L.n4);
         r.zp = ld4_cg(d + L.n5);
     }
-    r.L = ld4_cg(P.L + (int64_t)b * np + L.a);
     if (with_ab) {
+        // plain sweep: the constant Laplacian term was folded into b1..b3 at the last refresh
+        r.L.x = r.L.y = r.L.z = r.L.w = (ST)0;
         const double* AB = P.AB + (int64_t)b * 9 * np + L.a;
 #pragma unroll
         for (int k = 0; k < 9; ++k)
             r.A[k] = FR3D_LDCG(AB + k * np);
+    } else {
+        r.L = ld4_cg(P.L + (int64_t)b * np + L.a);
     }
 }
 
@@ -304,6 +307,12 @@ FR3D_HD void sor_process(const SorParams<ST>& P, const SorLoc& L)
             sor_load(P, L, b, false, r);
             sor_refresh<C>(P.a_data, P.J + (int64_t)b * C * 10 * np, P.wgt, np, a, (double)r.own.x, (double)r.own.y,
                            (double)r.own.z, den0, r.A);
+            // fold the constant Laplacian term of u, v, w into the right-hand side: the plain sweeps then
+            // read 9 system entries and no L  (num - b == (num - L) - (b - L))
+            r.A[6] -= (double)r.L.x;
+            r.A[7] -= (double)r.L.y;
+            r.A[8] -= (double)r.L.z;
+            r.L.x = r.L.y = r.L.z = (ST)0;
 #pragma unroll
             for (int e = 0; e < 9; ++e)
                 FR3D_STCG(AB + e * np, r.A[e]);
