@@ -143,3 +143,6 @@ def _select_for_tests(path) -> None:
     for c in core._bare.values():
         c.h = None  # the old library owns them; do not destroy through the new one
     core._bare.clear()
+    for r in core._PAIR_CACHE.values():
+        r.ctx.h = None
+    core._PAIR_CACHE.clear()

@@ -411,14 +411,34 @@ def get_displacement(fixed, moving, alpha=(2, 2, 2), update_lag=10, iterations=2
     Z, Y, X, Cn = fixed.shape
     fp = FlowParams(alpha=tuple(alpha), update_lag=update_lag, iterations=iterations, min_level=min_level,
                     levels=levels, eta=eta, a_smooth=a_smooth, a_data=a_data)
-    reg = Registration((Z, Y, X), Cn, fp, max_batch=1)
+    reg = _pair_registration((Z, Y, X), Cn, fp)
     reg.set_reference(fixed.astype(np.float32), weight=weight)
     uv = None if uvw is None else np.asarray(uvw).astype(np.float32)
     out = reg.get_displacement(moving.astype(np.float32)[None], uvw=uv, out_dtype=np.float64)
     reg.sync()
-    res = dev.to_host(out)[0].copy()
-    reg.ctx.close()
-    return res
+    return dev.to_host(out)[0].copy()
+
+
+# The reference's executors call get_displacement once per frame with the same shape and parameters
+# (sequential_3d.py:89-173): keep the last few contexts (plan tables, solver geometry, workspaces) alive
+# instead of rebuilding them on every call.
+_PAIR_CACHE: "dict" = {}
+_PAIR_CACHE_MAX = 4
+
+
+def _pair_registration(shape, Cn, fp: FlowParams) -> Registration:
+    device = dev.default_device()
+    key = (shape, Cn, tuple(float(a) for a in fp.alpha), int(fp.update_lag), int(fp.iterations), int(fp.min_level),
+           int(fp.levels), float(fp.eta), float(fp.a_smooth), tuple(np.asarray(fp.a_data, float).ravel().tolist()),
+           np.dtype(STATE_DTYPE).str, int(SWEEP), str(device), str(_lib.library_path()))
+    reg = _PAIR_CACHE.pop(key, None)
+    if reg is None or reg.ctx.h is None:
+        reg = Registration(shape, Cn, fp, max_batch=1, device=device)
+    _PAIR_CACHE[key] = reg                      # most recently used last
+    while len(_PAIR_CACHE) > _PAIR_CACHE_MAX:
+        old = _PAIR_CACHE.pop(next(iter(_PAIR_CACHE)))
+        old.ctx.close()
+    return reg
 
 
 def imregister_wrapper(f2_level, u, v, w, f1_level, interpolation_method="cubic"):

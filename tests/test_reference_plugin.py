@@ -1,0 +1,65 @@
+"""Boundary B1 against the UNMODIFIED reference: flowreg3D's own BatchMotionCorrector driving the B200
+executor plugin (kernel-logic emulator here; the CUDA library on a GPU box) and its own sequential
+executor, on the same input.  Runs only where the reference source tree is present (the build
+container); it cannot travel to the GPU box and is skipped there."""
+import os
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+REF = Path("/root/reference/src")
+pytestmark = pytest.mark.skipif(not (REF / "flowreg3d").is_dir(), reason="reference source tree not present")
+
+
+@pytest.fixture(scope="module")
+def reference():
+    os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/numba_cache")
+    sys.path.insert(0, str(REF))
+    for m in ("tifffile", "h5py", "hdf5storage"):      # optional I/O packages the array path never touches
+        if m not in sys.modules:
+            try:
+                __import__(m)
+            except Exception:
+                sys.modules[m] = types.ModuleType(m)
+    from flowreg3d.motion_correction.compensate_arr_3D import compensate_arr_3D
+    from flowreg3d.motion_correction.OF_options_3D import OFOptions
+    from flowreg3d._runtime import RuntimeContext
+    import flowreg3d.motion_correction.parallelization  # noqa: F401  (registers the reference executors)
+    yield types.SimpleNamespace(compensate_arr_3D=compensate_arr_3D, OFOptions=OFOptions, RuntimeContext=RuntimeContext)
+    sys.path.remove(str(REF))
+
+
+def test_reference_pipeline_with_b200_executor(emu_backend, golden, reference, monkeypatch):
+    import importlib
+    import flowreg3d_b200.executor as ex
+    importlib.reload(ex)                               # pick up the reference's BaseExecutor3D as the base class
+    from flowreg3d.motion_correction.parallelization.base_3d import BaseExecutor3D
+    assert issubclass(ex.B200Executor3D, BaseExecutor3D)
+    assert ex.B200Executor3D.register()
+    assert "b2003d" in reference.RuntimeContext.get_available_parallelization()
+    g = golden("sequence")
+    video, ref = g["video"][:5, :12, :24, :28], g["ref"][:12, :24, :28]
+    kw = dict(alpha=(0.25, 0.25, 0.25), levels=100, min_level=2, iterations=8, update_lag=4, buffer_size=3,
+              weight=[0.5, 0.5])
+    import flowreg3d.motion_correction.compensate_recording_3D as cr
+    seen = []
+    orig = cr.BatchMotionCorrector._setup_executor
+
+    def pick(name):
+        def setup(self):
+            self.config.parallelization = name
+            orig(self)
+            seen.append(type(self.executor).__name__)
+        return setup
+
+    monkeypatch.setattr(cr.BatchMotionCorrector, "_setup_executor", pick("b200"))
+    reg_b, w_b = reference.compensate_arr_3D(video, ref, reference.OFOptions(**kw))
+    monkeypatch.setattr(cr.BatchMotionCorrector, "_setup_executor", pick("sequential"))
+    reg_s, w_s = reference.compensate_arr_3D(video, ref, reference.OFOptions(**kw))
+    assert seen == ["B200Executor3D", "SequentialExecutor3D"]
+    e = np.sqrt(((w_b.astype(np.float64) - w_s) ** 2).sum(-1))
+    assert e.mean() <= 1e-4 and e.max() <= 5e-3, (e.mean(), e.max())      # tolerance: 0.01 / 0.05
+    assert np.linalg.norm(reg_b.astype(np.float64) - reg_s) <= 1e-5 * np.linalg.norm(reg_s)   # tolerance: 1e-4
