@@ -574,15 +574,33 @@ inline void sor_run_c(Device& dev, const SorParams<ST>& P, unsigned*)
 #else
 #define FR3D_SOR_THREADS 256
 
+#ifndef FR3D_BARRIER_VARIANT
+#define FR3D_BARRIER_VARIANT 0
+#endif
+// Grid barrier between waves: every CTA's thread 0 arrives on a global counter and spins until all CTAs of
+// the generation have arrived.  The gpu-scope fence / acquire after the spin also invalidates the SM's L1
+// (SASS: CCTL.IVALL), which the L1-cached neighbour loads of the next wave rely on.
 __device__ __forceinline__ void fr3d_grid_barrier(unsigned* ctr, unsigned target)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
+#if FR3D_BARRIER_VARIANT == 0
         __threadfence();
         atomicAdd(ctr, 1u);
         while (*((volatile unsigned*)ctr) < target) {
         }
         __threadfence();
+#else
+        unsigned v;
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+        do {
+#if FR3D_BARRIER_VARIANT == 2
+            __nanosleep(32);
+#endif
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        } while (v < target);
+        __threadfence();
+#endif
     }
     __syncthreads();
 }

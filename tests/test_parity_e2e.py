@@ -163,3 +163,37 @@ def test_split_streams_identical(backend, golden):
         outs.append((dev.to_host(reg).copy(), dev.to_host(fl).copy()))
         seq.close()
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("C", [1, 3, 4])
+def test_channel_counts_and_spatial_weight(backend, golden, C):
+    """1 / 3 / 4 channels (the templated solver paths), a spatially varying (Z,Y,X,C) weight and per-channel
+    a_data against the oracle."""
+    import flowreg3d_b200 as F
+    g = golden("flow_small")
+    rng = np.random.default_rng(C)
+    fx = np.stack([g["fixed"][:14, :26, :30, c % 2] * (1.0 + 0.1 * c) for c in range(C)], -1)
+    mv = np.stack([g["moving"][:14, :26, :30, c % 2] * (1.0 + 0.1 * c) for c in range(C)], -1)
+    weight = 0.2 + rng.random(fx.shape)
+    kw = dict(alpha=(0.3, 0.25, 0.2), update_lag=4, iterations=9, min_level=1, levels=100, eta=0.8, a_smooth=1.0,
+              a_data=np.linspace(0.45, 0.8, C), weight=weight)
+    flow = F.get_displacement(fx, mv, **kw)
+    mean, mx = epe_stats(flow, O.get_displacement(fx, mv, **kw))
+    assert mean <= 1e-6 and mx <= 1e-4, (C, mean, mx)
+
+
+def test_uint16_recording(backend, golden):
+    """Integer raw frames: pre-processing from uint16, scipy's integer output rounding in the compensation
+    warp, result cast back to the input dtype (sequential_3d.py:163-169)."""
+    import flowreg3d_b200 as F
+    g = golden("sequence")
+    video = np.clip(g["video"][:4, :12, :24, :28] * 4000.0 + 100.0, 0, 65535).astype(np.uint16)
+    ref = np.clip(g["ref"][:12, :24, :28] * 4000.0 + 100.0, 0, 65535).astype(np.uint16)
+    opts = F.OFOptions(min_level=2, iterations=8, update_lag=4, buffer_size=3, weight=[0.5, 0.5],
+                       output_typename=None)
+    reg, w = F.compensate_arr_3D(video, ref, opts)
+    oreg, ow = O.compensate_arr(video, ref, min_level=2, iterations=8, update_lag=4, buffer_size=3, weight=[0.5, 0.5])
+    assert reg.dtype == np.uint16 and reg.shape == video.shape
+    mean, mx = epe_stats(w, ow)
+    assert mean <= 1e-5 and mx <= 1e-3, (mean, mx)
+    assert (reg != oreg).mean() <= 1e-4          # identical up to a vanishing number of rounding ties
