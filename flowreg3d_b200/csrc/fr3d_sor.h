@@ -37,6 +37,9 @@
 namespace fr3d {
 
 #define FR3D_SOR_OMEGA 1.95
+#ifndef FR3D_SOR_FRAME_FAST
+#define FR3D_SOR_FRAME_FAST 0 /* item order inside a wave: 0 = chunk index fastest, 1 = frame group fastest */
+#endif
 
 // Per-state-dtype tuning (measured on B200, config 2, B = 16; profiles/r01_sor_variants.txt):
 //   float64 state: two frames in flight per lane, 2 CTAs/SM (128 registers), neighbour increments via L1
@@ -229,8 +232,14 @@ template <class ST>
 FR3D_HD SorLoc sor_locate(const SorParams<ST>& P, const SorTabs& tb, int q, const SorWave& w, int item, int lane)
 {
     const HPView& g = P.g;
+#if FR3D_SOR_FRAME_FAST
+    const int nfg = (P.B + P.fg - 1) / P.fg;
+    const int f = item / nfg;
+    const int fgi = item - f * nfg;
+#else
     const int fgi = item / w.chunks;
     const int f = item - fgi * w.chunks;
+#endif
     // hyperplane holding chunk f: smallest r with pe[s_lo + 2r] - base > f   (uniform per warp)
     int lo = 0, hi = w.nT - 1;
     while (lo < hi) {
