@@ -14,7 +14,7 @@ import numpy as np
 
 HERE = Path(__file__).resolve().parent
 MAX_CHANNELS = 4
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 F32, F64, U8, U16, I16, I32 = range(6)
 OPT_SOR_CTAS_PER_SM = 1
@@ -47,7 +47,8 @@ class Plan(C.Structure):
                 ("a_data", C.c_double * MAX_CHANNELS), ("a_smooth", C.c_double),
                 ("sweep", C.c_int32), ("interp", C.c_int32), ("state_dtype", C.c_int32),
                 ("gauss_radius", (C.c_int32 * 3) * MAX_CHANNELS),
-                ("gauss_w", (C.c_void_p * 3) * MAX_CHANNELS)]
+                ("gauss_w", (C.c_void_p * 3) * MAX_CHANNELS),
+                ("gauss_radius_t", C.c_int32 * MAX_CHANNELS), ("gauss_w_t", C.c_void_p * MAX_CHANNELS)]
 
 
 class Fr3dError(RuntimeError):
@@ -85,7 +86,7 @@ def load():
         "fr3d_launch_count": (i64, [vp]),
         "fr3d_device_bytes": (i64, [vp]),
         "fr3d_set_option": (ci, [vp, ci, i64]),
-        "fr3d_preprocess": (ci, [vp, vp, ci, ci, vp, vp, vp]),
+        "fr3d_preprocess": (ci, [vp, vp, ci, ci, vp, vp, ci, vp]),
         "fr3d_set_reference": (ci, [vp, vp, vp, vp]),
         "fr3d_get_displacement": (ci, [vp, vp, vp, ci, vp, ci]),
         "fr3d_level_count": (ci, [vp]),

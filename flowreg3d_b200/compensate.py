@@ -110,7 +110,10 @@ class SequenceCorrector:
         ref_dev = dev.to_device(self.reference_raw, self.device)
         # the reference normalises the fixed volume against ITS OWN range (normalization_ref=None);
         # that is the same (lo, den) as above
-        ref_proc = self.reg.preprocess(ref_dev[None], self.lo, self.den)
+        if self.world > 1 and self.reg.plan.temporal:
+            raise NotImplementedError("a temporal pre-filter (sigma_t >= 0.125) couples the frames of a batch; it is "
+                                      "not implemented for batches sharded over several GPUs")
+        ref_proc = self.reg.preprocess(ref_dev[None], self.lo, self.den, temporal=False)
         self.reg.set_reference(ref_proc[0], weight=weight, ref_raw=ref_dev)
         self.w_init: Optional[torch.Tensor] = None  # (Z,Y,X,3) float32 on device
 

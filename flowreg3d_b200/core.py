@@ -174,9 +174,11 @@ class Registration:
         self.ctx.sync()  # rp / wdev may be temporaries
 
     # -- stages ---------------------------------------------------------------------------
-    def preprocess(self, raw, lo, den, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def preprocess(self, raw, lo, den, out: Optional[torch.Tensor] = None, temporal: bool = True) -> torch.Tensor:
         """(raw - lo)/den then the Gaussian pre-filter; raw (B,Z,Y,X,C) any supported dtype, device
-        tensor or ndarray; returns device float32 (B,Z,Y,X,C)."""
+        tensor or ndarray; returns device float32 (B,Z,Y,X,C).  With a temporal sigma (>= 0.125) the B frames
+        are one batch of the reference and are filtered across frames first; temporal=False is the
+        reference's 4-D input case (fixed volume)."""
         raw_t = self._as_dev(raw, None, None)
         if raw_t.dim() == 4:
             raw_t = raw_t[None]
@@ -188,7 +190,8 @@ class Registration:
         lo = np.broadcast_to(np.asarray(lo, float), (self.C,)).copy()
         den = np.broadcast_to(np.asarray(den, float), (self.C,)).copy()
         _check(self.ctx.h, self.ctx.lib.fr3d_preprocess(self.ctx.h, dev.ptr(raw_t), self._code(raw_t), B,
-                                                        lo.ctypes.data, den.ctypes.data, dev.ptr(out)))
+                                                        lo.ctypes.data, den.ctypes.data, 1 if temporal else 0,
+                                                        dev.ptr(out)))
         self._keep = [raw_t]
         return out
 
@@ -336,14 +339,18 @@ class SplitRegistration:
     def _as_dev(self, a, dtype, shape):
         return self.parts[0]._as_dev(a, dtype, shape)
 
-    def preprocess(self, raw, lo, den, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def preprocess(self, raw, lo, den, out: Optional[torch.Tensor] = None, temporal: bool = True) -> torch.Tensor:
         raw_t = self._as_dev(raw, None, None)
         if raw_t.dim() == 4:
             raw_t = raw_t[None]
         B = raw_t.shape[0]
         if out is None:
             out = dev.empty((B,) + self.shape + (self.C,), np.float32, self.device)
-        self._run(B, lambda r, a, b: r.preprocess(raw_t[a:b], lo, den, out=out[a:b]))
+        if temporal and self.plan.temporal:
+            # the temporal filter couples the frames of the batch: one part takes all of it
+            self._run(1, lambda r, a, b: r.preprocess(raw_t, lo, den, out=out))
+        else:
+            self._run(B, lambda r, a, b: r.preprocess(raw_t[a:b], lo, den, out=out[a:b], temporal=temporal))
         return out
 
     def get_displacement(self, moving_proc, uvw=None, out_dtype=np.float32,

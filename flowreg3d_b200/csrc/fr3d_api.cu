@@ -117,7 +117,7 @@ struct fr3d_ctx {
     std::vector<std::unique_ptr<LevelDev>> levels;
     DevTable to_full[3];
     PreGauss pre;
-    Buf<double> pre_w[FR3D_MAX_CHANNELS][3];
+    Buf<double> pre_w[FR3D_MAX_CHANNELS][3], pre_wt[FR3D_MAX_CHANNELS], gt;
     // workspaces (grow-only)
     Buf<float> t1, t2, f2, tmp, fscr;
     Buf<double> uvw_a, uvw_b, coef, J, AB, dnat, g1, g2, wnat;
@@ -543,6 +543,14 @@ int fr3d_create(fr3d_ctx** out, int device, const fr3d_plan* plan, void* stream)
                     const double* hw = plan->gauss_w[ch][a] ? plan->gauss_w[ch][a] : one.data();
                     c->pre.w[ch][a] = c->pre_w[ch][a].upload(c->dev, hw, (size_t)r + 1);
                 }
+            for (int ch = 0; ch < c->C; ++ch) {
+                const int r = plan->gauss_radius_t[ch];
+                FR3D_REQUIRE(r >= 0 && (r == 0 || plan->gauss_w_t[ch]), "bad temporal Gaussian kernel (c=%d)", ch);
+                c->pre.rt[ch] = r;
+                std::vector<double> one(1, 1.0);
+                const double* hw = plan->gauss_w_t[ch] ? plan->gauss_w_t[ch] : one.data();
+                c->pre.wt[ch] = c->pre_wt[ch].upload(c->dev, hw, (size_t)r + 1);
+            }
             c->has_plan = true;
         }
         c->dev.sync();
@@ -590,7 +598,7 @@ int fr3d_set_option(fr3d_ctx* ctx, int option, int64_t value)
 }
 
 int fr3d_preprocess(fr3d_ctx* ctx, const void* raw, int dtype, int B, const double* lo, const double* den,
-                    float* out)
+                    int temporal_on, float* out)
 {
     FR3D_API_BEGIN(ctx)
     FR3D_REQUIRE(_c->has_plan, "fr3d_preprocess needs a context created with a plan");
@@ -604,6 +612,21 @@ int fr3d_preprocess(fr3d_ctx* ctx, const void* raw, int dtype, int B, const doub
         FR3D_REQUIRE(den[ch] != 0.0, "normalisation denominator is zero");
     }
     const size_t n = (size_t)B * C * Z * Y * X;
+    bool temporal = false;
+    for (int ch = 0; ch < C; ++ch)
+        temporal = temporal || (temporal_on && g.rt[ch] > 0);
+    if (temporal) {
+        // 4-D filter of the reference: the T axis first, on the normalised values; the spatial passes
+        // then read that float64 batch (lo = 0, den = 1 leaves it unchanged)
+        double* tb = _c->gt.ensure(_c->dev, n);
+        launch(_c->dev, PreTK{raw, dtype, tb, B, (int64_t)Z * Y * X * C, C, g}, (int64_t)n);
+        raw = tb;
+        dtype = FR3D_F64;
+        for (int ch = 0; ch < C; ++ch) {
+            g.lo[ch] = 0.0;
+            g.den[ch] = 1.0;
+        }
+    }
     double* a = _c->g1.ensure(_c->dev, n);
     int rz = g.r[0][0];
     for (int ch = 1; ch < C; ++ch)

@@ -85,6 +85,36 @@ struct PreGauss {
     int r[FR3D_MAX_CHANNELS][3];
     const double* w[FR3D_MAX_CHANNELS][3]; // device
     double lo[FR3D_MAX_CHANNELS], den[FR3D_MAX_CHANNELS];
+    int rt[FR3D_MAX_CHANNELS];             // temporal axis (filtered first, across the frames of the call)
+    const double* wt[FR3D_MAX_CHANNELS];
+};
+
+// T pass of the 4-D filter: raw (B,Z,Y,X,C) of dtype -> normalised, temporally filtered float64 of the same
+// layout; item = (b, voxel, c).  Same symmetric summation as the other axes, reflect over the B frames.
+struct PreTK {
+    const void* raw;
+    int dt;
+    double* out;
+    int B;
+    int64_t nvc; // Z*Y*X*C
+    int C;
+    PreGauss g;
+    FR3D_HD double nrm(int64_t o, int b, int c) const
+    {
+        return (load_as_double(raw, dt, (int64_t)b * nvc + o) - g.lo[c]) / g.den[c];
+    }
+    FR3D_HD void operator()(int64_t item) const
+    {
+        const int64_t o = item % nvc;
+        const int b = (int)(item / nvc);
+        const int c = (int)(o % C);
+        const int r = g.rt[c];
+        const double* w = g.wt[c];
+        double t = nrm(o, b, c) * w[0];
+        for (int j = r; j >= 1; --j)
+            t += (nrm(o, reflect_idx(b - j, B), c) + nrm(o, reflect_idx(b + j, B), c)) * w[j];
+        out[item] = t;
+    }
 };
 
 // Z pass: raw (B,Z,Y,X,C) of dtype -> planar float64 (B,C,Z,Y,X); item = (b,z,y,x,c), c fastest.

@@ -131,18 +131,27 @@ def gaussian_half_kernel(sigma: float, truncate: float = 4.0) -> np.ndarray:
 
 def sigma_zyx(sigma, C: int) -> np.ndarray:
     """OFOptions.sigma rows are [sx, sy, sz, st]; the filter wants (sz, sy, sx) per channel
-    (util/image_processing_3D.py:117-130, 140-146).  st must leave frames uncoupled."""
+    (util/image_processing_3D.py:117-130, 140-146)."""
     sig = np.asarray(sigma, dtype=float)
     if sig.ndim == 1:
         sig = sig[None]
     out = np.zeros((C, 3))
     for c in range(C):
         row = sig[min(c, len(sig) - 1)]
-        if len(row) >= 4 and int(4.0 * float(row[3]) + 0.5) > 0:
-            raise NotImplementedError(
-                f"temporal pre-filter sigma_t={row[3]} couples frames of a batch; only sigma_t < 0.125 "
-                "(identity, the reference default 0.1) is implemented on the GPU path")
         out[c] = (row[2], row[1], row[0])
+    return out
+
+
+def sigma_t(sigma, C: int) -> np.ndarray:
+    """Temporal sigma per channel (0 when the rows have no 4th entry): 5-D batches are filtered in 4-D
+    (util/image_processing_3D.py:140-156)."""
+    sig = np.asarray(sigma, dtype=float)
+    if sig.ndim == 1:
+        sig = sig[None]
+    out = np.zeros(C)
+    for c in range(C):
+        row = sig[min(c, len(sig) - 1)]
+        out[c] = float(row[3]) if len(row) >= 4 else 0.0
     return out
 
 
@@ -224,3 +233,11 @@ class PlanHolder:
                 self._keep.append(w)
                 P.gauss_radius[c][a] = len(w) - 1
                 P.gauss_w[c][a] = w.ctypes.data
+        st = sigma_t(sigma, self.C) if sigma is not None else np.zeros(self.C)
+        self.temporal = False
+        for c in range(self.C):
+            w = gaussian_half_kernel(st[c])
+            self._keep.append(w)
+            P.gauss_radius_t[c] = len(w) - 1
+            P.gauss_w_t[c] = w.ctypes.data
+            self.temporal = self.temporal or len(w) > 1

@@ -34,7 +34,7 @@ extern "C" {
 
 #define FR3D_MAX_CHANNELS 4
 #define FR3D_MAX_LEVELS 64
-#define FR3D_ABI_VERSION 2
+#define FR3D_ABI_VERSION 3
 
 typedef enum {
     FR3D_OK = 0,
@@ -98,6 +98,11 @@ typedef struct {
      * w[0..r] (w[0] = centre) per channel and axis (z, y, x); r = 0 means identity.  HOST. */
     int32_t gauss_radius[FR3D_MAX_CHANNELS][3];
     const double* gauss_w[FR3D_MAX_CHANNELS][3];
+    /* temporal axis of the 4-D (t,z,y,x) filter the reference applies to 5-D batches
+     * (image_processing_3D.py:140-156): filtered first, reflect at the ends of the B frames of one
+     * fr3d_preprocess call.  r = 0 (sigma_t < 0.125, the reference default 0.1) means identity. */
+    int32_t gauss_radius_t[FR3D_MAX_CHANNELS];
+    const double* gauss_w_t[FR3D_MAX_CHANNELS];
 } fr3d_plan;
 
 typedef struct fr3d_ctx fr3d_ctx;
@@ -131,9 +136,11 @@ int64_t fr3d_profile_report(fr3d_ctx* ctx, char* buf, int64_t cap);
 /* ---- pipeline (needs a plan) ------------------------------------------------------------ */
 /* Normalise + Gaussian pre-filter (compensate_recording_3D.py:229-254): out = G * ((raw-lo)/den),
  * float64 math, one rounding to float32 (the reference's first resize rounds it the same way).
- * raw: (B,Z,Y,X,C) of `dtype`; lo, den: host, C doubles; out: (B,Z,Y,X,C) float32. */
+ * raw: (B,Z,Y,X,C) of `dtype`; lo, den: host, C doubles; out: (B,Z,Y,X,C) float32.  With a temporal radius
+ * in the plan and temporal != 0 the B frames of the call are one batch of the reference (filtered across
+ * frames first); temporal = 0 is the reference's 4-D (Z,Y,X,C) case (fixed volume: spatial filter only). */
 int fr3d_preprocess(fr3d_ctx* ctx, const void* raw, int dtype, int B, const double* lo,
-                    const double* den, float* out);
+                    const double* den, int temporal, float* out);
 
 /* Cache the fixed volume's pyramid and the weight pyramid (frame-invariant).
  * ref_proc: (Z,Y,X,C) float32 pre-processed reference.  weight: (Z,Y,X,C) float32 or NULL, in which

@@ -189,6 +189,18 @@ def gen_preprocess():
     save("preprocess", **d)
 
 
+def gen_preprocess_t():
+    """Temporal pre-filter: 5-D batches are filtered in 4-D (t, z, y, x) per channel (image_processing_3D.py:140-156)."""
+    rng = np.random.default_rng(12)
+    ref = (np.stack([synth_volume((8, 14, 18), 30 + c) for c in range(2)], -1) * 3000 + 100).astype(np.float32)
+    batch = (ref[None] * (1 + 0.05 * rng.standard_normal((5,) + ref.shape))).astype(np.float32)
+    sigma = np.array([[1.0, 1.0, 1.0, 0.8], [1.5, 1.0, 0.7, 1.2]])
+    r64 = ref.astype(np.float64)
+    save("preprocess_t", ref=ref, batch=batch, sigma=sigma,
+         batch_proc=im3d.apply_gaussian_filter(im3d.normalize(batch, ref=r64, channel_normalization="joint"),
+                                               sigma, mode="reflect", truncate=4.0))
+
+
 def gen_sequence():
     """compensate_arr_3D through the reference's own BatchMotionCorrector (sequential executor)."""
     from flowreg3d.motion_correction.OF_options_3D import OFOptions
@@ -255,6 +267,6 @@ def gen_config1():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["tables", "resize", "warp", "motion_tensor", "solver", "flow_small",
-                             "preprocess", "sequence", "config1"]
+                             "preprocess", "preprocess_t", "sequence", "config1"]
     for w in which:
         globals()[f"gen_{w}"]()

@@ -79,8 +79,7 @@ def test_gaussian_kernel_matches_scipy():
         assert np.array_equal(k[c:c + len(w)], w)
     assert np.array_equal(plan.gaussian_half_kernel(0.0), [1.0])
     assert len(plan.gaussian_half_kernel(0.1)) == 1
-    with pytest.raises(NotImplementedError):
-        plan.sigma_zyx([[1, 1, 1, 0.5]], 1)
+    assert np.array_equal(plan.sigma_t([[1, 1, 1, 0.5], [1, 1, 1, 0.1]], 3), [0.5, 0.1, 0.1])
     assert np.array_equal(plan.sigma_zyx([[1, 2, 3, 0.1]], 2), [[3, 2, 1], [3, 2, 1]])
 
 

@@ -197,3 +197,19 @@ def test_uint16_recording(backend, golden):
     mean, mx = epe_stats(w, ow)
     assert mean <= 1e-5 and mx <= 1e-3, (mean, mx)
     assert (reg != oreg).mean() <= 1e-4          # identical up to a vanishing number of rounding ties
+
+
+def test_sequence_with_temporal_prefilter(backend, golden):
+    """OFOptions.sigma with a temporal component: frames of each batch are coupled in the pre-filter."""
+    import flowreg3d_b200 as F
+    g = golden("sequence")
+    video, ref = g["video"][:5, :12, :24, :28], g["ref"][:12, :24, :28]
+    sigma = [[1.0, 1.0, 1.0, 0.7], [1.0, 1.0, 1.0, 0.7]]
+    opts = F.OFOptions(min_level=2, iterations=6, update_lag=3, buffer_size=3, weight=[0.5, 0.5], sigma=sigma,
+                       output_typename=None)
+    reg, w = F.compensate_arr_3D(video, ref, opts)
+    oreg, ow = O.compensate_arr(video, ref, min_level=2, iterations=6, update_lag=3, buffer_size=3, weight=[0.5, 0.5],
+                                sigma=sigma)
+    mean, mx = epe_stats(w, ow)
+    assert mean <= 1e-5 and mx <= 1e-3, (mean, mx)
+    assert rel_l2(reg, oreg) <= 1e-6

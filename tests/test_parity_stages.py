@@ -200,3 +200,23 @@ def test_preprocess_bit_exact(backend, golden):
     lo, den = normalization_range(r64, "separate")
     assert np.array_equal(dev.to_host(reg.preprocess(batch, lo, den)), f32(g["batch_proc_sep"]))
     reg.ctx.close()
+
+
+def test_preprocess_temporal_filter(backend, golden):
+    """sigma_t >= 0.125: the frames of a batch are filtered across time first (4-D filter of the reference),
+    reflect at the batch ends; the fixed volume (4-D input) is not."""
+    import flowreg3d_b200 as F
+    from flowreg3d_b200 import device as dev
+    from flowreg3d_b200.compensate import normalization_range
+    g = golden("preprocess_t")
+    ref, batch, sigma = g["ref"], g["batch"], g["sigma"]
+    Z, Y, X, C = ref.shape
+    reg = F.Registration((Z, Y, X), C, F.FlowParams(min_level=1, a_smooth=1.0), max_batch=5, sigma=sigma)
+    assert reg.plan.temporal
+    lo, den = normalization_range(ref.astype(np.float64), "joint")
+    got = dev.to_host(reg.preprocess(batch, lo, den))
+    assert np.array_equal(got, g["batch_proc"].astype(np.float32))
+    one = dev.to_host(reg.preprocess(batch[:1], lo, den, temporal=False))
+    spatial_only = O.preprocess(batch[:1], np.concatenate([sigma[:, :3], np.full((2, 1), 0.1)], 1), ref.astype(np.float64))
+    assert np.array_equal(one, spatial_only.astype(np.float32))
+    reg.ctx.close()
