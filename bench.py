@@ -377,6 +377,7 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "kernel": top["kernel"], "achieved": None if ach is None else round(ach, 1),
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": None if ach is None else round(ach / peak, 4),
+                         "frac_of_nominal_8TBs": None if ach is None else round(ach / 8000.0, 4),
                          "traffic": (round(SOR_NCU_DRAM_BYTES_PER_FRAME_VOXEL * B * float(np.mean(level_n)))
                                      if top["kernel"].startswith("fr3d_sor_wavefront") and args.state == "f64"
                                      and args.sweep == "lexicographic" and opts.iterations == 100 else None),
