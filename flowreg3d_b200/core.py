@@ -421,9 +421,13 @@ def get_displacement(fixed, moving, alpha=(2, 2, 2), update_lag=10, iterations=2
     reg = _pair_registration((Z, Y, X), Cn, fp)
     reg.set_reference(fixed.astype(np.float32), weight=weight)
     uv = None if uvw is None else np.asarray(uvw).astype(np.float32)
-    out = reg.get_displacement(moving.astype(np.float32)[None], uvw=uv, out_dtype=np.float64)
+    # With min_level > 0 the flow is the output of the final resize, i.e. float32-exact values (the reference's
+    # imresize casts to float32 too): fetch 12 B/voxel and widen on the host.  At min_level == 0 it is the
+    # float64 accumulation of the level increments.
+    odt = np.float32 if reg.plan.min_level > 0 else np.float64
+    out = reg.get_displacement(moving.astype(np.float32)[None], uvw=uv, out_dtype=odt)
     reg.sync()
-    return dev.to_host(out)[0].copy()
+    return dev.to_host(out)[0].astype(np.float64)
 
 
 # The reference's executors call get_displacement once per frame with the same shape and parameters
