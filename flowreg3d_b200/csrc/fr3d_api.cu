@@ -153,6 +153,26 @@ static void resize_pass(fr3d_ctx* c, const SrcT* src, const int64_t ss[5], DstT*
     const int64_t per = ((1LL << 31) / inner) < 1 ? 1 : ((1LL << 31) / inner);
     for (int64_t b0 = 0; b0 < n[0]; b0 += per) {
         const int64_t nb = n[0] - b0 < per ? n[0] - b0 : per;
+        if (r != 3 && n[3] >= 96) {
+            // 4 outputs per thread along axis 3 (lane + 32u inside blocks of 128) share the tap look-ups
+            ResizePassK<SrcT, DstT, 4> k;
+            const int64_t runs = (n[3] + 127) / 128;
+            k.src = src + b0 * ss[0];
+            k.dst = dst + b0 * ds[0];
+            for (int q = 0; q < 5; ++q) {
+                k.ss[q] = ss[q];
+                k.ds[q] = ds[q];
+                k.fd[q] = FastDiv((uint32_t)(q == 3 ? runs : n[q]));
+            }
+            k.r = r;
+            k.P = t.P;
+            k.n4 = (int)n[4];
+            k.n3 = (int)n[3];
+            k.idx = t.idx.p;
+            k.wt = t.wt.p;
+            launch(c->dev, k, nb * n[1] * n[2] * runs * 32);
+            continue;
+        }
         ResizePassK<SrcT, DstT> k;
         k.src = src + b0 * ss[0];
         k.dst = dst + b0 * ds[0];
@@ -164,6 +184,7 @@ static void resize_pass(fr3d_ctx* c, const SrcT* src, const int64_t ss[5], DstT*
         k.r = r;
         k.P = t.P;
         k.n4 = (int)n[4];
+        k.n3 = (int)n[3];
         k.idx = t.idx.p;
         k.wt = t.wt.p;
         launch(c->dev, k, nb * inner);

@@ -35,22 +35,33 @@ FR3D_HD int mirror_idx(int j, int n)
 // Output iteration space n[0..4] (n[4] fastest); dimension r is the resampled one.
 // Each product is rounded to float32, accumulated in float64 in tap order, stored with one
 // rounding to float32 (then widened if DstT is double).
-template <class SrcT, class DstT>
+// RUN > 1: the thread produces RUN outputs along axis 3, 32 apart (lane + 32u inside a block of 32*RUN, so that
+// every access stays coalesced across the warp); only when axis 3 is not the resampled one.  The tap
+// look-ups and the index arithmetic are shared by the run.
+template <class SrcT, class DstT, int RUN = 1>
 struct ResizePassK {
     const SrcT* src;
     DstT* dst;
     int64_t ss[5], ds[5];
-    FastDiv fd[5]; // divisors n[1..3] at fd[1..3] (item < 2^32); axis 4 is walked inside the thread
+    FastDiv fd[5]; // divisors of the item space at fd[1..3] (axis 3 counted in runs; item < 2^32); axis 4 is walked inside the thread
     int r, P, n4;  // n4 = extent of axis 4 (1 unless the innermost axis is a short interleaved one)
+    int n3;        // extent of axis 3 (outputs)
     const int32_t* idx;
     const float* wt;
     FR3D_HD void operator()(int64_t item) const
     {
         uint32_t i[4];
         uint32_t e = (uint32_t)item;
+        uint32_t lane = 0;
+        if (RUN > 1) {
+            lane = e & 31u;
+            e >>= 5;
+        }
         fd[3].divmod(e, e, i[3]);
         fd[2].divmod(e, e, i[2]);
         fd[1].divmod(e, i[0], i[1]);
+        if (RUN > 1)
+            i[3] = i[3] * (32 * RUN) + lane;
         int64_t so = 0, dof = 0;
         uint32_t ir = 0;
 #pragma unroll
@@ -64,15 +75,45 @@ struct ResizePassK {
         const int32_t* ix = idx + (int64_t)ir * P;
         const float* w = wt + (int64_t)ir * P;
         const int64_t sr = ss[r];
-        for (int q = 0; q < n4; ++q) {
-            const SrcT* sp = src + so + q * ss[4];
-            double acc = 0.0;
-            for (int p = 0; p < P; ++p) {
-                const float a = (float)sp[(int64_t)ix[p] * sr];
-                const float prod = a * w[p];
-                acc += (double)prod;
+        if (RUN == 1) {
+            for (int q = 0; q < n4; ++q) {
+                const SrcT* sp = src + so + q * ss[4];
+                double acc = 0.0;
+                for (int p = 0; p < P; ++p) {
+                    const float a = (float)sp[(int64_t)ix[p] * sr];
+                    const float prod = a * w[p];
+                    acc += (double)prod;
+                }
+                dst[dof + q * ds[4]] = (DstT)(float)acc;
             }
-            dst[dof + q * ds[4]] = (DstT)(float)acc;
+        } else {
+            int nrun = 0;
+#pragma unroll
+            for (int u = 0; u < RUN; ++u)
+                nrun += (int)i[3] + 32 * u < n3;
+            for (int q = 0; q < n4; ++q) {
+                const SrcT* sp = src + so + q * ss[4];
+                double acc[RUN];
+#pragma unroll
+                for (int u = 0; u < RUN; ++u)
+                    acc[u] = 0.0;
+                for (int p = 0; p < P; ++p) {
+                    const SrcT* tp = sp + (int64_t)ix[p] * sr;
+                    const float wp = w[p];
+#pragma unroll
+                    for (int u = 0; u < RUN; ++u) {
+                        if (u < nrun) {
+                            const float a = (float)tp[(int64_t)(32 * u) * ss[3]];
+                            const float prod = a * wp;
+                            acc[u] += (double)prod;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < RUN; ++u)
+                    if (u < nrun)
+                        dst[dof + (int64_t)(32 * u) * ds[3] + q * ds[4]] = (DstT)(float)acc[u];
+            }
         }
     }
 };

@@ -42,7 +42,8 @@ def test_resize_edge_shapes(backend):
     from flowreg3d_b200 import core
     rng = np.random.default_rng(3)
     for shp, size in [((1, 7, 9), (1, 5, 4)), ((5, 6, 7), (5, 6, 7)), ((3, 4, 5), (9, 11, 13)),
-                      ((17, 3, 31), (6, 2, 12)), ((2, 2, 2), (4, 1, 3))]:
+                      ((17, 3, 31), (6, 2, 12)), ((2, 2, 2), (4, 1, 3)),
+                      ((4, 5, 130), (6, 7, 100)), ((3, 4, 40), (5, 9, 150)), ((3, 6, 200), (2, 5, 129))]:  # wide rows: 4-output runs
         a = rng.random(shp).astype(np.float32)
         assert np.array_equal(core.resize(a, size), O.resize(a, size)), (shp, size)
     a = rng.random((6, 7, 8)).astype(np.float32)
