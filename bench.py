@@ -194,11 +194,11 @@ def algorithmic_bytes(name, plan_levels, B, C, iters, lag):
     return None
 
 
-# ncu `dram__bytes_read.sum + dram__bytes_write.sum` of ONE fr3d_sor_wavefront<double,2> launch on the 10x168x168
-# level at B = 16 (profiles/r01_ncu_full_step_b16_f64.txt: 82.370 + 20.494 GB), per frame and level voxel.  The
-# other launch of a step (8x134x134 level) is scaled by its voxel count.  Valid for the default solver
-# (100 sweeps, lag 5, float64 state, lexicographic order) only.
-SOR_NCU_DRAM_BYTES_PER_FRAME_VOXEL = (82.370e9 + 20.494e9) / (16 * 10 * 168 * 168)
+# ncu `dram__bytes_read.sum + dram__bytes_write.sum` of the two fr3d_sor_wavefront<double,2> launches of a step at
+# B = 16 (profiles/r01_sor_dram_traffic_b16_f64.csv: 8x134x134 level 32.50 + 9.68 GB in 14.08 ms, 10x168x168 level
+# 70.47 + 20.28 GB in 24.05 ms), per frame and level voxel.  Valid for the default solver (100 sweeps, lag 5,
+# float64 state, lexicographic order) only.
+SOR_NCU_DRAM_BYTES_PER_FRAME_VOXEL = (32.505e9 + 9.676e9 + 70.472e9 + 20.279e9) / (16 * (8 * 134 * 134 + 10 * 168 * 168))
 
 
 def run_gpu(args):
@@ -381,7 +381,7 @@ def run_gpu(args):
                          "traffic": (round(SOR_NCU_DRAM_BYTES_PER_FRAME_VOXEL * B * float(np.mean(level_n)))
                                      if top["kernel"].startswith("fr3d_sor_wavefront") and args.state == "f64"
                                      and args.sweep == "lexicographic" and opts.iterations == 100 else None),
-                         "traffic_source": "ncu dram bytes per launch (profiles/r01_ncu_full_step_b16_f64.txt), mean of the two levels",
+                         "traffic_source": "ncu dram bytes per launch (profiles/r01_sor_dram_traffic_b16_f64.csv), mean of the two levels",
                          "share_of_step": top["share"]},
             "kernels": table[:8],
             "cpu_baseline": cpu,
