@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib, device as dev
-from .plan import FlowParams, PlanHolder, SWEEP_LEXICOGRAPHIC, TableSet, make_tables
+from .plan import FlowParams, PlanHolder, SWEEP_LEXICOGRAPHIC, make_tables
 
 
 # Storage precision of the solver state (du,dv,dw and the constant Laplacian term) used when a caller
@@ -494,10 +494,6 @@ def imregister_wrapper(f2_level, u, v, w, f1_level, interpolation_method="cubic"
 # --------------------------------------------------------------------------------------------
 # Stage wrappers (numpy in / numpy out) used by the stage-wise parity tests
 # --------------------------------------------------------------------------------------------
-def _np_stage(fn):
-    return fn
-
-
 def resize(img, size):
     """imresize_fused_gauss_cubic3D (util/resize_util_3D.py:114-156) for float images."""
     img = np.asarray(img)

@@ -1235,78 +1235,6 @@ struct ForgetStep<3> {
     }
 };
 
-struct Median5K {
-    const double* src; // (nvol, p, m, n)
-    double* dst;       // (nvol, p, m, n): dst = (add ? add : 0) + median
-    const double* add; // optional (nvol, p, m, n)
-    int p, m, n;
-    FR3D_HD void operator()(int64_t item) const
-    {
-        const int64_t N = (int64_t)p * m * n;
-        const int64_t vol = item / N;
-        const int64_t o = item % N;
-        const int i = (int)(o % n);
-        const int j = (int)((o / n) % m);
-        const int k = (int)(o / ((int64_t)n * m));
-        const double* f = src + vol * N;
-        int zi[5], yi[5], xi[5];
-#pragma unroll
-        for (int d = 0; d < 5; ++d) {
-            zi[d] = mirror_idx(k + d - 2, p);
-            yi[d] = mirror_idx(j + d - 2, m);
-            xi[d] = mirror_idx(i + d - 2, n);
-        }
-        float a[64], rest[61];
-#pragma unroll
-        for (int t = 0; t < 125; ++t) {
-            const float key = (float)f[((int64_t)zi[t / 25] * m + yi[(t / 5) % 5]) * n + xi[t % 5]];
-            if (t < 64)
-                a[t] = key;
-            else
-                rest[t - 64] = key;
-        }
-        const float med = ForgetStep<64>::run(a, rest);
-        // recover the float64 value of rank 62 (0-based)
-        int less = 0, eq = 0;
-        double tmin = 0.0, tmax = 0.0;
-        for (int t = 0; t < 125; ++t) {
-            const double v = f[((int64_t)zi[t / 25] * m + yi[(t / 5) % 5]) * n + xi[t % 5]];
-            const float key = (float)v;
-            less += key < med;
-            if (key == med) {
-                tmin = (eq == 0 || v < tmin) ? v : tmin;
-                tmax = (eq == 0 || v > tmax) ? v : tmax;
-                ++eq;
-            }
-        }
-        double res = tmin;
-        if (tmin != tmax) {
-            // distinct float64 values share the median key (rare; mirrored duplicates are equal and
-            // never get here): walk the tied values in increasing order up to rank (62 - less)
-            int want = 62 - less;
-            double cur = tmin;
-            for (;;) {
-                int mult = 0;
-                double next = tmax;
-                for (int t = 0; t < 125; ++t) {
-                    const double v = f[((int64_t)zi[t / 25] * m + yi[(t / 5) % 5]) * n + xi[t % 5]];
-                    if ((float)v != med)
-                        continue;
-                    mult += v == cur;
-                    if (v > cur && v < next)
-                        next = v;
-                }
-                if (want < mult || cur == tmax)
-                    break;
-                want -= mult;
-                cur = next;
-            }
-            res = cur;
-        }
-        dst[item] = add ? add[item] + res : res;
-    }
-};
-
 // Pair version: one thread produces the medians of two x-adjacent voxels (x = 2*ip, 2*ip + 1).
 // Their windows share 4 of 5 x-columns = 100 samples.  A shared sample with fewer than 37 or more
 // than 62 shared samples below it cannot have exactly 62 of the 125 window samples below it in
