@@ -223,6 +223,7 @@ def run_gpu(args):
 
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    bound = dev.bind_host_to_gpu(device) if world > 1 else []   # NUMA-local pinned buffers for the e2e path
     if world > 1:
         import datetime
         dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(minutes=20))
@@ -368,7 +369,8 @@ def run_gpu(args):
                                   "'kernels' are event-bracketed on each part's stream and include time shared with the other part)"
                                   if len(ctxs) > 1 else "1",
                        "arithmetic": "f64 solver/spline/pre-filter math on f32 images (the reference's rounding points)",
-                       "l2": "inputs (1.07 GB per step) exceed the 126 MB L2"},
+                       "l2": "inputs (1.07 GB per step) exceed the 126 MB L2",
+                       "host_affinity": f"rank 0 bound to {len(bound)} GPU-local cores" if bound else "unchanged"},
             "e2e": {"value": round(frames_total / (ms_e2e * 1e-3), 3), "unit": "volumes/s",
                     "h2d_bytes_per_step": int(B * Z * Y * X * C * 4),
                     "d2h_bytes_per_step": int(B * Z * Y * X * (C + 3) * 4)},

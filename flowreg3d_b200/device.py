@@ -51,3 +51,27 @@ def to_host(t: torch.Tensor) -> np.ndarray:
 
 def ptr(t) -> int:
     return 0 if t is None else t.data_ptr()
+
+
+def bind_host_to_gpu(device: torch.device) -> list:
+    """Pin the calling process to the CPU cores NVML reports as local to `device` (same NUMA node / PCIe root),
+    so that pinned staging buffers allocated afterwards are first-touched next to the GPU.  One process per GPU
+    launchers (torchrun) do not do this.  Returns the cores chosen ([] when nothing was changed)."""
+    import os
+    if device.type != "cuda" or not hasattr(os, "sched_setaffinity"):
+        return []
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(device).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid if not uuid.startswith("GPU-") else uuid).encode())
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        local = {i for i in range(ncpu) if (int(mask[i // 64]) >> (i % 64)) & 1}
+        cpus = sorted(local & set(os.sched_getaffinity(0)))
+        if cpus and len(cpus) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return []
