@@ -95,6 +95,8 @@ def load():
         "fr3d_level_sweeps": (ci, [vp, ci, ci, ci, ci, ci]),
         "fr3d_level_state": (ci, [vp, ci, ci, vp, i64, i64]),
         "fr3d_level_end": (ci, [vp, ci]),
+        "fr3d_level_end_range": (ci, [vp, ci, ci, ci]),
+        "fr3d_flow_slab": (ci, [vp, ci, ci, vp, ci, ci]),
         "fr3d_flow_finish": (ci, [vp, vp, ci]),
         "fr3d_compensate": (ci, [vp, vp, ci, vp, vp, ci, ci, vp]),
         "fr3d_resize3d": (ci, [vp, vp, ci, ci, ci, ci, C.POINTER(AxisTable), vp]),
@@ -121,7 +123,8 @@ EXPORTED_SYMBOLS = [
     "fr3d_abi_version", "fr3d_create", "fr3d_destroy", "fr3d_last_error", "fr3d_synchronize",
     "fr3d_launch_count", "fr3d_device_bytes", "fr3d_set_option", "fr3d_preprocess", "fr3d_set_reference",
     "fr3d_get_displacement", "fr3d_level_count", "fr3d_level_info", "fr3d_level_begin", "fr3d_level_sweeps",
-    "fr3d_level_state", "fr3d_level_end", "fr3d_flow_finish", "fr3d_compensate", "fr3d_resize3d", "fr3d_warp", "fr3d_motion_tensor",
+    "fr3d_level_state", "fr3d_level_end", "fr3d_level_end_range", "fr3d_flow_slab", "fr3d_flow_finish",
+    "fr3d_compensate", "fr3d_resize3d", "fr3d_warp", "fr3d_motion_tensor",
     "fr3d_sor_level", "fr3d_median5", "fr3d_mean_frames", "fr3d_profile_enable",
     "fr3d_profile_report", "fr3d_fill_resize_table",
 ]

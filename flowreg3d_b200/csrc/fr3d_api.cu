@@ -855,9 +855,15 @@ static void level_begin(fr3d_ctx* c, int li, const float* moving, const float* u
 }
 
 // Increments of the open level -> natural layout, 5^3 median, accumulation into the flow (:517-529).
-static void level_end(fr3d_ctx* c, int li)
+// [k0, k0+kn): z range of the flow this call updates (the other planes are left to other ranks; kn < 0 = all).
+static void level_end(fr3d_ctx* c, int li, int k0 = 0, int kn = -1)
 {
     FR3D_REQUIRE(c->run_level == li, "level %d is not open", li);
+    if (kn < 0) {
+        k0 = 0;
+        kn = c->levels[li]->pz;
+    }
+    FR3D_REQUIRE(k0 >= 0 && kn >= 0 && k0 + kn <= c->levels[li]->pz, "bad z range");
     Device& dev = c->dev;
     const int B = c->run_B;
     LevelDev& L = *c->levels[li];
@@ -870,9 +876,14 @@ static void level_end(fr3d_ctx* c, int li)
     run_buffers(c, B, ucur, uprev);
     sor_result(c, c->state_dtype, L.hp, B, dnat);
     if (L.median)
-        launch_occ2(dev, Median5PairK{dnat, ucur, ucur, p, m, n, (n + 1) / 2}, (int64_t)B * 3 * p * m * ((n + 1) / 2));
-    else
+        launch_occ2(dev, Median5PairK{dnat, ucur, ucur, p, m, n, (n + 1) / 2, k0, kn}, (int64_t)B * 3 * kn * m * ((n + 1) / 2));
+    else if (kn == p)
         launch(dev, AddK{ucur, dnat, ucur}, (int64_t)B * 3 * L.N);
+    else
+        for (int v = 0; v < B * 3; ++v) { // unfiltered level: add the slab of every field
+            const int64_t o = (int64_t)v * L.N + (int64_t)k0 * m * n;
+            launch(dev, AddK{ucur + o, dnat + o, ucur + o}, (int64_t)kn * m * n);
+        }
     c->run_level = -1;
     c->run_done = li;
 }
@@ -994,6 +1005,29 @@ int fr3d_level_end(fr3d_ctx* ctx, int level)
 {
     FR3D_API_BEGIN(ctx)
     level_end(_c, level);
+    FR3D_API_END()
+}
+
+int fr3d_level_end_range(fr3d_ctx* ctx, int level, int z_begin, int z_end)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(z_begin <= z_end, "bad z range");
+    level_end(_c, level, z_begin, z_end - z_begin);
+    FR3D_API_END()
+}
+
+int fr3d_flow_slab(fr3d_ctx* ctx, int level, int direction, double* ext, int z_begin, int z_end)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(_c->run_done == level && _c->run_level == -1, "level %d has not been completed", level);
+    FR3D_REQUIRE(ext && (direction == 0 || direction == 1), "bad argument");
+    const LevelDev& L = *_c->levels[level];
+    FR3D_REQUIRE(z_begin >= 0 && z_begin <= z_end && z_end <= L.pz, "bad z range");
+    double *ucur, *uprev;
+    run_buffers(_c, _c->run_B, ucur, uprev);
+    const int64_t plane = (int64_t)L.py * L.px;
+    launch(_c->dev, SlabCopyK{ucur, ext, plane, L.pz, z_begin, z_end - z_begin, direction == 0},
+           (int64_t)_c->run_B * 3 * (z_end - z_begin) * plane);
     FR3D_API_END()
 }
 
@@ -1127,7 +1161,7 @@ int fr3d_median5(fr3d_ctx* ctx, const double* src, int nvol, int p, int m, int n
     FR3D_API_BEGIN(ctx)
     FR3D_REQUIRE(src && dst && nvol >= 1 && p > 0 && m > 0 && n > 0, "bad argument");
     FR3D_REQUIRE(src != dst, "fr3d_median5 cannot run in place");
-    launch_occ2(_c->dev, Median5PairK{src, dst, nullptr, p, m, n, (n + 1) / 2}, (int64_t)nvol * p * m * ((n + 1) / 2));
+    launch_occ2(_c->dev, Median5PairK{src, dst, nullptr, p, m, n, (n + 1) / 2, 0, p}, (int64_t)nvol * p * m * ((n + 1) / 2));
     FR3D_API_END()
 }
 

@@ -1296,6 +1296,7 @@ struct Median5PairK {
     double* dst;       // (nvol, p, m, n): dst = (add ? add : 0) + median
     const double* add; // optional (nvol, p, m, n)
     int p, m, n, npair; // npair = (n + 1) / 2
+    int k0, kn;         // z range [k0, k0 + kn) of the outputs (the whole volume: 0, p)
     // float64 value of rank 62 among the window samples whose float32 key equals med
     FR3D_HD double recover(const double* f, const int* zi, const int* yi, int i, float med) const
     {
@@ -1343,8 +1344,8 @@ struct Median5PairK {
         int64_t q = item / npair;
         const int j = (int)(q % m);
         q /= m;
-        const int k = (int)(q % p);
-        const int64_t vol = q / p;
+        const int k = k0 + (int)(q % kn);
+        const int64_t vol = q / kn;
         const int64_t N = (int64_t)p * m * n;
         const double* f = src + vol * N;
         const int i0 = 2 * ip;
@@ -1394,6 +1395,24 @@ struct AddK {
     const double* b;
     double* dst;
     FR3D_HD void operator()(int64_t i) const { dst[i] = a[i] + b[i]; }
+};
+
+// z-slab [k0, k0+kn) of nvol planar volumes (p, plane) <-> packed (nvol, kn, plane); item = packed index
+struct SlabCopyK {
+    double* vol;
+    double* packed;
+    int64_t plane; // m * n
+    int p, k0, kn, to_packed;
+    FR3D_HD void operator()(int64_t item) const
+    {
+        const int64_t per = (int64_t)kn * plane;
+        const int64_t v = item / per, o = item % per;
+        double* a = vol + v * (int64_t)p * plane + (int64_t)k0 * plane + o;
+        if (to_packed)
+            packed[item] = *a;
+        else
+            *a = packed[item];
+    }
 };
 
 // broadcast a float32 field set (3, N) to (B, 3, N) float64

@@ -11,9 +11,11 @@ hyperplane-major) while both keep sweeping -- a one-directional NVLink pipeline 
 NCCL send/recv per level, no per-wave synchronisation between GPUs, and exactly the reference's
 update order (the result is bit-identical to the single-GPU solve).
 
-Everything around the solve (pyramid, warp, assembly, median) is computed redundantly on every rank
-from the same inputs -- it is deterministic, so all ranks stay identical without communication; only
-levels large enough to be bandwidth-bound are pipelined, small ones are solved redundantly too.
+The 5x5x5 median of the increments (a fifth of the time of a large level) is z-slab parallel: every rank
+holds the finished increments, filters its own planes and the flow slabs are exchanged.  Everything else
+around the solve (pyramid, warp, assembly) is computed redundantly on every rank from the same inputs -- it
+is deterministic, so all ranks stay identical without communication; only levels large enough to be
+bandwidth-bound are pipelined, small ones are solved redundantly too.
 
     reg  = Registration(shape, C, params, max_batch=1)        # on every rank, same arguments
     reg.set_reference(fixed_proc)
@@ -151,10 +153,32 @@ def get_displacement_pipelined(reg: Registration, moving_proc, uvw=None, group=N
             if rank != active[-1]:
                 _check(h, lib.fr3d_level_state(h, li, 1, dev.ptr(full), 0, nslots))
             keep.append(full)
+            # z-slab parallel median / accumulation: own planes, then one broadcast per rank's slab
+            (pz, py, px) = _level_info(reg, li)[0]
+            bounds = [_split(pz, world, r) for r in range(world)]
+            z0, z1 = bounds[rank]
+            _check(h, lib.fr3d_level_end_range(h, li, z0, z1))
+            for r, (a, b) in enumerate(bounds):
+                if b <= a:
+                    continue
+                slab = dev.empty((B, 3, b - a, py, px), np.float64, reg.device)
+                if r == rank:
+                    _check(h, lib.fr3d_flow_slab(h, li, 0, dev.ptr(slab), a, b))
+                dist.broadcast(slab, src=_global_rank(group, r), group=group)
+                if r != rank:
+                    _check(h, lib.fr3d_flow_slab(h, li, 1, dev.ptr(slab), a, b))
+                keep.append(slab)
+            continue
         _check(h, lib.fr3d_level_end(h, li))
     _check(h, lib.fr3d_flow_finish(h, dev.ptr(out), reg._code(out)))
     reg._keep = [mv, uv, keep]
     return out
+
+
+def _split(n: int, world: int, rank: int) -> Tuple[int, int]:
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
 
 
 def _global_rank(group, r: int) -> int:

@@ -179,6 +179,12 @@ int fr3d_level_sweeps(fr3d_ctx* ctx, int level, int t_begin, int t_end, int q_be
 int fr3d_level_state(fr3d_ctx* ctx, int level, int direction, void* ext, int64_t slot_begin,
                      int64_t slot_end);
 int fr3d_level_end(fr3d_ctx* ctx, int level);
+/* fr3d_level_end restricted to the planes z_begin <= z < z_end of the level's flow (the median of a plane needs
+ * the increments of two planes on either side, which every rank holds); the other planes of the flow are then
+ * fetched from the ranks that computed them:  fr3d_flow_slab copies the planes [z_begin, z_end) of the level's
+ * flow out of (direction 0) or into (direction 1) `ext` (device, B x 3 x (z_end - z_begin) x py x px float64). */
+int fr3d_level_end_range(fr3d_ctx* ctx, int level, int z_begin, int z_end);
+int fr3d_flow_slab(fr3d_ctx* ctx, int level, int direction, double* ext, int z_begin, int z_end);
 int fr3d_flow_finish(fr3d_ctx* ctx, void* flow_out, int out_dtype);
 
 /* Compensation warp of B raw frames (parallelization/sequential_3d.py:153-160):
