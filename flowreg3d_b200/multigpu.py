@@ -117,6 +117,8 @@ def get_displacement_pipelined(reg: Registration, moving_proc, uvw=None, group=N
     pipelinable = reg.plan.plan.sweep == 0 and float(reg.plan.plan.a_smooth) == 1.0
     nl = lib.fr3d_level_count(h)
     keep = []
+    if world > 1 and pipelinable:
+        _pair_group(group, world, 0, 1)         # collective: every rank builds the pair communicators
     for li in range(nl):
         _check(h, lib.fr3d_level_begin(h, li, dev.ptr(mv), dev.ptr(uv), B))
         _, S, nslots, start = _level_info(reg, li)
@@ -131,20 +133,30 @@ def get_displacement_pipelined(reg: Registration, moving_proc, uvw=None, group=N
                 pos = active.index(rank)
                 src = active[pos - 1] if pos > 0 else None
                 dst = active[pos + 1] if pos + 1 < len(active) else None
-                for rcv, q0, q1, snd in sched[rank]:
+                # one communicator per neighbouring pair: the receives from rank-1 and the sends to rank+1 then
+                # progress independently (on one communicator NCCL would serialise them into a lock-step chain);
+                # all receives of the level are posted up front
+                g_in = _pair_group(group, world, src, rank) if src is not None else None
+                g_out = _pair_group(group, world, rank, dst) if dst is not None else None
+                pending = []
+                for rcv, _, _, _ in sched[rank]:
                     if rcv is not None:
                         a, b = int(start[rcv[0]]), int(start[rcv[1]])
                         buf = dev.empty((B, b - a, 4), state_dt, reg.device)
-                        dist.recv(buf, src=_global_rank(group, src), group=group)
-                        _check(h, lib.fr3d_level_state(h, li, 1, dev.ptr(buf), a, b))
+                        pending.append((buf, dist.irecv(buf, src=_global_rank(group, src), group=g_in)))
                         keep.append(buf)
+                for rcv, q0, q1, snd in sched[rank]:
+                    if rcv is not None:
+                        a, b = int(start[rcv[0]]), int(start[rcv[1]])
+                        buf, work = pending.pop(0)
+                        work.wait()
+                        _check(h, lib.fr3d_level_state(h, li, 1, dev.ptr(buf), a, b))
                     _check(h, lib.fr3d_level_sweeps(h, li, t0, t1, q0, q1))
                     if snd is not None:
                         a, b = int(start[snd[0]]), int(start[snd[1]])
                         buf = dev.empty((B, b - a, 4), state_dt, reg.device)
                         _check(h, lib.fr3d_level_state(h, li, 0, dev.ptr(buf), a, b))
-                        dist.send(buf, dst=_global_rank(group, dst), group=group)
-                        keep.append(buf)
+                        keep.append((buf, dist.isend(buf, dst=_global_rank(group, dst), group=g_out)))
             # the last active rank holds the finished increments: hand them to everybody
             full = dev.empty((B, nslots, 4), state_dt, reg.device)
             if rank == active[-1]:
@@ -173,6 +185,22 @@ def get_displacement_pipelined(reg: Registration, moving_proc, uvw=None, group=N
     _check(h, lib.fr3d_flow_finish(h, dev.ptr(out), reg._code(out)))
     reg._keep = [mv, uv, keep]
     return out
+
+
+_PAIR_GROUPS: dict = {}
+
+
+def _pair_group(group, world: int, a: int, b: int):
+    """Process group of the neighbouring ranks (a, b).  new_group is collective over the parent group, so the
+    groups of ALL neighbouring pairs are created together, once, in the same order on every rank."""
+    key = (id(group), world)
+    if key not in _PAIR_GROUPS:
+        pairs = {}
+        for r in range(world - 1):
+            ranks = [_global_rank(group, r), _global_rank(group, r + 1)]
+            pairs[(r, r + 1)] = dist.new_group(ranks=ranks)
+        _PAIR_GROUPS[key] = pairs
+    return _PAIR_GROUPS[key][(a, b)]
 
 
 def _split(n: int, world: int, rank: int) -> Tuple[int, int]:
