@@ -369,7 +369,7 @@ def run_gpu(args):
                                   "'kernels' are event-bracketed on each part's stream and include time shared with the other part)"
                                   if len(ctxs) > 1 else "1",
                        "arithmetic": "f64 solver/spline/pre-filter math on f32 images (the reference's rounding points)",
-                       "l2": "inputs (1.07 GB per step) exceed the 126 MB L2",
+                       "l2": f"inputs ({B * Z * Y * X * C * 4 / 2 ** 30:.2f} GiB per step) exceed the 126 MB L2",
                        "host_affinity": f"rank 0 bound to {len(bound)} GPU-local cores" if bound else "unchanged"},
             "e2e": {"value": round(frames_total / (ms_e2e * 1e-3), 3), "unit": "volumes/s",
                     "h2d_bytes_per_step": int(B * Z * Y * X * C * 4),
@@ -419,7 +419,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="frames per GPU per step")
+    ap.add_argument("--batch", type=int, default=25,
+                    help="frames per GPU per step (OFOptions.buffer_size; 25 = the 200-frame recording of config 2 "
+                         "in 8 batches, or one batch per GPU at 8 GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=1, help="concurrent half-batch pipelines per GPU")
     ap.add_argument("--sweep", default="lexicographic", choices=["lexicographic", "redblack"],
