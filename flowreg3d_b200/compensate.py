@@ -160,6 +160,9 @@ class SequenceCorrector:
             first = G - 20 if G > 20 else 0
             a, b = max(0, first - local_offset), t
             self.w_init = self._mean_of(flows[a:b] if (flows is not None and b > a) else None, G - first)
+        # flows are final here: the host pipeline may start fetching them while the compensation warp runs
+        self._flows_ready = (torch.cuda.current_stream(self.device).record_event()
+                             if self.device.type == "cuda" else None)
         reg = None
         if compensate and t > 0:
             outs = []
@@ -273,9 +276,10 @@ class SequenceCorrector:
             # host buffer k % 2 must have been consumed (batch k-2 drained below) before it is refilled
             if t > 0:
                 with torch.cuda.stream(s_out):
+                    s_out.wait_event(self._flows_ready)        # the flow fields go first, under the compensation warp
+                    out_flow[k][:t].copy_(fl, non_blocking=True)
                     s_out.wait_event(ev_done[k])
                     out_reg[k][:t].copy_(reg, non_blocking=True)
-                    out_flow[k][:t].copy_(fl, non_blocking=True)
                     reg.record_stream(s_out)
                     fl.record_stream(s_out)
                     ev_out[k] = s_out.record_event()
