@@ -204,6 +204,8 @@ SOR_NCU_DRAM_BYTES_PER_FRAME_VOXEL = (32.505e9 + 9.676e9 + 70.472e9 + 20.279e9) 
 def run_gpu(args):
     import torch
     import torch.distributed as dist
+    from flowreg3d_b200 import build as fr3d_build
+    fr3d_build.ensure_built(int(os.environ.get("LOCAL_RANK", "0")))     # no-op when libfr3d.so is present
     import flowreg3d_b200 as F
     from flowreg3d_b200 import core, device as dev
 

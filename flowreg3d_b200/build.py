@@ -57,6 +57,27 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return OUT
 
 
+def ensure_built(local_rank: int = 0, timeout_s: float = 600.0) -> Path:
+    """Build the library if (and only if) it is MISSING -- e.g. a fresh checkout on a box with nvcc.  Safe under a
+    one-process-per-GPU launcher: local rank 0 compiles into a temporary name and renames, the others wait for
+    the file.  This builds the CUDA extension; it is not a fallback (without nvcc it raises)."""
+    import time
+    if OUT.exists():
+        return OUT
+    if local_rank == 0:
+        tmp = OUT.with_suffix(".so.tmp%d" % os.getpid())
+        cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(tmp), *map(str, sources())]
+        subprocess.check_call(cmd)
+        os.replace(tmp, OUT)
+        return OUT
+    t0 = time.time()
+    while not OUT.exists():
+        if time.time() - t0 > timeout_s:
+            raise RuntimeError(f"{OUT} did not appear within {timeout_s:.0f} s (local rank 0 builds it)")
+        time.sleep(0.5)
+    return OUT
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(OUT)

@@ -53,6 +53,8 @@ def _select(backend):
     else:
         import torch
         assert torch.cuda.is_available(), "gpu-marked test running without a CUDA device"
+        from flowreg3d_b200 import build as fr3d_build
+        fr3d_build.ensure_built()                 # fresh checkout: compile once (needs nvcc); no-op otherwise
         _lib._select_for_tests(None)
         lib = _lib.load()
         assert not _lib.is_emulator() and str(_lib.library_path()).endswith("libfr3d.so")
