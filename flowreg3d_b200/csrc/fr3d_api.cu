@@ -379,9 +379,7 @@ static void sor_prepare_t(fr3d_ctx* c, const HPGeom& hp, int B, int C, const flo
     as.uvw = uvw;
     as.J = Jpre ? nullptr : J;
     as.L = const_cast<Vec4<ST>*>(P.L);
-    as.d = P.d;
     as.U = const_cast<Vec4<ST>*>(P.U);
-    as.dold = P.dold;
     as.hp = P.g;
     as.g = MTGeom{hp.p, hp.m, hp.n, hz, hy, hx, f2f32};
     as.B = B;
@@ -389,7 +387,14 @@ static void sor_prepare_t(fr3d_ctx* c, const HPGeom& hp, int B, int C, const flo
     as.ax = P.ax;
     as.ay = P.ay;
     as.az = P.az;
-    launch_occ2(dev, as, (int64_t)B * np);
+    // pad slots of the vectors the solver or the state copies may touch: cleared once, the kernel fills the rest
+    dev.zero(P.d, (size_t)B * np * sizeof(Vec4<ST>));
+    dev.zero(const_cast<Vec4<ST>*>(P.L), (size_t)B * np * sizeof(Vec4<ST>));
+    if (P.U) {
+        dev.zero(const_cast<Vec4<ST>*>(P.U), (size_t)B * np * sizeof(Vec4<ST>));
+        dev.zero(P.dold, (size_t)B * np * sizeof(Vec4<ST>));
+    }
+    launch_occ2(dev, as, (int64_t)B * hp.p * hp.m * hp.n);
     c->sp_hp = &hp;
 }
 

@@ -1054,7 +1054,7 @@ struct HPBuildK {
 // Assemble the level system directly in solver storage: motion tensor J (B,C,10,npad), the constant
 // part of the smoothness term L = ax*(u_ip+u_im-2u) + ay*(...) + az*(...) for u,v,w, with replicate
 // boundary (the reference's edge-padded ring, core/optical_flow_3d.py:88-89,418-426), and the
-// zero-initialised increments.  item = (b, slot).
+// (the increments are zero-initialised by the caller).
 template <class ST>
 struct AssembleK {
     const float* f1;   // (C, N) planar natural, shared by all frames
@@ -1062,33 +1062,22 @@ struct AssembleK {
     const double* uvw; // (B, 3, N) natural
     double* J;         // (B, C, 10, npad) or null
     Vec4<ST>* L;       // (B, npad)
-    Vec4<ST>* d;       // (B, npad)
     Vec4<ST>* U;       // (B, npad) u, v, w in solver storage, or null (nonlinear smoothness only)
-    Vec4<ST>* dold;    // (B, npad) zero-initialised, or null
     HPView hp;
     MTGeom g;
     int B, C;
     double ax, ay, az; // alpha/h^2
+    // item = (b, natural voxel index): the 33-point image stencils and the Laplacian read coalesced rows; the
+    // results are scattered to the voxel's solver slot (pad slots are cleared by the caller's memset)
     FR3D_HD void operator()(int64_t item) const
     {
         const int64_t N = hp.nvox(), np = hp.npad;
-        const int64_t a = item % np;
-        const int b = (int)(item / np);
-        Vec4<ST> zero;
-        zero.x = zero.y = zero.z = zero.w = (ST)0;
-        d[(int64_t)b * np + a] = zero;
-        if (dold)
-            dold[(int64_t)b * np + a] = zero;
-        const int32_t nat = hp.perm[a];
-        if (nat < 0) {
-            L[(int64_t)b * np + a] = zero;
-            if (U)
-                U[(int64_t)b * np + a] = zero;
-            return;
-        }
-        const int i = nat % g.n;
-        const int j = (nat / g.n) % g.m;
-        const int k = nat / (g.n * g.m);
+        const int64_t nat = item % N;
+        const int b = (int)(item / N);
+        const int i = (int)(nat % g.n);
+        const int j = (int)((nat / g.n) % g.m);
+        const int k = (int)(nat / ((int64_t)g.n * g.m));
+        const int64_t a = hp.addr(k, j, i);
         if (J) {
             for (int c = 0; c < C; ++c) {
                 MTImages im{f1 + (int64_t)c * N, f2 + ((int64_t)b * C + c) * N, g};
