@@ -11,6 +11,8 @@ from oracle import oracle as O
 from tests_inputs import synth_volume
 
 RUNS = {
+    "ml1s": dict(alpha=(0.5,) * 3, update_lag=10, iterations=15, min_level=1, levels=100, eta=0.8,
+                 a_smooth=0.5, a_data=0.45),                     # nonlinear smoothness term
     "ml0": dict(alpha=(0.25,) * 3, update_lag=5, iterations=30, min_level=0, levels=100, eta=0.8,
                 a_smooth=1.0, a_data=0.45),
     "ml2w": dict(alpha=(0.25, 0.3, 0.2), update_lag=5, iterations=20, min_level=2, levels=100, eta=0.8,
@@ -19,7 +21,7 @@ RUNS = {
 
 
 @pytest.mark.parametrize("state", ["f32", "f64"])
-@pytest.mark.parametrize("run", ["ml2w", "ml0", "ml2w_uvw"])
+@pytest.mark.parametrize("run", ["ml2w", "ml0", "ml2w_uvw", "ml1s"])
 def test_get_displacement_vs_reference_and_oracle(backend, golden, run, state, monkeypatch):
     """state f64 = the shipped default; f32 = reduced-traffic mode (solver increments stored in float32)."""
     import flowreg3d_b200 as F
