@@ -105,6 +105,7 @@ def load():
         "fr3d_sor_level": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, vp, cd, cd, cd, ci, ci, vp, cd, ci, ci, vp]),
         "fr3d_median5": (ci, [vp, vp, ci, ci, ci, ci, vp]),
         "fr3d_mean_frames": (ci, [vp, vp, ci, i64, vp]),
+        "fr3d_flow_stats": (ci, [vp, vp, ci, ci, ci, ci, vp]),
         "fr3d_profile_enable": (ci, [vp, ci]),
         "fr3d_profile_report": (i64, [vp, C.c_char_p, i64]),
         "fr3d_fill_resize_table": (ci, [ci, ci, vp, ci, vp, vp]),
@@ -125,7 +126,7 @@ EXPORTED_SYMBOLS = [
     "fr3d_get_displacement", "fr3d_level_count", "fr3d_level_info", "fr3d_level_begin", "fr3d_level_sweeps",
     "fr3d_level_state", "fr3d_level_end", "fr3d_level_end_range", "fr3d_flow_slab", "fr3d_flow_finish",
     "fr3d_compensate", "fr3d_resize3d", "fr3d_warp", "fr3d_motion_tensor",
-    "fr3d_sor_level", "fr3d_median5", "fr3d_mean_frames", "fr3d_profile_enable",
+    "fr3d_sor_level", "fr3d_median5", "fr3d_mean_frames", "fr3d_flow_stats", "fr3d_profile_enable",
     "fr3d_profile_report", "fr3d_fill_resize_table",
 ]
 

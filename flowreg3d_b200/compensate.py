@@ -70,7 +70,7 @@ class SequenceCorrector:
     """Stateful batch processor: owns the Registration, the fixed volume and the w_init chain."""
 
     def __init__(self, reference_raw: np.ndarray, options, max_batch: Optional[int] = None,
-                 device: Optional[torch.device] = None, group=None, streams: int = 1):
+                 device: Optional[torch.device] = None, group=None, streams: int = 1, statistics: bool = False):
         if bool(getattr(options, "cc_initialization", False)):
             raise NotImplementedError("cc_initialization is not implemented on the B200 path")
         if bool(getattr(options, "update_reference", False)):
@@ -116,6 +116,8 @@ class SequenceCorrector:
         ref_proc = self.reg.preprocess(ref_dev[None], self.lo, self.den, temporal=False)
         self.reg.set_reference(ref_proc[0], weight=weight, ref_raw=ref_dev)
         self.w_init: Optional[torch.Tensor] = None  # (Z,Y,X,3) float32 on device
+        self.collect_statistics = bool(statistics)
+        self._stats: List[torch.Tensor] = []        # per batch (t,4) device tensors, see statistics()
 
     # -- helpers ------------------------------------------------------------------------
     def _flows(self, proc: torch.Tensor, uvw: Optional[torch.Tensor]) -> torch.Tensor:
@@ -160,6 +162,8 @@ class SequenceCorrector:
             first = G - 20 if G > 20 else 0
             a, b = max(0, first - local_offset), t
             self.w_init = self._mean_of(flows[a:b] if (flows is not None and b > a) else None, G - first)
+        if t > 0 and self.collect_statistics:
+            self._stats.append(self.reg.flow_stats(flows))      # stays on the device until statistics() is read
         # flows are final here: the host pipeline may start fetching them while the compensation warp runs
         self._flows_ready = (torch.cuda.current_stream(self.device).record_event()
                              if self.device.type == "cuda" else None)
@@ -288,6 +292,15 @@ class SequenceCorrector:
         main.synchronize()
         drain(K - 1)
         return out_reg, out_flow
+
+    def statistics(self) -> dict:
+        """The per-frame lists BatchMotionCorrector keeps (compensate_recording_3D.py:488-508) for this rank's
+        frames so far: mean_disp, max_disp, mean_div, mean_translation (computed on the device from the flows)."""
+        if not self._stats:
+            return {"mean_disp": [], "max_disp": [], "mean_div": [], "mean_translation": []}
+        a = dev.to_host(torch.cat(self._stats, 0))
+        return {"mean_disp": a[:, 0].tolist(), "max_disp": a[:, 1].tolist(), "mean_div": a[:, 2].tolist(),
+                "mean_translation": a[:, 3].tolist()}
 
     def close(self):
         if isinstance(self.reg, SplitRegistration):

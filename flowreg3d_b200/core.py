@@ -241,6 +241,17 @@ class Registration:
         self._keep = [fr]
         return out
 
+    def flow_stats(self, flows: torch.Tensor) -> torch.Tensor:
+        """Per-frame statistics of BatchMotionCorrector (compensate_recording_3D.py:488-508) for float32 device
+        flows (B,Z,Y,X,3): (B,4) float64 = mean |w|, max |w|, mean divergence, |mean translation|."""
+        fl = flows.contiguous()
+        B = fl.shape[0]
+        Z, Y, X = self.shape
+        out = dev.empty((B, 4), np.float64, self.device)
+        _check(self.ctx.h, self.ctx.lib.fr3d_flow_stats(self.ctx.h, dev.ptr(fl), B, Z, Y, X, dev.ptr(out)))
+        self._keep = [fl]
+        return out
+
     def sync(self):
         self.ctx.sync()
 
@@ -380,6 +391,11 @@ class SplitRegistration:
     def mean_frames(self, frames: torch.Tensor) -> torch.Tensor:
         res = []
         self._run(1, lambda r, a, b: res.append(r.mean_frames(frames)))
+        return res[0]
+
+    def flow_stats(self, flows: torch.Tensor) -> torch.Tensor:
+        res = []
+        self._run(1, lambda r, a, b: res.append(r.flow_stats(flows)))
         return res[0]
 
     def sync(self):

@@ -1208,6 +1208,26 @@ int64_t fr3d_profile_report(fr3d_ctx* ctx, char* buf, int64_t cap)
     return (int64_t)out.size();
 }
 
+int fr3d_flow_stats(fr3d_ctx* ctx, const float* flow, int B, int Z, int Y, int X, double* out)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(flow && out && B >= 1 && Z > 0 && Y > 0 && X > 0, "bad argument");
+    const int64_t N = (int64_t)Z * Y * X;
+    double* acc = _c->wnat.ensure(_c->dev, (size_t)B * 6);
+    _c->dev.zero(acc, (size_t)B * 6 * sizeof(double));
+    FlowStatsK k;
+    k.flow = flow;
+    k.acc = acc;
+    k.Z = Z;
+    k.Y = Y;
+    k.X = X;
+    k.chunk = 256 * 64;
+    k.chunks = (int)((N + k.chunk - 1) / k.chunk);
+    launch_tiles(_c->dev, k, (int64_t)B * k.chunks, 256, (size_t)256 * 6 * sizeof(double));
+    launch(_c->dev, FlowStatsFinishK{acc, out, 1.0 / (double)N}, B);
+    FR3D_API_END()
+}
+
 int fr3d_mean_frames(fr3d_ctx* ctx, const float* frames, int T, int64_t n, float* out)
 {
     FR3D_API_BEGIN(ctx)

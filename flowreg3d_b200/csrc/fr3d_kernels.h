@@ -1444,6 +1444,112 @@ struct MeanFramesK {
     }
 };
 
+// Per-frame flow statistics of BatchMotionCorrector (compensate_recording_3D.py:488-508): mean and max of the
+// displacement magnitude, mean divergence (numpy.gradient: central differences, one-sided at the ends, unit
+// spacing) and the mean of each component.  Tile kernel: block = (frame, chunk of voxels); partial sums are
+// reduced in shared memory and added to the frame's accumulators (float64; max through its bit pattern, which
+// orders like the value for non-negative numbers).  acc: (B, 6) = sum|w|, max|w| bits, sum div, sum u, sum v, sum w.
+struct FlowStatsK {
+    static constexpr int PHASES = 2;
+    const float* flow; // (B, Z, Y, X, 3)
+    double* acc;       // (B, 6), zero-initialised
+    int Z, Y, X;
+    int64_t chunk;     // voxels per block
+    int chunks;        // blocks per frame
+    FR3D_HD float comp(const float* f, int z, int y, int x, int q) const
+    {
+        return f[(((int64_t)z * Y + y) * X + x) * 3 + q];
+    }
+    FR3D_HD float grad(const float* f, int z, int y, int x, int q, int ax) const
+    {
+        const int n = ax == 0 ? Z : (ax == 1 ? Y : X);
+        const int c = ax == 0 ? z : (ax == 1 ? y : x);
+        if (n < 2)
+            return 0.0f;
+        const int lo = c > 0 ? c - 1 : c, hi = c < n - 1 ? c + 1 : c;
+        const float a = comp(f, ax == 0 ? lo : z, ax == 1 ? lo : y, ax == 2 ? lo : x, q);
+        const float b = comp(f, ax == 0 ? hi : z, ax == 1 ? hi : y, ax == 2 ? hi : x, q);
+        return (b - a) / (float)(hi - lo);
+    }
+    FR3D_HD void phase(int ph, int64_t blk, int tid, int nthreads, double* sm) const
+    {
+        const int b = (int)(blk / chunks);
+        const int64_t v0 = (blk % chunks) * chunk;
+        const int64_t N = (int64_t)Z * Y * X;
+        const int64_t v1 = v0 + chunk < N ? v0 + chunk : N;
+        const float* f = flow + (int64_t)b * N * 3;
+        double* part = sm + (size_t)tid * 6;
+        if (ph == 0) {
+            double s_mag = 0.0, s_div = 0.0, s_u = 0.0, s_v = 0.0, s_w = 0.0;
+            float mx = 0.0f;
+            for (int64_t v = v0 + tid; v < v1; v += nthreads) {
+                const int x = (int)(v % X);
+                const int y = (int)((v / X) % Y);
+                const int z = (int)(v / ((int64_t)X * Y));
+                const float u = f[v * 3], vv = f[v * 3 + 1], w = f[v * 3 + 2];
+                const float mag = sqrtf(u * u + vv * vv + w * w);
+                s_mag += (double)mag;
+                mx = fmaxf(mx, mag);
+                s_div += (double)(grad(f, z, y, x, 0, 2) + grad(f, z, y, x, 1, 1) + grad(f, z, y, x, 2, 0));
+                s_u += (double)u;
+                s_v += (double)vv;
+                s_w += (double)w;
+            }
+            part[0] = s_mag;
+            part[1] = (double)mx;
+            part[2] = s_div;
+            part[3] = s_u;
+            part[4] = s_v;
+            part[5] = s_w;
+            return;
+        }
+        if (tid != 0)
+            return;
+        double t[6] = {0, 0, 0, 0, 0, 0};
+        for (int k = 0; k < nthreads; ++k) {
+            const double* p = sm + (size_t)k * 6;
+            t[0] += p[0];
+            t[1] = p[1] > t[1] ? p[1] : t[1];
+            t[2] += p[2];
+            t[3] += p[3];
+            t[4] += p[4];
+            t[5] += p[5];
+        }
+        double* a = acc + (int64_t)b * 6;
+#ifdef __CUDA_ARCH__
+        atomicAdd(a + 0, t[0]);
+        atomicMax(reinterpret_cast<unsigned long long*>(a + 1), (unsigned long long)__double_as_longlong(t[1]));
+        atomicAdd(a + 2, t[2]);
+        atomicAdd(a + 3, t[3]);
+        atomicAdd(a + 4, t[4]);
+        atomicAdd(a + 5, t[5]);
+#else
+        a[0] += t[0];
+        a[1] = t[1] > a[1] ? t[1] : a[1];
+        a[2] += t[2];
+        a[3] += t[3];
+        a[4] += t[4];
+        a[5] += t[5];
+#endif
+    }
+};
+
+// (B,6) accumulators -> (B,4): mean |w|, max |w|, mean divergence, |mean translation|
+struct FlowStatsFinishK {
+    const double* acc;
+    double* out;
+    double inv_n;
+    FR3D_HD void operator()(int64_t b) const
+    {
+        const double* a = acc + b * 6;
+        const double mu = a[3] * inv_n, mv = a[4] * inv_n, mw = a[5] * inv_n;
+        out[b * 4 + 0] = a[0] * inv_n;
+        out[b * 4 + 1] = a[1];
+        out[b * 4 + 2] = a[2] * inv_n;
+        out[b * 4 + 3] = sqrt(mu * mu + mv * mv + mw * mw);
+    }
+};
+
 template <class T>
 struct FillK {
     T* dst;

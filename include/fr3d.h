@@ -230,6 +230,12 @@ int fr3d_median5(fr3d_ctx* ctx, const double* src, int nvol, int p, int m, int n
  * BatchMotionCorrector (compensate_recording_3D.py:388, 481-485), float32 accumulation in frame order. */
 int fr3d_mean_frames(fr3d_ctx* ctx, const float* frames, int T, int64_t n, float* out);
 
+/* Per-frame statistics BatchMotionCorrector keeps (compensate_recording_3D.py:488-508), computed where the flow
+ * lives: flow (B,Z,Y,X,3) float32 -> out (B,4) float64 (device) = mean |w|, max |w|, mean divergence
+ * (numpy.gradient semantics, unit spacing), |mean translation|.  float64 accumulation (the reference
+ * accumulates in float32: agreement to ~1e-6 relative, not bit-exact). */
+int fr3d_flow_stats(fr3d_ctx* ctx, const float* flow, int B, int Z, int Y, int X, double* out);
+
 /* ---- host helpers ----------------------------------------------------------------------- */
 /* util/resize_util_3D.py:76-95: fill idx/wt (host, out_len*(2R+4)) from the float32 Gaussian g
  * (host, 2R+1 taps; numpy-computed by the caller so that it is bit-identical to the reference). */

@@ -215,3 +215,25 @@ def test_sequence_with_temporal_prefilter(backend, golden):
     mean, mx = epe_stats(w, ow)
     assert mean <= 1e-5 and mx <= 1e-3, (mean, mx)
     assert rel_l2(reg, oreg) <= 1e-6
+
+
+def test_flow_statistics(backend, golden):
+    """mean / max displacement, mean divergence and mean translation per frame, as BatchMotionCorrector computes
+    them from the returned flows (compensate_recording_3D.py:488-508)."""
+    import flowreg3d_b200 as F
+    g = golden("sequence")
+    video, ref = g["video"][:4, :12, :24, :28], g["ref"][:12, :24, :28]
+    opts = F.OFOptions(min_level=2, iterations=6, update_lag=3, buffer_size=3, weight=[0.5, 0.5])
+    seq = F.SequenceCorrector(ref, opts, statistics=True)
+    _, flows = seq.run_pipelined([video[:3], video[3:]])
+    st = seq.statistics()
+    seq.close()
+    w = np.concatenate([f.numpy() for f in flows], 0)
+    mag = np.sqrt(w[..., 0] ** 2 + w[..., 1] ** 2 + w[..., 2] ** 2)
+    np.testing.assert_allclose(st["mean_disp"], mag.mean(axis=(1, 2, 3)), rtol=1e-5)
+    np.testing.assert_allclose(st["max_disp"], mag.max(axis=(1, 2, 3)), rtol=1e-6)
+    div = [float(np.mean(np.gradient(w[t, ..., 0], axis=2) + np.gradient(w[t, ..., 1], axis=1) +
+                         np.gradient(w[t, ..., 2], axis=0))) for t in range(4)]
+    np.testing.assert_allclose(st["mean_div"], div, rtol=1e-4, atol=1e-7)
+    tr = [float(np.sqrt(sum(float(np.mean(w[t, ..., q])) ** 2 for q in range(3)))) for t in range(4)]
+    np.testing.assert_allclose(st["mean_translation"], tr, rtol=1e-5)
