@@ -63,3 +63,32 @@ def test_reference_pipeline_with_b200_executor(emu_backend, golden, reference, m
     e = np.sqrt(((w_b.astype(np.float64) - w_s) ** 2).sum(-1))
     assert e.mean() <= 1e-4 and e.max() <= 5e-3, (e.mean(), e.max())      # tolerance: 0.01 / 0.05
     assert np.linalg.norm(reg_b.astype(np.float64) - reg_s) <= 1e-5 * np.linalg.norm(reg_s)   # tolerance: 1e-4
+
+
+def test_reference_executor_consistency_bar(emu_backend, reference, monkeypatch):
+    """The reference's own cross-executor test (tests/motion_correction/test_parallelization.py:152-198: noise
+    video, quality 'fast', levels 2, 5 iterations, rtol 1e-5 / atol 1e-6) with the B200 executor against
+    sequential3d -- a registered '*3d' executor is swept into that test automatically."""
+    import importlib
+    import flowreg3d_b200.executor as ex
+    importlib.reload(ex)
+    assert ex.B200Executor3D.register()
+    from flowreg3d.motion_correction.compensate_recording_3D import BatchMotionCorrector, RegistrationConfig
+    from flowreg3d.motion_correction.OF_options_3D import OutputFormat
+    T, Z, Y, X, C = 8, 6, 12, 12, 2
+    np.random.seed(42)
+    video = np.random.rand(T, Z, Y, X, C).astype(np.float32)
+    ref = np.mean(video[:2], axis=0)
+    results = {}
+    for name in ("sequential3d", "b2003d"):
+        options = reference.OFOptions(quality_setting="fast", levels=2, iterations=5)
+        options.input_file = video.copy()
+        options.reference_frames = ref.copy()
+        options.output_format = OutputFormat.ARRAY
+        options.save_w = True
+        options.save_meta_info = False
+        comp = BatchMotionCorrector(options, RegistrationConfig(parallelization=name, n_jobs=2))
+        comp.run()
+        assert type(comp.executor).__name__ == ("B200Executor3D" if name == "b2003d" else "SequentialExecutor3D")
+        results[name] = comp.video_writer.get_array()
+    np.testing.assert_allclose(results["b2003d"], results["sequential3d"], rtol=1e-5, atol=1e-6)
