@@ -14,7 +14,7 @@ import numpy as np
 
 HERE = Path(__file__).resolve().parent
 MAX_CHANNELS = 4
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 F32, F64, U8, U16, I16, I32 = range(6)
 OPT_SOR_CTAS_PER_SM = 1
@@ -86,7 +86,7 @@ def load():
         "fr3d_launch_count": (i64, [vp]),
         "fr3d_device_bytes": (i64, [vp]),
         "fr3d_set_option": (ci, [vp, ci, i64]),
-        "fr3d_preprocess": (ci, [vp, vp, ci, ci, vp, vp, ci, vp]),
+        "fr3d_preprocess": (ci, [vp, vp, ci, ci, vp, vp, ci, vp, vp]),
         "fr3d_set_reference": (ci, [vp, vp, vp, vp]),
         "fr3d_get_displacement": (ci, [vp, vp, vp, ci, vp, ci]),
         "fr3d_level_count": (ci, [vp]),
@@ -105,6 +105,7 @@ def load():
         "fr3d_sor_level": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, vp, cd, cd, cd, ci, ci, vp, cd, ci, ci, vp]),
         "fr3d_median5": (ci, [vp, vp, ci, ci, ci, ci, vp]),
         "fr3d_mean_frames": (ci, [vp, vp, ci, i64, vp]),
+        "fr3d_mean_frames_f64": (ci, [vp, vp, ci, i64, vp]),
         "fr3d_flow_stats": (ci, [vp, vp, ci, ci, ci, ci, vp]),
         "fr3d_profile_enable": (ci, [vp, ci]),
         "fr3d_profile_report": (i64, [vp, C.c_char_p, i64]),
@@ -126,7 +127,7 @@ EXPORTED_SYMBOLS = [
     "fr3d_get_displacement", "fr3d_level_count", "fr3d_level_info", "fr3d_level_begin", "fr3d_level_sweeps",
     "fr3d_level_state", "fr3d_level_end", "fr3d_level_end_range", "fr3d_flow_slab", "fr3d_flow_finish",
     "fr3d_compensate", "fr3d_resize3d", "fr3d_warp", "fr3d_motion_tensor",
-    "fr3d_sor_level", "fr3d_median5", "fr3d_mean_frames", "fr3d_flow_stats", "fr3d_profile_enable",
+    "fr3d_sor_level", "fr3d_median5", "fr3d_mean_frames", "fr3d_mean_frames_f64", "fr3d_flow_stats", "fr3d_profile_enable",
     "fr3d_profile_report", "fr3d_fill_resize_table",
 ]
 

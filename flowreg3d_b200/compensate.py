@@ -73,8 +73,6 @@ class SequenceCorrector:
                  device: Optional[torch.device] = None, group=None, streams: int = 1, statistics: bool = False):
         if bool(getattr(options, "cc_initialization", False)):
             raise NotImplementedError("cc_initialization is not implemented on the B200 path")
-        if bool(getattr(options, "update_reference", False)):
-            raise NotImplementedError("update_reference is not implemented on the B200 path")
         self.options = options
         ref = np.asarray(reference_raw)
         if ref.ndim == 3:
@@ -110,10 +108,16 @@ class SequenceCorrector:
         ref_dev = dev.to_device(self.reference_raw, self.device)
         # the reference normalises the fixed volume against ITS OWN range (normalization_ref=None);
         # that is the same (lo, den) as above
+        self.update_reference = bool(getattr(options, "update_reference", False))
+        if self.update_reference and (self.world > 1 or isinstance(self.reg, SplitRegistration)):
+            raise NotImplementedError("update_reference re-averages the fixed volume from all frames of a batch; it "
+                                      "is implemented for one process / one stream only")
         if self.world > 1 and self.reg.plan.temporal:
             raise NotImplementedError("a temporal pre-filter (sigma_t >= 0.125) couples the frames of a batch; it is "
                                       "not implemented for batches sharded over several GPUs")
-        ref_proc = self.reg.preprocess(ref_dev[None], self.lo, self.den, temporal=False)
+        self._weight = weight
+        self._ref_proc64 = (dev.empty((1, Z, Y, X, Cn), np.float64, self.device) if self.update_reference else None)
+        ref_proc = self.reg.preprocess(ref_dev[None], self.lo, self.den, temporal=False, out64=self._ref_proc64)
         self.reg.set_reference(ref_proc[0], weight=weight, ref_raw=ref_dev)
         self.w_init: Optional[torch.Tensor] = None  # (Z,Y,X,3) float32 on device
         self.collect_statistics = bool(statistics)
@@ -147,7 +151,8 @@ class SequenceCorrector:
         raw = self.reg._as_dev(raw_local, None, None)
         t = raw.shape[0]
         G = t if global_size is None else int(global_size)
-        proc = self.reg.preprocess(raw, self.lo, self.den) if t > 0 else None
+        proc64 = (dev.empty(tuple(raw.shape), np.float64, self.device) if (self.update_reference and t > 0) else None)
+        proc = self.reg.preprocess(raw, self.lo, self.den, out64=proc64) if t > 0 else None
         if self.w_init is None:
             # bootstrap (compensate_recording_3D.py:359-388): first min(22, G) frames from zero flow
             n_init = min(22, G)
@@ -173,6 +178,15 @@ class SequenceCorrector:
             for t0 in range(0, t, self.reg.max_batch):
                 outs.append(self.reg.compensate(raw[t0:t0 + self.reg.max_batch], flows[t0:t0 + self.reg.max_batch]))
             reg = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+        if self.update_reference and t > 0:
+            # (compensate_recording_3D.py:395-429) new fixed volume = mean of the last <= 100 pre-processed frames of
+            # the batch warped by their flows (float64 frames in, float32 warps, float64 mean); used from the next
+            # batch on.  Out-of-volume voxels take the current pre-processed reference.
+            n_ref = min(100, t)
+            comp = self.reg.compensate(proc64[t - n_ref:], flows[t - n_ref:], ref_raw=self._ref_proc64[0])
+            new64 = self.reg.mean_frames_f64(comp)
+            self._ref_proc64 = new64[None]
+            self.reg.set_reference(new64.to(torch.float32), weight=self._weight)
         return reg, flows
 
     # -- host-resident recordings: copy / compute / copy pipeline --------------------------

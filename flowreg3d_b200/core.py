@@ -174,11 +174,13 @@ class Registration:
         self.ctx.sync()  # rp / wdev may be temporaries
 
     # -- stages ---------------------------------------------------------------------------
-    def preprocess(self, raw, lo, den, out: Optional[torch.Tensor] = None, temporal: bool = True) -> torch.Tensor:
+    def preprocess(self, raw, lo, den, out: Optional[torch.Tensor] = None, temporal: bool = True,
+                   out64: Optional[torch.Tensor] = None) -> torch.Tensor:
         """(raw - lo)/den then the Gaussian pre-filter; raw (B,Z,Y,X,C) any supported dtype, device
         tensor or ndarray; returns device float32 (B,Z,Y,X,C).  With a temporal sigma (>= 0.125) the B frames
         are one batch of the reference and are filtered across frames first; temporal=False is the
-        reference's 4-D input case (fixed volume)."""
+        reference's 4-D input case (fixed volume).  out64: optional float64 tensor of the same shape that
+        receives the result before its rounding to float32."""
         raw_t = self._as_dev(raw, None, None)
         if raw_t.dim() == 4:
             raw_t = raw_t[None]
@@ -191,7 +193,7 @@ class Registration:
         den = np.broadcast_to(np.asarray(den, float), (self.C,)).copy()
         _check(self.ctx.h, self.ctx.lib.fr3d_preprocess(self.ctx.h, dev.ptr(raw_t), self._code(raw_t), B,
                                                         lo.ctypes.data, den.ctypes.data, 1 if temporal else 0,
-                                                        dev.ptr(out)))
+                                                        dev.ptr(out), dev.ptr(out64)))
         self._keep = [raw_t]
         return out
 
@@ -238,6 +240,16 @@ class Registration:
         out = dev.empty(tuple(frames.shape[1:]), np.float32, self.device)
         fr = frames.contiguous()
         _check(self.ctx.h, self.ctx.lib.fr3d_mean_frames(self.ctx.h, dev.ptr(fr), T, n, dev.ptr(out)))
+        self._keep = [fr]
+        return out
+
+    def mean_frames_f64(self, frames: torch.Tensor) -> torch.Tensor:
+        """numpy.mean(axis=0) of float32 device frames (T, ...) accumulated in float64 -> float64 (...)."""
+        T = frames.shape[0]
+        n = frames[0].numel()
+        out = dev.empty(tuple(frames.shape[1:]), np.float64, self.device)
+        fr = frames.contiguous()
+        _check(self.ctx.h, self.ctx.lib.fr3d_mean_frames_f64(self.ctx.h, dev.ptr(fr), T, n, dev.ptr(out)))
         self._keep = [fr]
         return out
 
@@ -350,7 +362,8 @@ class SplitRegistration:
     def _as_dev(self, a, dtype, shape):
         return self.parts[0]._as_dev(a, dtype, shape)
 
-    def preprocess(self, raw, lo, den, out: Optional[torch.Tensor] = None, temporal: bool = True) -> torch.Tensor:
+    def preprocess(self, raw, lo, den, out: Optional[torch.Tensor] = None, temporal: bool = True,
+                   out64: Optional[torch.Tensor] = None) -> torch.Tensor:
         raw_t = self._as_dev(raw, None, None)
         if raw_t.dim() == 4:
             raw_t = raw_t[None]
@@ -359,9 +372,10 @@ class SplitRegistration:
             out = dev.empty((B,) + self.shape + (self.C,), np.float32, self.device)
         if temporal and self.plan.temporal:
             # the temporal filter couples the frames of the batch: one part takes all of it
-            self._run(1, lambda r, a, b: r.preprocess(raw_t, lo, den, out=out))
+            self._run(1, lambda r, a, b: r.preprocess(raw_t, lo, den, out=out, out64=out64))
         else:
-            self._run(B, lambda r, a, b: r.preprocess(raw_t[a:b], lo, den, out=out[a:b], temporal=temporal))
+            self._run(B, lambda r, a, b: r.preprocess(raw_t[a:b], lo, den, out=out[a:b], temporal=temporal,
+                                                      out64=None if out64 is None else out64[a:b]))
         return out
 
     def get_displacement(self, moving_proc, uvw=None, out_dtype=np.float32,

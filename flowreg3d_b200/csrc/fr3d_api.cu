@@ -631,7 +631,7 @@ int fr3d_set_option(fr3d_ctx* ctx, int option, int64_t value)
 }
 
 int fr3d_preprocess(fr3d_ctx* ctx, const void* raw, int dtype, int B, const double* lo, const double* den,
-                    int temporal_on, float* out)
+                    int temporal_on, float* out, double* out64)
 {
     FR3D_API_BEGIN(ctx)
     FR3D_REQUIRE(_c->has_plan, "fr3d_preprocess needs a context created with a plan");
@@ -688,7 +688,7 @@ int fr3d_preprocess(fr3d_ctx* ctx, const void* raw, int dtype, int B, const doub
         const int64_t nblk = (int64_t)B * Z * ty * tx;
 #define FR3D_PRE_WIN(R_)                                                                                   \
     case R_:                                                                                               \
-        launch_tiles(_c->dev, PreYXWinK<R_>{a, out, B, Z, Y, X, C, g, ty, tx}, nblk, 256,                   \
+        launch_tiles(_c->dev, PreYXWinK<R_>{a, out, out64, B, Z, Y, X, C, g, ty, tx}, nblk, 256,            \
                      PreYXWinK<R_>::smem_bytes(C));                                                        \
         break;
         switch (RY) {
@@ -704,6 +704,7 @@ int fr3d_preprocess(fr3d_ctx* ctx, const void* raw, int dtype, int B, const doub
         PreYXTileK k;
         k.in = a;
         k.out = out;
+        k.out64 = out64;
         k.B = B;
         k.Z = Z;
         k.Y = Y;
@@ -715,13 +716,12 @@ int fr3d_preprocess(fr3d_ctx* ctx, const void* raw, int dtype, int B, const doub
         k.tiles_y = (Y + PreYXTileK::TY - 1) / PreYXTileK::TY;
         k.tiles_x = (X + PreYXTileK::TX - 1) / PreYXTileK::TX;
         const int IW = PreYXTileK::TX + 2 * RX, IH = PreYXTileK::TY + 2 * RY;
-        const size_t smem = (size_t)(IH * IW + PreYXTileK::TY * IW) * sizeof(double) +
-                            (size_t)PreYXTileK::TY * PreYXTileK::TX * C * sizeof(float);
+        const size_t smem = (size_t)(IH * IW + PreYXTileK::TY * IW + PreYXTileK::TY * PreYXTileK::TX * C) * sizeof(double);
         launch_tiles(_c->dev, k, (int64_t)B * Z * k.tiles_y * k.tiles_x, 256, smem);
     } else {
         double* b = _c->g2.ensure(_c->dev, n);
         launch(_c->dev, PreYK{a, b, C, Z, Y, X, g}, (int64_t)n);
-        launch(_c->dev, PreXK{b, out, B, Z, Y, X, C, g}, (int64_t)n);
+        launch(_c->dev, PreXK{b, out, out64, B, Z, Y, X, C, g}, (int64_t)n);
     }
     FR3D_API_END()
 }
@@ -1233,6 +1233,14 @@ int fr3d_mean_frames(fr3d_ctx* ctx, const float* frames, int T, int64_t n, float
     FR3D_API_BEGIN(ctx)
     FR3D_REQUIRE(frames && out && T >= 1 && n >= 1, "bad argument");
     launch(_c->dev, MeanFramesK{frames, out, T, n}, n);
+    FR3D_API_END()
+}
+
+int fr3d_mean_frames_f64(fr3d_ctx* ctx, const float* frames, int T, int64_t n, double* out)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(frames && out && T >= 1 && n >= 1, "bad argument");
+    launch(_c->dev, MeanFramesF64K{frames, out, T, n}, n);
     FR3D_API_END()
 }
 

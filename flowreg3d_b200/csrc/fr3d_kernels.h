@@ -264,6 +264,7 @@ struct PreYK {
 struct PreXK {
     const double* in;
     float* out;
+    double* out64; // optional: the unrounded float64 result (what the reference keeps), same layout
     int B, Z, Y, X, C;
     PreGauss g;
     FR3D_HD void operator()(int64_t item) const
@@ -281,6 +282,8 @@ struct PreXK {
         for (int j = r; j >= 1; --j)
             t += (line[reflect_idx(x - j, X)] + line[reflect_idx(x + j, X)]) * w[j];
         out[item] = (float)t;
+        if (out64)
+            out64[item] = t;
     }
 };
 
@@ -294,6 +297,7 @@ struct PreYXTileK {
     static constexpr int TY = 16, TX = 64;
     const double* in; // (B, C, Z, Y, X) planar
     float* out;       // (B, Z, Y, X, C)
+    double* out64;    // optional: unrounded float64 result, same layout
     int B, Z, Y, X, C;
     int RY, RX;       // halo = max radius over channels
     PreGauss g;
@@ -310,13 +314,16 @@ struct PreYXTileK {
         const int IW = TX + 2 * RX, IH = TY + 2 * RY;
         double* tin = sm;                       // [IH][IW]
         double* mid = tin + IH * IW;            // [TY][IW]
-        float* tout = (float*)(mid + TY * IW);  // [TY][TX][C]
+        double* tout = mid + TY * IW;           // [TY][TX][C]
         if (ph == 3 * FR3D_MAX_CHANNELS) {
             const int ny = Y - y0 < TY ? Y - y0 : TY, nx = X - x0 < TX ? X - x0 : TX;
             const int rowlen = nx * C;
             for (int e = tid; e < ny * rowlen; e += nthreads) {
                 const int yy = e / rowlen, r = e - yy * rowlen;
-                out[((((int64_t)b * Z + z) * Y + (y0 + yy)) * X + x0) * C + r] = tout[yy * TX * C + r];
+                const int64_t o = ((((int64_t)b * Z + z) * Y + (y0 + yy)) * X + x0) * C + r;
+                out[o] = (float)tout[yy * TX * C + r];
+                if (out64)
+                    out64[o] = tout[yy * TX * C + r];
             }
             return;
         }
@@ -349,7 +356,7 @@ struct PreYXTileK {
                 double t = row[0] * w[0];
                 for (int j = r; j >= 1; --j)
                     t += (row[-j] + row[j]) * w[j];
-                tout[(yy * TX + xx) * C + c] = (float)t;
+                tout[(yy * TX + xx) * C + c] = t;
             }
         }
     }
@@ -365,10 +372,11 @@ struct PreYXWinK {
     static constexpr int IW = TX + 2 * R, IH = TY + 2 * R, MW = IW + 1; // MW: padded row of the Y-pass buffer
     const double* in; // (B, C, Z, Y, X) planar
     float* out;       // (B, Z, Y, X, C)
+    double* out64;    // optional: unrounded float64 result, same layout
     int B, Z, Y, X, C;
     PreGauss g;
     int tiles_y, tiles_x;
-    static size_t smem_bytes(int C_) { return (size_t)(IH * IW + TY * MW) * sizeof(double) + (size_t)TY * TX * C_ * sizeof(float); }
+    static size_t smem_bytes(int C_) { return (size_t)(IH * IW + TY * MW + TY * TX * C_) * sizeof(double); }
     FR3D_HD void phase(int ph, int64_t blk, int tid, int nthreads, double* sm) const
     {
         const int tx = (int)(blk % tiles_x);
@@ -380,15 +388,18 @@ struct PreYXWinK {
         const int y0 = ty * TY, x0 = tx * TX;
         double* tin = sm;                       // [IH][IW]
         double* mid = tin + IH * IW;            // [TY][MW]
-        float* tout = (float*)(mid + TY * MW);  // [TY][TX][C]
+        double* tout = mid + TY * MW;           // [TY][TX][C]
         if (ph == 3 * FR3D_MAX_CHANNELS) {
             const int ny = Y - y0 < TY ? Y - y0 : TY, nx = X - x0 < TX ? X - x0 : TX;
             const int rowlen = nx * C;
             const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
             for (int yy = warp; yy < ny; yy += nwarps) {
-                float* o = out + ((((int64_t)b * Z + z) * Y + (y0 + yy)) * X + x0) * C;
-                for (int r = lane; r < rowlen; r += 32)
-                    o[r] = tout[yy * TX * C + r];
+                const int64_t ob = ((((int64_t)b * Z + z) * Y + (y0 + yy)) * X + x0) * C;
+                for (int r = lane; r < rowlen; r += 32) {
+                    out[ob + r] = (float)tout[yy * TX * C + r];
+                    if (out64)
+                        out64[ob + r] = tout[yy * TX * C + r];
+                }
             }
             return;
         }
@@ -440,7 +451,7 @@ struct PreYXWinK {
 #pragma unroll
                     for (int j = R; j >= 1; --j)
                         t += (win[o + R - j] + win[o + R + j]) * w[j];
-                    tout[(yy * TX + run * RUN + o) * C + c] = (float)t;
+                    tout[(yy * TX + run * RUN + o) * C + c] = t;
                 }
             }
         }
@@ -1547,6 +1558,22 @@ struct FlowStatsFinishK {
         out[b * 4 + 1] = a[1];
         out[b * 4 + 2] = a[2] * inv_n;
         out[b * 4 + 3] = sqrt(mu * mu + mv * mv + mw * mw);
+    }
+};
+
+// numpy.mean(x, axis=0) of T float32 arrays held in a float64 array (compensate_recording_3D.py:425:
+// sequential float64 accumulation over the frame axis, one division by the count)
+struct MeanFramesF64K {
+    const float* src; // (T, n)
+    double* dst;      // (n)
+    int T;
+    int64_t n;
+    FR3D_HD void operator()(int64_t i) const
+    {
+        double acc = (double)src[i];
+        for (int t = 1; t < T; ++t)
+            acc += (double)src[(int64_t)t * n + i];
+        dst[i] = acc / (double)T;
     }
 };
 

@@ -34,7 +34,7 @@ extern "C" {
 
 #define FR3D_MAX_CHANNELS 4
 #define FR3D_MAX_LEVELS 64
-#define FR3D_ABI_VERSION 3
+#define FR3D_ABI_VERSION 4
 
 typedef enum {
     FR3D_OK = 0,
@@ -138,9 +138,11 @@ int64_t fr3d_profile_report(fr3d_ctx* ctx, char* buf, int64_t cap);
  * float64 math, one rounding to float32 (the reference's first resize rounds it the same way).
  * raw: (B,Z,Y,X,C) of `dtype`; lo, den: host, C doubles; out: (B,Z,Y,X,C) float32.  With a temporal radius
  * in the plan and temporal != 0 the B frames of the call are one batch of the reference (filtered across
- * frames first); temporal = 0 is the reference's 4-D (Z,Y,X,C) case (fixed volume: spatial filter only). */
+ * frames first); temporal = 0 is the reference's 4-D (Z,Y,X,C) case (fixed volume: spatial filter only).
+ * out64 (optional, may be NULL): the same result before its rounding to float32 -- what the reference keeps in
+ * float64 and warps when it re-averages the reference volume (update_reference). */
 int fr3d_preprocess(fr3d_ctx* ctx, const void* raw, int dtype, int B, const double* lo,
-                    const double* den, int temporal, float* out);
+                    const double* den, int temporal, float* out, double* out64);
 
 /* Cache the fixed volume's pyramid and the weight pyramid (frame-invariant).
  * ref_proc: (Z,Y,X,C) float32 pre-processed reference.  weight: (Z,Y,X,C) float32 or NULL, in which
@@ -229,6 +231,10 @@ int fr3d_median5(fr3d_ctx* ctx, const double* src, int nvol, int p, int m, int n
 /* numpy.mean(frames, axis=0) of T float32 arrays of n elements: the w_init bootstrap / chaining of
  * BatchMotionCorrector (compensate_recording_3D.py:388, 481-485), float32 accumulation in frame order. */
 int fr3d_mean_frames(fr3d_ctx* ctx, const float* frames, int T, int64_t n, float* out);
+
+/* numpy.mean(axis=0) of T float32 arrays accumulated in float64 (the reference re-averaging its fixed volume from
+ * compensated frames, compensate_recording_3D.py:395-429); out: n float64. */
+int fr3d_mean_frames_f64(fr3d_ctx* ctx, const float* frames, int T, int64_t n, double* out);
 
 /* Per-frame statistics BatchMotionCorrector keeps (compensate_recording_3D.py:488-508), computed where the flow
  * lives: flow (B,Z,Y,X,3) float32 -> out (B,4) float64 (device) = mean |w|, max |w|, mean divergence

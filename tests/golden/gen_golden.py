@@ -201,6 +201,20 @@ def gen_preprocess_t():
                                                sigma, mode="reflect", truncate=4.0))
 
 
+def gen_sequence_update_ref():
+    """compensate_arr_3D with update_reference=True (the fixed volume re-averaged from compensated frames after
+    every batch, compensate_recording_3D.py:395-429)."""
+    from flowreg3d.motion_correction.compensate_arr_3D import compensate_arr_3D
+    from flowreg3d.motion_correction.OF_options_3D import OFOptions
+    g = np.load(OUT / "sequence.npz")
+    video, ref = g["video"][:6, :12, :24, :28], g["ref"][:12, :24, :28]
+    opts = OFOptions(alpha=(0.25, 0.25, 0.25), levels=100, min_level=2, iterations=8, update_lag=4, buffer_size=3,
+                     weight=[0.5, 0.5], update_reference=True)
+    reg, w = compensate_arr_3D(video, ref, opts)
+    save("sequence_update_ref", registered=reg.astype(np.float32), w=w.astype(np.float32),
+         params=np.array([2, 8, 4, 3]))
+
+
 def gen_sequence():
     """compensate_arr_3D through the reference's own BatchMotionCorrector (sequential executor)."""
     from flowreg3d.motion_correction.OF_options_3D import OFOptions
@@ -267,6 +281,6 @@ def gen_config1():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["tables", "resize", "warp", "motion_tensor", "solver", "flow_small",
-                             "preprocess", "preprocess_t", "sequence", "config1"]
+                             "preprocess", "preprocess_t", "sequence", "sequence_update_ref", "config1"]
     for w in which:
         globals()[f"gen_{w}"]()

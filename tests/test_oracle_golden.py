@@ -131,3 +131,26 @@ def test_config1_default_options(golden):
     assert mean <= 1e-4 and mx <= 5e-3, (mean, mx)
     reg = O.imregister_wrapper(g["low_moving"], f32[..., 0], f32[..., 1], f32[..., 2], V64[..., 0], "cubic")
     assert rel_l2(reg[::2, ::2, ::2], g["low_reg_s2"]) <= 1e-5
+
+
+def test_preprocess_temporal(golden):
+    g = golden("preprocess_t")
+    assert np.array_equal(O.preprocess(g["batch"], g["sigma"], g["ref"].astype(np.float64)), g["batch_proc"])
+
+
+def test_sequence_update_reference(golden):
+    g, gs = golden("sequence_update_ref"), golden("sequence")
+    ml, it, lag, buf = (int(v) for v in g["params"])
+    video, ref = gs["video"][:6, :12, :24, :28], gs["ref"][:12, :24, :28]
+    reg, w = O.compensate_arr(video, ref, min_level=ml, iterations=it, update_lag=lag, buffer_size=buf,
+                              weight=[0.5, 0.5], update_reference=True)
+    mean, mx = epe_stats(w, g["w"])
+    assert mean <= 1e-4 and mx <= 5e-3, (mean, mx)
+    assert rel_l2(reg, g["registered"]) <= 1e-5
+
+
+def test_flow_nonlinear_smoothness(golden):
+    g = golden("flow_small")
+    kw = dict(alpha=(0.5,) * 3, update_lag=10, iterations=15, min_level=1, levels=100, eta=0.8, a_smooth=0.5, a_data=0.45)
+    mean, mx = epe_stats(O.get_displacement(g["fixed"], g["moving"], **kw), g["flow_ml1s"])
+    assert mean <= 1e-4 and mx <= 5e-3, (mean, mx)

@@ -237,3 +237,24 @@ def test_flow_statistics(backend, golden):
     np.testing.assert_allclose(st["mean_div"], div, rtol=1e-4, atol=1e-7)
     tr = [float(np.sqrt(sum(float(np.mean(w[t, ..., q])) ** 2 for q in range(3)))) for t in range(4)]
     np.testing.assert_allclose(st["mean_translation"], tr, rtol=1e-5)
+
+
+def test_update_reference(backend, golden):
+    """update_reference=True: the fixed volume is re-averaged from the compensated pre-processed frames after every
+    batch (compensate_recording_3D.py:395-429); golden from the live reference, and the oracle restatement."""
+    import flowreg3d_b200 as F
+    g, gs = golden("sequence_update_ref"), golden("sequence")
+    video, ref = gs["video"][:6, :12, :24, :28], gs["ref"][:12, :24, :28]
+    opts = F.OFOptions(alpha=(0.25, 0.25, 0.25), levels=100, min_level=2, iterations=8, update_lag=4, buffer_size=3,
+                       weight=[0.5, 0.5], update_reference=True, output_typename=None)
+    reg, w = F.compensate_arr_3D(video, ref, opts)
+    mean, mx = epe_stats(w, g["w"])
+    assert mean <= 1e-4 and mx <= 5e-3, (mean, mx)              # tolerance: 0.01 / 0.05
+    assert rel_l2(reg, g["registered"]) <= 1e-5                  # tolerance: 1e-4
+    oreg, ow = O.compensate_arr(video, ref, min_level=2, iterations=8, update_lag=4, buffer_size=3, weight=[0.5, 0.5],
+                                update_reference=True)
+    mean, mx = epe_stats(w, ow)
+    assert mean <= 1e-6 and mx <= 1e-4, (mean, mx)
+    # and it matters: the second batch differs from a run with a fixed reference
+    _, w_fixed = F.compensate_arr_3D(video, ref, F.OFOptions(**{**opts.model_dump(), "update_reference": False}))
+    assert np.abs(w[3:] - w_fixed[3:]).max() > 1e-3
