@@ -313,7 +313,13 @@ static void check_dtype(int dt)
 }
 
 // Frames per warp work item: enough items to balance the busiest wave over the grid.
-static int sor_frame_group(int B) { return B >= 2 ? 2 : 1; }
+static int sor_frame_group(int B)
+{
+    static const int fg_env = getenv("FR3D_SOR_FG") ? atoi(getenv("FR3D_SOR_FG")) : 0; // tuning aid
+    if (fg_env > 0)
+        return fg_env < B ? fg_env : B;
+    return B >= 2 ? 2 : 1;
+}
 
 // Level solve in solver storage: assembles J (when f1/f2 are given; otherwise Jpre is used as is), the
 // Laplacian term L and zero increments, then runs the wavefront solver.  Result in c->d.
