@@ -296,7 +296,7 @@ static void spline_prefilter(fr3d_ctx* c, const void* src, int dt, int64_t sb, i
                              int64_t sy, int64_t sx, int B, int C, int Z, int Y, int X)
 {
     const size_t n = (size_t)B * C * (Z + 3) * (Y + 3) * (X + 3);
-    double* coef = c->coef.ensure(c->dev, n);
+    double* coef = c->coef.ensure(c->dev, n + 2); // + 2: WarpGatherPairK's aligned 16-byte loads may touch them
     // (measured slower than this in-place pass, 2.1 ms per 16-frame step: shared-memory staged 3.6 ms, per-thread
     // local line 2.7 ms)
     SplineZK kz{src, dt, sb, sc, sz, sy, sx, coef, B, C, Z, Y, X};
@@ -305,6 +305,18 @@ static void spline_prefilter(fr3d_ctx* c, const void* src, int dt, int64_t sb, i
                      [&] { launch(c->dev, SplineYK{coef, Z, Y, X}, (int64_t)B * C * (Z + 3) * X); });
     spline_tile_pass(c, coef, X, (int64_t)B * C * (Z + 3) * (Y + 3), (int64_t)1 << 62, 0, X + 3, 1, 0, 0,
                      [&] { launch(c->dev, SplineXK{coef, X}, (int64_t)B * C * (Z + 3) * (Y + 3)); });
+}
+
+// Order-3 gathers run two x-adjacent outputs per thread (FR3D_WARP_PAIR=0 selects the one-output kernel: A/B aid).
+static void launch_gather(fr3d_ctx* c, const WarpGatherK& g)
+{
+    static const int pair = getenv("FR3D_WARP_PAIR") ? atoi(getenv("FR3D_WARP_PAIR")) : 1;
+    if (g.order == 3 && pair) {
+        WarpGatherPairK k{g, (g.X + 1) / 2};
+        launch(c->dev, k, (int64_t)g.B * g.Z * g.Y * k.XP);
+    } else {
+        launch(c->dev, g, (int64_t)g.B * g.Z * g.Y * g.X);
+    }
 }
 
 static void check_dtype(int dt)
@@ -857,7 +869,7 @@ static void level_begin(fr3d_ctx* c, int li, const float* moving, const float* u
         g.Z = p;
         g.Y = m;
         g.X = n;
-        launch(dev, g, (int64_t)B * N);
+        launch_gather(c, g);
         warped = tmp;
         f2f32 = 1; // numpy keeps the float32 warp output in float32 through its derivatives
     }
@@ -1089,7 +1101,7 @@ static void warp_common(fr3d_ctx* c, const void* vol, int vdt, const double* d64
     g.Z = Z;
     g.Y = Y;
     g.X = X;
-    launch(c->dev, g, (int64_t)B * NF);
+    launch_gather(c, g);
 }
 
 int fr3d_compensate(fr3d_ctx* ctx, const void* vol, int vol_dtype, const float* flow, const void* ref,
