@@ -97,6 +97,29 @@ def test_warp_long_lines_segmented_prefilter(backend):
     assert d.max() <= 1 and (d > 0).mean() <= 1e-4, (d.max(), (d > 0).mean())
 
 
+@pytest.mark.parametrize("shape,C", [((6, 9, 13), 1), ((5, 10, 16), 2), ((7, 8, 11), 3)])
+def test_warp_rough_flow(backend, shape, C):
+    """Rough (per-voxel random) displacements: neighbouring outputs gather from unrelated tap boxes, odd X, large
+    displacements (out-of-volume replacement, clipped taps), 1-3 channels and an integer source; every case must
+    equal scipy (through the oracle)."""
+    import flowreg3d_b200 as F
+    rng = np.random.default_rng(shape[2] + C)
+    f2 = rng.random(shape + (C,))
+    f1 = rng.random(shape + (C,))
+    for scale in (0.4, 1.5, 6.0):
+        u, v, w = (scale * rng.standard_normal(shape) for _ in range(3))
+        out = F.imregister_wrapper(f2, u, v, w, f1, "cubic")
+        ref = O.imregister_wrapper(f2, u, v, w, f1, "cubic")
+        assert out.shape == ref.shape
+        d = ulp_diff(out, ref)
+        assert d.max() <= 1 and (d > 0).mean() <= 2e-3, (scale, d.max(), (d > 0).mean())
+    raw = rng.integers(0, 60000, shape + (C,)).astype(np.uint16)
+    rref = rng.integers(0, 60000, shape + (C,)).astype(np.uint16)
+    u, v, w = (1.5 * rng.standard_normal(shape).astype(np.float32) for _ in range(3))
+    assert np.array_equal(F.imregister_wrapper(raw, u, v, w, rref, "cubic"),
+                          O.imregister_wrapper(raw, u, v, w, rref, "cubic"))
+
+
 def test_motion_tensor(backend, golden):
     from flowreg3d_b200 import core
     g = golden("motion_tensor")
