@@ -296,7 +296,7 @@ static void spline_prefilter(fr3d_ctx* c, const void* src, int dt, int64_t sb, i
                              int64_t sy, int64_t sx, int B, int C, int Z, int Y, int X)
 {
     const size_t n = (size_t)B * C * (Z + 3) * (Y + 3) * (X + 3);
-    double* coef = c->coef.ensure(c->dev, n + 2); // + 2: WarpGatherPairK's aligned 16-byte loads may touch them
+    double* coef = c->coef.ensure(c->dev, n);
     // (measured slower than this in-place pass, 2.1 ms per 16-frame step: shared-memory staged 3.6 ms, per-thread
     // local line 2.7 ms)
     SplineZK kz{src, dt, sb, sc, sz, sy, sx, coef, B, C, Z, Y, X};
@@ -307,16 +307,24 @@ static void spline_prefilter(fr3d_ctx* c, const void* src, int dt, int64_t sb, i
                      [&] { launch(c->dev, SplineXK{coef, X}, (int64_t)B * C * (Z + 3) * (Y + 3)); });
 }
 
-// Order-3 gathers run two x-adjacent outputs per thread (FR3D_WARP_PAIR=0 selects the one-output kernel: A/B aid).
-static void launch_gather(fr3d_ctx* c, const WarpGatherK& g)
+// Gather launch: compact output tiles per block (FR3D_WARP_TILE="tx,ty,tz" overrides; "0" = x-runs of 256: A/B aid).
+static void launch_gather(fr3d_ctx* c, WarpGatherK g)
 {
-    static const int pair = getenv("FR3D_WARP_PAIR") ? atoi(getenv("FR3D_WARP_PAIR")) : 1;
-    if (g.order == 3 && pair) {
-        WarpGatherPairK k{g, (g.X + 1) / 2};
-        launch(c->dev, k, (int64_t)g.B * g.Z * g.Y * k.XP);
-    } else {
-        launch(c->dev, g, (int64_t)g.B * g.Z * g.Y * g.X);
+    static int tx = 32, ty = 4, tz = 2, parsed = 0;
+    if (!parsed) {
+        parsed = 1;
+        if (const char* e = getenv("FR3D_WARP_TILE")) {
+            int a = 0, b = 1, d = 1;
+            const int n = sscanf(e, "%d,%d,%d", &a, &b, &d);
+            if (n >= 1 && (a == 0 || (n == 3 && a * b * d == 256))) {
+                tx = a;
+                ty = b;
+                tz = d;
+            }
+        }
     }
+    g.set_tile(tx, ty, tz);
+    launch(c->dev, g, g.items());
 }
 
 static void check_dtype(int dt)

@@ -825,15 +825,52 @@ struct WarpGatherK {
     float* out;
     int64_t ob, oc, oz, oy, ox;
     int B, C, Z, Y, X;
+    // Output tiling: a 256-thread block covers TX x TY x TZ outputs (TX*TY*TZ == 256; TX == 0: one x-run of 256).
+    // The 4x4x4 tap boxes of a compact tile overlap in y and z as well as in x, so the block pulls
+    // (TY+3)(TZ+3)(TX+3) coefficients through L2 instead of 16 (256+3).
+    int TX, TY, TZ, nbx, nby, nbz;
+
+    void set_tile(int tx, int ty, int tz)
+    {
+        TX = tx;
+        TY = ty;
+        TZ = tz;
+        if (tx > 0) {
+            nbx = (X + tx - 1) / tx;
+            nby = (Y + ty - 1) / ty;
+            nbz = (Z + tz - 1) / tz;
+        } else {
+            nbx = nby = nbz = 0;
+        }
+    }
+    int64_t items() const
+    {
+        return TX > 0 ? (int64_t)B * nbz * nby * nbx * 256 : (int64_t)B * Z * Y * X;
+    }
 
     FR3D_HD void operator()(int64_t item) const
     {
-        const int x = (int)(item % X);
-        int64_t q = item / X;
-        const int y = (int)(q % Y);
-        q /= Y;
-        const int z = (int)(q % Z);
-        const int b = (int)(q / Z);
+        int x, y, z, b;
+        if (TX > 0) {
+            const int t = (int)(item & 255);
+            int64_t blk = item >> 8;
+            const int tx = t % TX, tyz = t / TX;
+            x = (int)(blk % nbx) * TX + tx;
+            blk /= nbx;
+            y = (int)(blk % nby) * TY + tyz % TY;
+            blk /= nby;
+            z = (int)(blk % nbz) * TZ + tyz / TY;
+            b = (int)(blk / nbz);
+            if (x >= X || y >= Y || z >= Z)
+                return;
+        } else {
+            x = (int)(item % X);
+            int64_t q = item / X;
+            y = (int)(q % Y);
+            q /= Y;
+            z = (int)(q % Z);
+            b = (int)(q / Z);
+        }
         double dx, dy, dz;
         if (disp64) {
             const int64_t nvox = (int64_t)Z * Y * X;
@@ -911,159 +948,6 @@ struct WarpGatherK {
                         }
                 out[obase + c * oc] = (float)integer_round(t, sdt);
             }
-        }
-    }
-};
-
-// Order-3 gather, two x-adjacent outputs per thread (same reference lines and the same arithmetic as
-// WarpGatherK, bit for bit).  The gather is bound by L1 wavefronts (64 float64 taps per output and
-// channel), so the pair fetches each coefficient row ONCE with three aligned 16-byte loads covering
-// slots ix..ix+4: consecutive lanes then read consecutive 16-byte words (4 full lines per warp
-// instruction instead of 2-3 lines for each of 8 scalar loads).  When the two tap boxes are not
-// x-adjacent neighbours of the same rows (flow discontinuity, clipping, out-of-volume) the second
-// output falls back to its own four scalar loads per row -- only those lanes issue them, the
-// arithmetic below is common to both cases.  `coef` needs two doubles of slack at its end.
-struct Dbl2 {
-    double x, y;
-};
-FR3D_HD Dbl2 ld_dbl2(const double* p)
-{
-#ifdef __CUDA_ARCH__
-    const double2 v = *reinterpret_cast<const double2*>(p);
-    return Dbl2{v.x, v.y};
-#else
-    return Dbl2{p[0], p[1]};
-#endif
-}
-
-struct WarpGatherPairK {
-    WarpGatherK g; // order == 3
-    int XP;        // pairs per row = ceil(X / 2)
-
-    struct Tap {
-        bool act;
-        int ix, iy, iz;
-        double wx[4], wy[4], wz[4];
-        int64_t obase;
-    };
-
-    FR3D_HD void locate(int b, int z, int y, int x, Tap& o) const
-    {
-        o.act = false;
-        if (x >= g.X)
-            return;
-        double dx, dy, dz;
-        if (g.disp64) {
-            const int64_t nvox = (int64_t)g.Z * g.Y * g.X;
-            const int64_t v = ((int64_t)z * g.Y + y) * g.X + x;
-            const double* d = g.disp64 + (int64_t)b * 3 * nvox;
-            dx = d[v] / g.hx;
-            dy = d[nvox + v] / g.hy;
-            dz = d[2 * nvox + v] / g.hz;
-        } else {
-            const float* d = g.disp32 + ((((int64_t)b * g.Z + z) * g.Y + y) * g.X + x) * 3;
-            dx = (double)d[0];
-            dy = (double)d[1];
-            dz = (double)d[2];
-        }
-        float mx = (float)((double)x + dx);
-        float my = (float)((double)y + dy);
-        float mz = (float)((double)z + dz);
-        const bool oob = (mx < 0.0f) | (mx >= (float)g.X) | (my < 0.0f) | (my >= (float)g.Y) | (mz < 0.0f) |
-                         (mz >= (float)g.Z);
-        o.obase = b * g.ob + z * g.oz + y * g.oy + x * g.ox;
-        if (oob) {
-            for (int c = 0; c < g.C; ++c)
-                g.out[o.obase + c * g.oc] =
-                    (float)load_as_double(g.ref, g.rdt, c * g.rc + z * g.rz + y * g.ry + x * g.rx);
-            return;
-        }
-        mx = fminf(fmaxf(mx, 0.0f), (float)(g.X - 1));
-        my = fminf(fmaxf(my, 0.0f), (float)(g.Y - 1));
-        mz = fminf(fmaxf(mz, 0.0f), (float)(g.Z - 1));
-        const double cx = (double)mx, cy = (double)my, cz = (double)mz;
-        const double fx = floor(cx), fy = floor(cy), fz = floor(cz);
-        o.ix = (int)fx;
-        o.iy = (int)fy;
-        o.iz = (int)fz;
-        bspline3_weights(cx - fx, o.wx);
-        bspline3_weights(cy - fy, o.wy);
-        bspline3_weights(cz - fz, o.wz);
-        o.act = true;
-    }
-
-    FR3D_HD void operator()(int64_t item) const
-    {
-        const int xp = (int)(item % XP);
-        int64_t q = item / XP;
-        const int y = (int)(q % g.Y);
-        q /= g.Y;
-        const int z = (int)(q % g.Z);
-        const int b = (int)(q / g.Z);
-        Tap o0, o1;
-        locate(b, z, y, 2 * xp, o0);
-        locate(b, z, y, 2 * xp + 1, o1);
-        if (!o0.act && !o1.act)
-            return;
-        const bool share = o0.act && o1.act && o1.iz == o0.iz && o1.iy == o0.iy && o1.ix == o0.ix + 1;
-        const int64_t rowlen = g.X + 3, pl = (int64_t)(g.Y + 3) * rowlen;
-        for (int c = 0; c < g.C; ++c) {
-            const int64_t chan = ((int64_t)b * g.C + c) * (g.Z + 3) * pl;
-            const int64_t base0 = chan + (int64_t)o0.iz * pl + (int64_t)o0.iy * rowlen + o0.ix;
-            const int64_t base1 = chan + (int64_t)o1.iz * pl + (int64_t)o1.iy * rowlen + o1.ix;
-            double t0 = 0.0, t1 = 0.0;
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-#pragma unroll
-                for (int bb = 0; bb < 4; ++bb) {
-                    const int64_t ro = a * pl + bb * rowlen;
-                    double v0[4], v1[4];
-                    if (o0.act) {
-                        const int64_t off = base0 + ro;
-                        const bool par = (off & 1) != 0;
-                        const double* e = g.coef + (off & ~(int64_t)1);
-                        const Dbl2 q0 = ld_dbl2(e), q1 = ld_dbl2(e + 2), q2 = ld_dbl2(e + 4);
-                        v0[0] = par ? q0.y : q0.x;
-                        v0[1] = par ? q1.x : q0.y;
-                        v0[2] = par ? q1.y : q1.x;
-                        v0[3] = par ? q2.x : q1.y;
-                        v1[0] = v0[1];
-                        v1[1] = v0[2];
-                        v1[2] = v0[3];
-                        v1[3] = par ? q2.y : q2.x;
-                    }
-                    if (o1.act && !share) {
-                        const double* row = g.coef + base1 + ro;
-#pragma unroll
-                        for (int cc = 0; cc < 4; ++cc)
-                            v1[cc] = row[cc];
-                    }
-                    if (o0.act) {
-#pragma unroll
-                        for (int cc = 0; cc < 4; ++cc) {
-                            double v = v0[cc];
-                            v *= o0.wz[a];
-                            v *= o0.wy[bb];
-                            v *= o0.wx[cc];
-                            t0 += v;
-                        }
-                    }
-                    if (o1.act) {
-#pragma unroll
-                        for (int cc = 0; cc < 4; ++cc) {
-                            double v = v1[cc];
-                            v *= o1.wz[a];
-                            v *= o1.wy[bb];
-                            v *= o1.wx[cc];
-                            t1 += v;
-                        }
-                    }
-                }
-            }
-            if (o0.act)
-                g.out[o0.obase + c * g.oc] = (float)integer_round(t0, g.sdt);
-            if (o1.act)
-                g.out[o1.obase + c * g.oc] = (float)integer_round(t1, g.sdt);
         }
     }
 };
