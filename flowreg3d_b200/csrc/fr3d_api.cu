@@ -307,16 +307,19 @@ static void spline_prefilter(fr3d_ctx* c, const void* src, int dt, int64_t sb, i
                      [&] { launch(c->dev, SplineXK{coef, X}, (int64_t)B * C * (Z + 3) * (Y + 3)); });
 }
 
-// Gather launch: compact output tiles per block (FR3D_WARP_TILE="tx,ty,tz" overrides; "0" = x-runs of 256: A/B aid).
+// Gather launch.  The kernel is latency-bound (ncu: 53 % long-scoreboard stalls at 16 warps per SM), so what pays is
+// resident warps and independent work per thread, not fewer bytes (profiles/r01_sor_variants.txt, gather
+// experiments): cubic warps of 1 or 2 channels run the channel-interleaved kernel with a rolled z loop at 64
+// registers (4 CTAs per SM): 7.6 ms against 10.5 ms for 16 frames of 32x512x512x2; other channel counts run the
+// generic kernel capped to 64 registers (8.7 ms).  Blocks cover 32x8x1 outputs (FR3D_WARP_TILE="tx,ty,tz": A/B aid).
 static void launch_gather(fr3d_ctx* c, WarpGatherK g)
 {
-    static int tx = 32, ty = 4, tz = 2, parsed = 0;
+    static int tx = 32, ty = 8, tz = 1, parsed = 0;
     if (!parsed) {
         parsed = 1;
         if (const char* e = getenv("FR3D_WARP_TILE")) {
             int a = 0, b = 1, d = 1;
-            const int n = sscanf(e, "%d,%d,%d", &a, &b, &d);
-            if (n >= 1 && (a == 0 || (n == 3 && a * b * d == 256))) {
+            if (sscanf(e, "%d,%d,%d", &a, &b, &d) == 3 && a > 0 && a * b * d == 256) {
                 tx = a;
                 ty = b;
                 tz = d;
@@ -324,7 +327,15 @@ static void launch_gather(fr3d_ctx* c, WarpGatherK g)
         }
     }
     g.set_tile(tx, ty, tz);
-    launch(c->dev, g, g.items());
+    const int64_t n = g.items();
+    if (g.order == 3 && g.C == 2)
+        launch_occ<4>(c->dev, WarpGatherLeanK<2, 0>{g}, n);
+    else if (g.order == 3 && g.C == 1)
+        launch_occ<4>(c->dev, WarpGatherLeanK<1, 0>{g}, n);
+    else if (g.order == 3)
+        launch_occ<4>(c->dev, g, n);
+    else
+        launch(c->dev, g, n);
 }
 
 static void check_dtype(int dt)

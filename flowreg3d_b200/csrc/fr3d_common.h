@@ -264,6 +264,37 @@ __global__ void __launch_bounds__(256, 2) fr3d_kernel_occ2(const K k, const int6
 }
 #endif
 
+#ifndef FR3D_EMU
+// Variant with a chosen number of resident CTAs per SM (register cap 65536 / (256 MB) per thread).
+template <class K, int MB>
+__global__ void __launch_bounds__(256, MB) fr3d_kernel_occ(const K k, const int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        k(i);
+}
+#endif
+
+template <int MB, class K>
+void launch_occ(Device& dev, const K& k, int64_t n)
+{
+    if (n <= 0)
+        return;
+#ifdef FR3D_EMU
+    for (int64_t i = 0; i < n; ++i)
+        k(i);
+#else
+    const int threads = 256;
+    const int64_t blocks = (n + threads - 1) / threads;
+    FR3D_REQUIRE(blocks < (int64_t)2147483647, "launch too large: %lld items", (long long)n);
+    dev.span_begin(typeid(K).name());
+    fr3d_kernel_occ<K, MB><<<(unsigned)blocks, threads, 0, dev.stream>>>(k, n);
+    dev.span_end();
+    FR3D_CUDA(cudaGetLastError());
+#endif
+    dev.launches++;
+}
+
 template <class K>
 void launch_occ2(Device& dev, const K& k, int64_t n)
 {

@@ -952,6 +952,117 @@ struct WarpGatherK {
     }
 };
 
+// Order-3 gather with the channel loop innermost (CH independent accumulation chains per thread: the
+// 64-term float64 sum of one channel is a serial DADD chain, so a second channel doubles the work in
+// flight at the same occupancy) and the z-plane loop rolled (UNROLL_A == 0: 4*CH..16*CH loads live
+// instead of 64: fewer registers, more resident warps -- the kernel is latency-bound).  Same
+// reference lines, same arithmetic and tap order per channel as WarpGatherK, bit for bit.
+template <int CH, int UNROLL_A>
+struct WarpGatherLeanK {
+    WarpGatherK g; // order == 3, g.C == CH
+
+    FR3D_HD void operator()(int64_t item) const
+    {
+        int x, y, z, b;
+        {
+            const int t = (int)(item & 255);
+            int64_t blk = item >> 8;
+            const int tx = t % g.TX, tyz = t / g.TX;
+            x = (int)(blk % g.nbx) * g.TX + tx;
+            blk /= g.nbx;
+            y = (int)(blk % g.nby) * g.TY + tyz % g.TY;
+            blk /= g.nby;
+            z = (int)(blk % g.nbz) * g.TZ + tyz / g.TY;
+            b = (int)(blk / g.nbz);
+            if (x >= g.X || y >= g.Y || z >= g.Z)
+                return;
+        }
+        double dx, dy, dz;
+        if (g.disp64) {
+            const int64_t nvox = (int64_t)g.Z * g.Y * g.X;
+            const int64_t o = ((int64_t)z * g.Y + y) * g.X + x;
+            const double* d = g.disp64 + (int64_t)b * 3 * nvox;
+            dx = d[o] / g.hx;
+            dy = d[nvox + o] / g.hy;
+            dz = d[2 * nvox + o] / g.hz;
+        } else {
+            const float* d = g.disp32 + ((((int64_t)b * g.Z + z) * g.Y + y) * g.X + x) * 3;
+            dx = (double)d[0];
+            dy = (double)d[1];
+            dz = (double)d[2];
+        }
+        float mx = (float)((double)x + dx);
+        float my = (float)((double)y + dy);
+        float mz = (float)((double)z + dz);
+        const bool oob = (mx < 0.0f) | (mx >= (float)g.X) | (my < 0.0f) | (my >= (float)g.Y) | (mz < 0.0f) |
+                         (mz >= (float)g.Z);
+        const int64_t obase = b * g.ob + z * g.oz + y * g.oy + x * g.ox;
+        if (oob) {
+            for (int c = 0; c < CH; ++c)
+                g.out[obase + c * g.oc] =
+                    (float)load_as_double(g.ref, g.rdt, c * g.rc + z * g.rz + y * g.ry + x * g.rx);
+            return;
+        }
+        mx = fminf(fmaxf(mx, 0.0f), (float)(g.X - 1));
+        my = fminf(fmaxf(my, 0.0f), (float)(g.Y - 1));
+        mz = fminf(fmaxf(mz, 0.0f), (float)(g.Z - 1));
+        const double cx = (double)mx, cy = (double)my, cz = (double)mz;
+        const double fx = floor(cx), fy = floor(cy), fz = floor(cz);
+        double wx[4], wy[4], wz[4];
+        bspline3_weights(cx - fx, wx);
+        bspline3_weights(cy - fy, wy);
+        bspline3_weights(cz - fz, wz);
+        const int rowlen = g.X + 3;
+        const int64_t pl = (int64_t)(g.Y + 3) * rowlen, cvol = (int64_t)(g.Z + 3) * pl;
+        const double* cf = g.coef + (int64_t)b * CH * cvol + (int64_t)(int)fz * pl + (int64_t)(int)fy * rowlen + (int)fx;
+        double t[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+            t[c] = 0.0;
+        if (UNROLL_A) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+                plane(cf + a * pl, cvol, rowlen, wz[a], wy, wx, t);
+        } else {
+#pragma unroll 1
+            for (int a = 0; a < 4; ++a) {
+                const double wza = a == 0 ? wz[0] : (a == 1 ? wz[1] : (a == 2 ? wz[2] : wz[3]));
+                plane(cf, cvol, rowlen, wza, wy, wx, t);
+                cf += pl;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+            g.out[obase + c * g.oc] = (float)integer_round(t[c], g.sdt);
+    }
+
+    // one z-plane of taps: 4 rows x 4 taps x CH channels, all loads first
+    FR3D_HD static void plane(const double* p, int64_t cvol, int rowlen, double wza, const double* wy, const double* wx,
+                              double* t)
+    {
+        double v[CH][4][4];
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb)
+#pragma unroll
+            for (int c = 0; c < CH; ++c)
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc)
+                    v[c][bb][cc] = p[c * cvol + bb * rowlen + cc];
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb)
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    double q = v[c][bb][cc];
+                    q *= wza;
+                    q *= wy[bb];
+                    q *= wx[cc];
+                    t[c] += q;
+                }
+    }
+};
+
 // ------------------------------------------------------------------------------------------
 // Motion tensor, gradient constancy (core/optical_flow_3d.py:92-152), one channel at one voxel.
 // f1, f2: level images (float32-exact values).  All derivatives are central differences on
