@@ -314,18 +314,22 @@ static void spline_prefilter(fr3d_ctx* c, const void* src, int dt, int64_t sb, i
 // generic kernel capped to 64 registers (8.7 ms).  Blocks cover 32x8x1 outputs (FR3D_WARP_TILE="tx,ty,tz": A/B aid).
 static void launch_gather(fr3d_ctx* c, WarpGatherK g)
 {
-    static int tx = 32, ty = 8, tz = 1, parsed = 0;
-    if (!parsed) {
-        parsed = 1;
-        if (const char* e = getenv("FR3D_WARP_TILE")) {
-            int a = 0, b = 1, d = 1;
-            if (sscanf(e, "%d,%d,%d", &a, &b, &d) == 3 && a > 0 && a * b * d == 256) {
-                tx = a;
-                ty = b;
-                tz = d;
+    struct Tile {
+        int tx = 32, ty = 8, tz = 1;
+        Tile()
+        {
+            if (const char* e = getenv("FR3D_WARP_TILE")) {
+                int a = 0, b = 1, d = 1;
+                if (sscanf(e, "%d,%d,%d", &a, &b, &d) == 3 && a > 0 && b > 0 && d > 0 && a * b * d == 256) {
+                    tx = a;
+                    ty = b;
+                    tz = d;
+                }
             }
         }
-    }
+    };
+    static const Tile tile; // initialised once, thread-safe (contexts may be driven from several host threads)
+    const int tx = tile.tx, ty = tile.ty, tz = tile.tz;
     g.set_tile(tx, ty, tz);
     const int64_t n = g.items();
     if (g.order == 3 && g.C == 2)
