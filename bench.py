@@ -228,6 +228,10 @@ def run_gpu(args):
     bound = dev.bind_host_to_gpu(device) if world > 1 else []   # NUMA-local pinned buffers for the e2e path
     if world > 1:
         import datetime
+        # NCCL_DEBUG=VERSION makes NCCL print its version banner on STDOUT, ahead of the one JSON line this
+        # script owes the driver; keep warnings, drop the banner (INFO etc. are left alone when asked for)
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(minutes=20))
 
     B = args.batch
