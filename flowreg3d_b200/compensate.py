@@ -72,7 +72,8 @@ class SequenceCorrector:
     def __init__(self, reference_raw: np.ndarray, options, max_batch: Optional[int] = None,
                  device: Optional[torch.device] = None, group=None, streams: int = 1, statistics: bool = False):
         if bool(getattr(options, "cc_initialization", False)):
-            raise NotImplementedError("cc_initialization is not implemented on the B200 path")
+            raise NotImplementedError("cc_initialization (rigid cross-correlation pre-alignment) is not implemented on "
+                                      "the B200 path yet (its oracle is oracle/xcorr.py)")
         self.options = options
         ref = np.asarray(reference_raw)
         if ref.ndim == 3:

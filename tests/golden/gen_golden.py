@@ -279,8 +279,77 @@ def gen_config1():
     save("config1", **d)
 
 
+def gen_xcorr():
+    """Rigid cross-correlation pre-alignment (util/xcorr_prealignment.py, sequential_3d.py:89-145).
+    scikit-image is absent here, so the live reference is run with `skimage.registration` STUBBED by the oracle's
+    restatement of phase_cross_correlation (oracle/xcorr.py): the golden pins everything the reference itself
+    does around that call (projections, 2-D resize, whitening, Hann window, scaling, sign, the six executor
+    steps), not scikit-image's arithmetic."""
+    sys.path.insert(0, str(OUT.parent.parent))
+    from oracle import xcorr as OX
+    sk = types.ModuleType("skimage")
+    skr = types.ModuleType("skimage.registration")
+    skr.phase_cross_correlation = lambda a, b, **kw: (OX.phase_cross_correlation(a, b, **kw), None, None)
+    sk.registration = skr
+    sys.modules["skimage"] = sk
+    sys.modules["skimage.registration"] = skr
+    from flowreg3d.util.xcorr_prealignment import estimate_rigid_xcorr_3d
+    from flowreg3d.motion_correction.parallelization.sequential_3d import SequentialExecutor3D
+    from scipy.ndimage import shift as ndi_shift
+    rng = np.random.default_rng(21)
+    Z, Y, X, C = 24, 72, 96, 2
+    ref = np.stack([synth_volume((Z, Y, X), 50 + c) for c in range(C)], -1)
+    d = {}
+    shifts = [(3.2, -1.5, 2.0), (-4.6, 2.4, -1.0)]
+    movs = []
+    for k, sh in enumerate(shifts):
+        mov = np.stack([ndi_shift(ref[..., c], shift=(sh[2], sh[1], sh[0]), order=1, mode="nearest")
+                        for c in range(C)], -1)
+        mov = (mov + 0.01 * rng.standard_normal(mov.shape)).astype(np.float32)
+        movs.append(mov)
+        d[f"est{k}_w"] = estimate_rigid_xcorr_3d(ref, mov, target_hw=(48, 64), up=10,
+                                                 weight=np.array([0.3, 0.7], np.float32))
+        d[f"est{k}_full"] = estimate_rigid_xcorr_3d(ref, mov, target_hw=None, up=20)
+        d[f"est{k}_z"] = estimate_rigid_xcorr_3d(ref[..., 0], mov[..., 0], target_hw=(72, 48), target_z=12, up=5)
+        print("xcorr", sh, d[f"est{k}_w"], d[f"est{k}_full"], d[f"est{k}_z"])
+    # The executor steps.  NOTE (reference behaviour): BatchMotionCorrector passes the FULL (Z,Y,X,C) weight array in
+    # flow_params (compensate_recording_3D.py:212-222, 303), which estimate_rigid_xcorr_3d reshapes to a vector and
+    # contracts with the channel axis (xcorr_prealignment.py:26-30) -> ValueError("shape-mismatch for sum") for
+    # C > 1.  cc_initialization therefore only runs for single-channel recordings in the reference; the golden
+    # uses C = 1 and additionally records that the 2-channel call raises.
+    batch = np.stack(movs, 0)[..., :1]
+    ref1 = ref[..., :1]
+    sigma = np.array([[1.0, 1.0, 1.0, 0.1]])
+    rp = im3d.apply_gaussian_filter(im3d.normalize(ref1.astype(np.float64), ref=None), sigma)
+    bp = im3d.apply_gaussian_filter(im3d.normalize(batch.astype(np.float64), ref=ref1.astype(np.float64)), sigma)
+    w_init = np.zeros((Z, Y, X, 3), np.float32)
+    w_init[..., 0] = 0.5
+    fp = dict(alpha=(0.25, 0.25, 0.25), levels=100, min_level=2, eta=0.8, update_lag=4, iterations=8,
+              a_smooth=1.0, a_data=0.45, weight=np.ones((Z, Y, X, 1)), cc_initialization=True, cc_hw=(48, 64),
+              cc_up=10)
+    ex = SequentialExecutor3D()
+    reg, flows = ex.process_batch(batch, bp, ref1, rp, w_init, R.get_displacement, R.imregister_wrapper, "cubic",
+                                  None, flow_params=fp)
+    raised = 0
+    try:
+        fp2 = dict(fp, weight=np.full((Z, Y, X, 2), 0.5))
+        b2 = np.stack(movs, 0)
+        ex.process_batch(b2, b2.astype(np.float64), ref, ref.astype(np.float64), w_init, R.get_displacement,
+                         R.imregister_wrapper, "cubic", None, flow_params=fp2)
+    except ValueError as e:
+        raised = 1
+        print("2-channel cc_initialization raises:", e)
+    d["two_channel_raises"] = np.array([raised])
+    # ref = stack(synth_volume((24,72,96), 50 + c)) is rebuilt by the test (tests_inputs.synth_volume); flows and the
+    # registered frames are stored on every other y/x sample
+    save("xcorr", ref_checksum=np.array([ref.astype(np.float64).sum(), float(ref[5, 7, 11, 1])]),
+         batch=np.stack(movs, 0), shifts=np.array(shifts), w_init=w_init,
+         registered_s2=np.asarray(reg, np.float32)[:, :, ::2, ::2], flows_s2=np.asarray(flows, np.float32)[:, :, ::2, ::2],
+         **d)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["tables", "resize", "warp", "motion_tensor", "solver", "flow_small",
-                             "preprocess", "preprocess_t", "sequence", "sequence_update_ref", "config1"]
+                             "preprocess", "preprocess_t", "sequence", "sequence_update_ref", "config1", "xcorr"]
     for w in which:
         globals()[f"gen_{w}"]()
