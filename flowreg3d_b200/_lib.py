@@ -14,7 +14,7 @@ import numpy as np
 
 HERE = Path(__file__).resolve().parent
 MAX_CHANNELS = 4
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 F32, F64, U8, U16, I16, I32 = range(6)
 OPT_SOR_CTAS_PER_SM = 1
@@ -107,6 +107,16 @@ def load():
         "fr3d_mean_frames": (ci, [vp, vp, ci, i64, vp]),
         "fr3d_mean_frames_f64": (ci, [vp, vp, ci, i64, vp]),
         "fr3d_flow_stats": (ci, [vp, vp, ci, ci, ci, ci, vp]),
+        "fr3d_warp_flow": (ci, [vp, vp, ci, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]),
+        "fr3d_cc_project": (ci, [vp, vp, ci, ci, ci, ci, ci, vp, vp]),
+        "fr3d_cc_window": (ci, [vp, vp, ci, ci, ci, vp, vp, vp]),
+        "fr3d_cc_cgemm": (ci, [vp, vp, i64, vp, i64, vp, ci, ci, ci, ci]),
+        "fr3d_cc_cross_power": (ci, [vp, vp, vp, vp, i64, ci, ci]),
+        "fr3d_cc_abs_argmax": (ci, [vp, vp, i64, ci, vp]),
+        "fr3d_cc_wrap_shift": (ci, [vp, vp, ci, ci, ci, vp, vp, vp]),
+        "fr3d_cc_tile_sums": (ci, [vp, vp, vp, ci, ci, ci, vp, vp]),
+        "fr3d_rigid_flow": (ci, [vp, vp, vp, ci, i64, vp]),
+        "fr3d_add_flow": (ci, [vp, vp, vp, i64, vp]),
         "fr3d_profile_enable": (ci, [vp, ci]),
         "fr3d_profile_report": (i64, [vp, C.c_char_p, i64]),
         "fr3d_fill_resize_table": (ci, [ci, ci, vp, ci, vp, vp]),
@@ -129,6 +139,8 @@ EXPORTED_SYMBOLS = [
     "fr3d_compensate", "fr3d_resize3d", "fr3d_warp", "fr3d_motion_tensor",
     "fr3d_sor_level", "fr3d_median5", "fr3d_mean_frames", "fr3d_mean_frames_f64", "fr3d_flow_stats", "fr3d_profile_enable",
     "fr3d_profile_report", "fr3d_fill_resize_table",
+    "fr3d_warp_flow", "fr3d_cc_project", "fr3d_cc_window", "fr3d_cc_cgemm", "fr3d_cc_cross_power",
+    "fr3d_cc_abs_argmax", "fr3d_cc_wrap_shift", "fr3d_cc_tile_sums", "fr3d_rigid_flow", "fr3d_add_flow",
 ]
 
 

@@ -71,9 +71,6 @@ class SequenceCorrector:
 
     def __init__(self, reference_raw: np.ndarray, options, max_batch: Optional[int] = None,
                  device: Optional[torch.device] = None, group=None, streams: int = 1, statistics: bool = False):
-        if bool(getattr(options, "cc_initialization", False)):
-            raise NotImplementedError("cc_initialization (rigid cross-correlation pre-alignment) is not implemented on "
-                                      "the B200 path yet (its oracle is oracle/xcorr.py)")
         self.options = options
         ref = np.asarray(reference_raw)
         if ref.ndim == 3:
@@ -95,6 +92,17 @@ class SequenceCorrector:
         else:
             self.reg = Registration(self.shape, Cn, fp, max_batch=mb, device=device, **kw)
         self.device = self.reg.device
+        # rigid cross-correlation pre-alignment (OFOptions.cc_initialization / cc_hw / cc_up)
+        self.cc = bool(getattr(options, "cc_initialization", False))
+        self.cc_hw = getattr(options, "cc_hw", 256)
+        self.cc_up = int(getattr(options, "cc_up", 10))
+        if self.cc and Cn != 1:
+            # the reference pipeline fails the same way at its first batch (xcorr_prealignment.py:26-30 contracts the
+            # full (Z,Y,X,C) weight array with the channel axis)
+            raise ValueError("shape-mismatch for sum: cc_initialization supports single-channel recordings only, "
+                             "as in the reference")
+        if self.cc and isinstance(self.reg, SplitRegistration):
+            raise NotImplementedError("cc_initialization is implemented for one stream per GPU")
         # weights (compensate_recording_3D.py:211-224)
         wvec = [options.get_weight_at(c, Cn) for c in range(Cn)]
         if all(np.ndim(w) == 0 for w in wvec):
@@ -117,7 +125,8 @@ class SequenceCorrector:
             raise NotImplementedError("a temporal pre-filter (sigma_t >= 0.125) couples the frames of a batch; it is "
                                       "not implemented for batches sharded over several GPUs")
         self._weight = weight
-        self._ref_proc64 = (dev.empty((1, Z, Y, X, Cn), np.float64, self.device) if self.update_reference else None)
+        self._ref_proc64 = (dev.empty((1, Z, Y, X, Cn), np.float64, self.device)
+                            if (self.update_reference or self.cc) else None)
         ref_proc = self.reg.preprocess(ref_dev[None], self.lo, self.den, temporal=False, out64=self._ref_proc64)
         self.reg.set_reference(ref_proc[0], weight=weight, ref_raw=ref_dev)
         self.w_init: Optional[torch.Tensor] = None  # (Z,Y,X,3) float32 on device
@@ -125,7 +134,16 @@ class SequenceCorrector:
         self._stats: List[torch.Tensor] = []        # per batch (t,4) device tensors, see statistics()
 
     # -- helpers ------------------------------------------------------------------------
-    def _flows(self, proc: torch.Tensor, uvw: Optional[torch.Tensor]) -> torch.Tensor:
+    def _flows(self, proc: torch.Tensor, uvw: Optional[torch.Tensor], proc64: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if self.cc:
+            # sequential_3d.py:89-145 -- also for the w_init bootstrap (the reference's bootstrap goes through the
+            # same executor call with a zero field); the warps read the float64 pre-processed frames as there
+            Z, Y, X = self.shape
+            w0 = uvw if uvw is not None else torch.zeros((Z, Y, X, 3), dtype=torch.float32, device=self.device)
+            src = proc64 if proc64 is not None else proc
+            flows, _ = self.reg.get_displacement_cc(src, w0, cc_hw=self.cc_hw, cc_up=self.cc_up,
+                                                    ref_proc64=self._ref_proc64[0, ..., 0])
+            return flows
         outs = []
         for t0 in range(0, proc.shape[0], self.reg.max_batch):
             outs.append(self.reg.get_displacement(proc[t0:t0 + self.reg.max_batch], uvw=uvw))
@@ -152,17 +170,18 @@ class SequenceCorrector:
         raw = self.reg._as_dev(raw_local, None, None)
         t = raw.shape[0]
         G = t if global_size is None else int(global_size)
-        proc64 = (dev.empty(tuple(raw.shape), np.float64, self.device) if (self.update_reference and t > 0) else None)
+        proc64 = (dev.empty(tuple(raw.shape), np.float64, self.device)
+                  if ((self.update_reference or self.cc) and t > 0) else None)
         proc = self.reg.preprocess(raw, self.lo, self.den, out64=proc64) if t > 0 else None
         if self.w_init is None:
             # bootstrap (compensate_recording_3D.py:359-388): first min(22, G) frames from zero flow
             n_init = min(22, G)
             a, b = max(0, -local_offset), max(0, min(t, n_init - local_offset))
-            w0 = self._flows(proc[a:b], None) if b > a else None
+            w0 = self._flows(proc[a:b], None, None if proc64 is None else proc64[a:b]) if b > a else None
             self.w_init = self._mean_of(w0, n_init)
         use_chain = bool(getattr(self.options, "update_initialization_w", True))
         uvw = self.w_init if use_chain else torch.zeros_like(self.w_init)
-        flows = self._flows(proc, uvw) if t > 0 else None
+        flows = self._flows(proc, uvw, proc64) if t > 0 else None
         if use_chain:
             # (:481-485) mean of the last <= 20 flows of the global batch
             first = G - 20 if G > 20 else 0

@@ -10,7 +10,7 @@ context they are built on.  All per-voxel work happens in libfr3d's CUDA kernels
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Sequence
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -166,6 +166,8 @@ class Registration:
             # the reference resizes float32(weight); FillK rounds the float64 constant to float32 the same way
             wc = (C.c_double * _lib.MAX_CHANNELS)(*([float(v) for v in wconst] + [0.0] * (_lib.MAX_CHANNELS - self.C)))
         _check(self.ctx.h, self.ctx.lib.fr3d_set_reference(self.ctx.h, dev.ptr(rp), dev.ptr(wdev), wc))
+        self._ref_proc = rp      # out-of-volume fill of the pre-alignment warps (cc_initialization)
+        self._xcorr = None       # (key, RigidXCorr) for this reference
         if ref_raw is not None:
             rr = ref_raw if isinstance(ref_raw, torch.Tensor) else np.asarray(ref_raw)
             if not isinstance(rr, torch.Tensor) and rr.dtype not in _lib._DTYPES:
@@ -214,6 +216,70 @@ class Registration:
             self.ctx.h, dev.ptr(mv), dev.ptr(uv), B, dev.ptr(out), self._code(out)))
         self._keep = [mv, uv]
         return out
+
+    def get_displacement_cc(self, moving_proc, w_init, cc_hw=256, cc_up: int = 10,
+                            ref_proc64=None) -> Tuple[torch.Tensor, np.ndarray]:
+        """Flows of B frames with the rigid cross-correlation pre-alignment (cc_initialization=True), the six steps
+        of parallelization/sequential_3d.py:89-145 for all frames of the batch at once:
+        (1) warp every frame by w_init ("linear"), (2) rigid residual per frame by phase correlation of the mean
+        projections (flowreg3d_b200.xcorr), (3) w_init + rigid, (4) warp the ORIGINAL frame by the combined field
+        ("linear"), (5) non-rigid residual flow from zero, (6) total = combined + residual, rounded once to float32.
+        moving_proc: (B,Z,Y,X,1) pre-processed frames, float64 (as the reference warps them) or float32.
+        ref_proc64: the float64 pre-processed fixed volume if the caller has it (the reference averages its
+        projections in float64); default: the float32 volume given to set_reference.
+        Single channel only, like the reference pipeline (see flowreg3d_b200/xcorr.py).
+        Returns (flows (B,Z,Y,X,3) float32 on the device, rigid (B,3) float32 host)."""
+        from .xcorr import RigidXCorr
+        if self.C != 1:
+            # what the reference pipeline does for C > 1: estimate_rigid_xcorr_3d contracts the full (Z,Y,X,C)
+            # weight array with the channel axis (xcorr_prealignment.py:26-30)
+            raise ValueError("shape-mismatch for sum (cc_initialization supports single-channel recordings only, "
+                             "as in the reference)")
+        Z, Y, X = self.shape
+        mv = self._as_dev(moving_proc, None, None)
+        if mv.dim() == 4:
+            mv = mv[None]
+        B = mv.shape[0]
+        if tuple(mv.shape[1:]) != (Z, Y, X, 1):
+            raise ValueError(f"moving frames have shape {tuple(mv.shape)}, expected (B,{self.shape},1)")
+        wi = self._as_dev(w_init, np.float32, (Z, Y, X, 3))
+        lib, h = self.ctx.lib, self.ctx.h
+        key = (cc_hw if isinstance(cc_hw, int) else tuple(cc_hw), int(cc_up))
+        if self._xcorr is None or self._xcorr[0] != key:
+            xc = RigidXCorr(self.shape, target_hw=cc_hw, up=int(cc_up), ctx=self.ctx)
+            if ref_proc64 is not None:
+                r64 = self._as_dev(ref_proc64, np.float64, (Z, Y, X))
+                xc.set_reference(r64.to(torch.float32), float64_mean=True)   # projections of float32(ref): <= 1 ulp
+            else:
+                xc.set_reference(self._ref_proc.reshape(Z, Y, X), float64_mean=True)
+            self._xcorr = (key, xc)
+        xc = self._xcorr[1]
+        nvox = Z * Y * X
+
+        def rigid_field(rigid):
+            out = dev.empty((B, Z, Y, X, 3), np.float32, self.device)
+            r = np.ascontiguousarray(rigid, np.float32)
+            _check(h, lib.fr3d_rigid_flow(h, dev.ptr(wi), r.ctypes.data, B, nvox, dev.ptr(out)))
+            return out
+
+        def warp_linear(flow):
+            out = dev.empty((B, Z, Y, X, 1), np.float32, self.device)
+            _check(h, lib.fr3d_warp_flow(h, dev.ptr(mv), self._code(mv), dev.ptr(flow), dev.ptr(self._ref_proc),
+                                         _lib.F32, B, Z, Y, X, 1, 1, dev.ptr(out)))
+            return out
+
+        part = warp_linear(rigid_field(np.zeros((B, 3), np.float32)))            # (1)
+        rigid = xc.estimate(part.reshape(B, Z, Y, X))                             # (2)
+        comb = rigid_field(rigid)                                                 # (3)
+        aligned = warp_linear(comb)                                               # (4)
+        flows = dev.empty((B, Z, Y, X, 3), np.float32, self.device)
+        for t0 in range(0, B, self.max_batch):                                    # (5), (6)
+            t1 = min(B, t0 + self.max_batch)
+            resid = self.get_displacement(aligned[t0:t1], uvw=None, out_dtype=np.float64)
+            _check(h, lib.fr3d_add_flow(h, dev.ptr(comb[t0:t1]), dev.ptr(resid), (t1 - t0) * nvox * 3,
+                                        dev.ptr(flows[t0:t1])))
+        self._keep = [mv, wi, comb, aligned, part]
+        return flows, rigid
 
     def compensate(self, raw, flow, ref_raw=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Warp B raw frames with their flows (float32), out-of-volume voxels from ref_raw."""

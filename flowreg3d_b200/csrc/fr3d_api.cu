@@ -8,6 +8,7 @@
 #endif
 
 #include "fr3d_sor.h"
+#include "fr3d_xcorr.h"
 
 using namespace fr3d;
 
@@ -121,6 +122,9 @@ struct fr3d_ctx {
     // workspaces (grow-only)
     Buf<float> t1, t2, f2, tmp, fscr;
     Buf<double> uvw_a, uvw_b, coef, J, AB, dnat, g1, g2, wnat;
+    Buf<double> cc_shift;      // rigid pre-alignment: small per-frame parameter blocks
+    Buf<int> cc_int;
+    Buf<float> cc_f32;
     Buf<char> L, d, U, dold; // (B, npad) Vec4 of the state dtype
     Buf<double> psi_c, psi_r;
     Buf<unsigned> bar;
@@ -1328,4 +1332,114 @@ int fr3d_fill_resize_table(int in_len, int out_len, const float* g, int R, int32
     return FR3D_OK;
 }
 
+// ---- rigid cross-correlation pre-alignment (fr3d_xcorr.h) -------------------------------------------------------
+int fr3d_warp_flow(fr3d_ctx* ctx, const void* vol, int vol_dtype, const float* flow, const void* ref, int ref_dtype,
+                   int B, int Z, int Y, int X, int C, int interp, float* out)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(vol && flow && ref && out && B >= 1, "null argument");
+    FR3D_REQUIRE(Z > 0 && Y > 0 && X > 0 && C >= 1 && C <= FR3D_MAX_CHANNELS, "bad shape");
+    warp_common(_c, vol, vol_dtype, nullptr, flow, ref, ref_dtype, B, Z, Y, X, C, interp, out);
+    FR3D_API_END()
+}
+
+int fr3d_cc_project(fr3d_ctx* ctx, const float* vol, int B, int Z, int Y, int X, int acc64, float* pxy, float* pxz)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(vol && pxy && pxz && B >= 1 && Z > 0 && Y > 0 && X > 0, "bad argument");
+    launch(_c->dev, CcProjectK{vol, pxy, pxz, B, Z, Y, X, acc64}, (int64_t)B * X * ((int64_t)Y + Z));
+    FR3D_API_END()
+}
+
+int fr3d_cc_window(fr3d_ctx* ctx, const float* p, int B, int H, int W, const float* hy, const float* hx, double* out)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(p && hy && hx && out && B >= 1 && H > 0 && W > 0, "bad argument");
+    float* mean = _c->cc_f32.ensure(_c->dev, (size_t)B);
+    launch(_c->dev, CcPlaneMeanK{p, mean, (int64_t)H * W}, B);
+    launch(_c->dev, CcWindowK{p, mean, hy, hx, out, H, W}, (int64_t)B * H * W);
+    FR3D_API_END()
+}
+
+int fr3d_cc_cgemm(fr3d_ctx* ctx, const double* A, int64_t a_stride, const double* Bm, int64_t b_stride, double* Cm,
+                  int M, int N, int K, int nbatch)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(A && Bm && Cm && M > 0 && N > 0 && K > 0 && nbatch >= 1 && a_stride >= 0 && b_stride >= 0,
+                 "bad argument");
+    launch(_c->dev, CcGemmK{A, Bm, Cm, a_stride, b_stride, M, N, K}, (int64_t)nbatch * M * N);
+    FR3D_API_END()
+}
+
+int fr3d_cc_cross_power(fr3d_ctx* ctx, const double* Fr, const double* Fm, double* P, int64_t n, int nbatch,
+                        int normalize)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(Fr && Fm && P && n > 0 && nbatch >= 1, "bad argument");
+    launch(_c->dev, CcCrossPowerK{Fr, Fm, P, n, normalize}, (int64_t)nbatch * n);
+    FR3D_API_END()
+}
+
+int fr3d_cc_abs_argmax(fr3d_ctx* ctx, const double* cc, int64_t n, int nbatch, int64_t* idx)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(cc && idx && n > 0 && nbatch >= 1, "bad argument");
+    launch(_c->dev, CcAbsArgmaxK{cc, idx, n}, nbatch);
+    FR3D_API_END()
+}
+
+int fr3d_cc_wrap_shift(fr3d_ctx* ctx, const double* img_c, int B, int H, int W, const double* shift_host,
+                       double* work, double* out)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(img_c && shift_host && work && out && B >= 1 && H > 0 && W > 0, "bad argument");
+    std::vector<int> order((size_t)B);
+    bool any3 = false;
+    for (int b = 0; b < B; ++b) {
+        // scikit-image: spline order 3 when any component of the shift is fractional, 0 otherwise
+        const double sy = shift_host[2 * b], sx = shift_host[2 * b + 1];
+        order[b] = (sy != floor(sy) || sx != floor(sx)) ? 3 : 0;
+        any3 = any3 || order[b] == 3;
+    }
+    double* dshift = _c->cc_shift.upload(_c->dev, shift_host, (size_t)2 * B);
+    int* dorder = _c->cc_int.upload(_c->dev, order.data(), (size_t)B);
+    const int64_t n = (int64_t)H * W;
+    launch(_c->dev, StridedCopyK{img_c, work, 2}, (int64_t)B * n); // real parts of the complex planes
+    if (any3) {
+        // axis 0 (lines along y: element stride W, one line per x), then axis 1
+        launch(_c->dev, CcSplineWrapK{work, H, (int64_t)W, 1, n, W}, (int64_t)B * W);
+        launch(_c->dev, CcSplineWrapK{work, W, 1, (int64_t)W, n, H}, (int64_t)B * H);
+    }
+    launch(_c->dev, CcWrapShiftK{work, img_c, dshift, dorder, out, H, W}, (int64_t)B * n);
+    FR3D_API_END()
+}
+
+int fr3d_cc_tile_sums(fr3d_ctx* ctx, const double* ref_c, const double* shifted, int B, int H, int W,
+                      const int* split_host, double* out)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(ref_c && shifted && split_host && out && B >= 1 && H > 0 && W > 0, "bad argument");
+    int* dsplit = _c->cc_int.upload(_c->dev, split_host, (size_t)2 * B);
+    launch(_c->dev, CcTileSumsK{ref_c, shifted, dsplit, out, H, W}, (int64_t)B * 4);
+    FR3D_API_END()
+}
+
+int fr3d_rigid_flow(fr3d_ctx* ctx, const float* w_init, const float* rigid_host, int B, int64_t nvox, float* out)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(w_init && rigid_host && out && B >= 1 && nvox > 0, "bad argument");
+    float* dr = _c->cc_f32.upload(_c->dev, rigid_host, (size_t)3 * B);
+    launch(_c->dev, CcRigidFlowK{w_init, dr, out, 3 * nvox}, (int64_t)B * 3 * nvox);
+    FR3D_API_END()
+}
+
+int fr3d_add_flow(fr3d_ctx* ctx, const float* comb, const double* resid, int64_t n, float* out)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(comb && resid && out && n > 0, "bad argument");
+    launch(_c->dev, CcAddFlowK{comb, resid, out}, n);
+    FR3D_API_END()
+}
+
 } // extern "C"
+

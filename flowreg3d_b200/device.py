@@ -13,7 +13,8 @@ from . import _lib
 
 _TORCH_DT = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
              np.dtype(np.uint8): torch.uint8, np.dtype(np.uint16): torch.uint16,
-             np.dtype(np.int16): torch.int16, np.dtype(np.int32): torch.int32}
+             np.dtype(np.int16): torch.int16, np.dtype(np.int32): torch.int32,
+             np.dtype(np.int64): torch.int64}
 
 
 def torch_dtype(dt):

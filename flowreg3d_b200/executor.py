@@ -89,9 +89,9 @@ class B200Executor3D(_Base):
             raise ValueError(f"batch must be (T,Z,Y,X,C), got shape {batch.shape}")
         T, Z, Y, X, Cn = batch.shape
         fp_all = kwargs.get("flow_params", {})
-        if bool(fp_all.get("cc_initialization", False)):
-            raise NotImplementedError("cc_initialization (rigid cross-correlation pre-alignment) is not "
-                                      "implemented on the B200 path")
+        use_cc = bool(fp_all.get("cc_initialization", False))            # sequential_3d.py:62-72
+        cc_hw = fp_all.get("cc_hw", 256)
+        cc_up = int(fp_all.get("cc_up", 10))
         fp, weight = flow_params_from_dict(fp_all)
         reg = self._registration((Z, Y, X), Cn, fp, interpolation_method)
         self._ensure_reference(reg, reference_proc, reference_raw, weight)
@@ -101,8 +101,14 @@ class B200Executor3D(_Base):
         uvt = None if uv is None else dev.to_device(uv, reg.device)
         for t0 in range(0, T, reg.max_batch):
             t1 = min(T, t0 + reg.max_batch)
-            mv = np.asarray(batch_proc[t0:t1]).astype(np.float32)
-            flow = reg.get_displacement(mv, uvw=uvt)
+            if use_cc:
+                w0 = uvt if uvt is not None else np.zeros((Z, Y, X, 3), np.float32)
+                flow, _ = reg.get_displacement_cc(np.asarray(batch_proc[t0:t1], np.float64), w0, cc_hw=cc_hw,
+                                                  cc_up=cc_up, ref_proc64=np.asarray(reference_proc, np.float64)
+                                                  .reshape(Z, Y, X, -1)[..., 0])
+            else:
+                mv = np.asarray(batch_proc[t0:t1]).astype(np.float32)
+                flow = reg.get_displacement(mv, uvw=uvt)
             out = reg.compensate(batch[t0:t1], flow)
             reg.sync()
             flows[t0:t1] = dev.to_host(flow)

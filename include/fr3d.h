@@ -34,7 +34,7 @@ extern "C" {
 
 #define FR3D_MAX_CHANNELS 4
 #define FR3D_MAX_LEVELS 64
-#define FR3D_ABI_VERSION 4
+#define FR3D_ABI_VERSION 5
 
 typedef enum {
     FR3D_OK = 0,
@@ -241,6 +241,50 @@ int fr3d_mean_frames_f64(fr3d_ctx* ctx, const float* frames, int T, int64_t n, d
  * (numpy.gradient semantics, unit spacing), |mean translation|.  float64 accumulation (the reference
  * accumulates in float32: agreement to ~1e-6 relative, not bit-exact). */
 int fr3d_flow_stats(fr3d_ctx* ctx, const float* flow, int B, int Z, int Y, int X, double* out);
+
+/* ---- rigid cross-correlation pre-alignment: cc_initialization=True -----------------------------
+ * (util/xcorr_prealignment.py:15-99 estimate_rigid_xcorr_3d; executor steps
+ * motion_correction/parallelization/sequential_3d.py:89-145).  Stage entry points; the host logic
+ * between them (peak -> refinement window -> wrap disambiguation, i.e. what the reference delegates
+ * to skimage.registration.phase_cross_correlation) is flowreg3d_b200/xcorr.py.  "complex" arrays are
+ * interleaved (re, im) float64, row-major. */
+/* imregister_wrapper for B frames with per-frame float32 flows and an explicit interpolation
+ * (sequential_3d.py:92-99, 124-131 use "linear" whatever OFOptions.interpolation_method says). */
+int fr3d_warp_flow(fr3d_ctx* ctx, const void* vol, int vol_dtype, const float* flow, const void* ref,
+                   int ref_dtype, int B, int Z, int Y, int X, int C, int interp, float* out);
+/* _proj_xy / _proj_xz (xcorr_prealignment.py:8-13): vol (B,Z,Y,X) float32 -> pxy (B,Y,X), pxz (B,Z,X)
+ * float32; acc64 = 0: numpy's float32 slice-by-slice mean of the float32 warp output, 1: float64
+ * accumulation (the float64 reference volume). */
+int fr3d_cc_project(fr3d_ctx* ctx, const float* vol, int B, int Z, int Y, int X, int acc64, float* pxy,
+                    float* pxz);
+/* p - p.mean(), times the separable Hann window hy[:,None]*hx[None,:], all float32
+ * (xcorr_prealignment.py:50-58, 81-89); p (B,H,W) float32, hy/hx device float32; out (B,H,W) complex. */
+int fr3d_cc_window(fr3d_ctx* ctx, const float* p, int B, int H, int W, const float* hy, const float* hx,
+                   double* out);
+/* C[b] = A[b] (M,K) x Bm[b] (K,N), complex; batch strides in complex elements, 0 = shared matrix.  The 2-D DFTs
+ * of phase_cross_correlation (forward, inverse and the up-sampled refinement window) are products with host-built
+ * DFT matrices. */
+int fr3d_cc_cgemm(fr3d_ctx* ctx, const double* A, int64_t a_stride, const double* Bm, int64_t b_stride,
+                  double* Cm, int M, int N, int K, int nbatch);
+/* P[b] = Fr * conj(Fm[b]) (n complex each); normalize != 0: P /= max(|P|, 100 eps_float32) ("phase"). */
+int fr3d_cc_cross_power(fr3d_ctx* ctx, const double* Fr, const double* Fm, double* P, int64_t n, int nbatch,
+                        int normalize);
+/* idx[b] = numpy.argmax(numpy.abs(cc[b])) (first maximum), cc (nbatch, n) complex; idx device int64. */
+int fr3d_cc_abs_argmax(fr3d_ctx* ctx, const double* cc, int64_t n, int nbatch, int64_t* idx);
+/* scipy.ndimage.shift(img[b], shift[b], mode="grid-wrap", order = 3 if the shift is fractional else 0) ->
+ * float32 values (skimage _disambiguate_shift); img_c (B,H,W) complex (real part used), shift_host (B,2) host
+ * (sy, sx); work, out (B,H,W) float64 device. */
+int fr3d_cc_wrap_shift(fr3d_ctx* ctx, const double* img_c, int B, int H, int W, const double* shift_host,
+                       double* work, double* out);
+/* sums for the Pearson correlation of the four tiles split at (sy, sx) of the reference plane ref_c (H,W) complex
+ * and shifted[b] (H,W): out (B,4,6) device = n, Sa, Sb, Saa, Sbb, Sab; tile = 2*(y >= sy) + (x >= sx). */
+int fr3d_cc_tile_sums(fr3d_ctx* ctx, const double* ref_c, const double* shifted, int B, int H, int W,
+                      const int* split_host, double* out);
+/* w_combined[b] = w_init + rigid[b] (sequential_3d.py:117-121), float32; rigid_host (B,3) host. */
+int fr3d_rigid_flow(fr3d_ctx* ctx, const float* w_init, const float* rigid_host, int B, int64_t nvox,
+                    float* out);
+/* (w_combined + w_residual).astype(float32) (sequential_3d.py:140-141): n elements. */
+int fr3d_add_flow(fr3d_ctx* ctx, const float* comb, const double* resid, int64_t n, float* out);
 
 /* ---- host helpers ----------------------------------------------------------------------- */
 /* util/resize_util_3D.py:76-95: fill idx/wt (host, out_len*(2R+4)) from the float32 Gaussian g

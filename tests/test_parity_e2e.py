@@ -88,7 +88,9 @@ def test_executor_matches_sequential_semantics(backend, golden):
     assert rel_l2(reg, oreg) <= 1e-6
     oreg2, _ = O.process_batch(batch[:1], bproc[:1], ref_raw, ref_proc, w0, "linear", fp)
     assert rel_l2(reg2, oreg2) <= 1e-6
-    with pytest.raises(NotImplementedError):
+    # cc_initialization on a multi-channel batch: ValueError, as the reference pipeline raises (the full weight array
+    # meets estimate_rigid_xcorr_3d's tensordot, xcorr_prealignment.py:26-30); single channel: tests/test_xcorr.py
+    with pytest.raises(ValueError):
         ex.process_batch(batch, bproc, ref_raw, ref_proc, w0, flow_params={**fp, "cc_initialization": True})
 
 
