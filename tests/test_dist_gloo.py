@@ -18,7 +18,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, emu_path, tmp):
+def _worker(rank, world, port, emu_path, tmp, cc=False):
     os.environ["FR3D_LIBRARY_OVERRIDE"] = emu_path
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -31,23 +31,32 @@ def _worker(rank, world, port, emu_path, tmp):
     opts = F.OFOptions(min_level=3, iterations=8, update_lag=4, buffer_size=5, weight=[0.5, 0.5])
     v = g["video"][:, :12, :24, :28]
     r = g["ref"][:12, :24, :28]
+    if cc:   # rigid cross-correlation pre-alignment: single channel (as in the reference), per-rank estimator
+        opts = F.OFOptions(min_level=3, iterations=8, update_lag=4, buffer_size=5, cc_initialization=True,
+                           cc_hw=(20, 24), cc_up=10)
+        v, r = v[..., :1], r[..., :1]
     reg, w, idx = F.compensate_arr_3D_sharded(v, r, opts)
     np.savez(os.path.join(tmp, f"r{rank}.npz"), reg=reg, w=w, idx=idx)
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_rank_sharding_matches_single_process(emu_backend, tmp_path):
+@pytest.mark.parametrize("cc", [False, True])
+def test_two_rank_sharding_matches_single_process(emu_backend, tmp_path, cc):
     from emu.build_emu import build
     import flowreg3d_b200 as F
     emu = str(build())
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), emu, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), emu, str(tmp_path), cc), nprocs=world, join=True)
     g = np.load(ROOT / "tests" / "golden" / "sequence.npz")
     opts = F.OFOptions(min_level=3, iterations=8, update_lag=4, buffer_size=5, weight=[0.5, 0.5],
                        output_typename=None)
     v = g["video"][:, :12, :24, :28]
     r = g["ref"][:12, :24, :28]
+    if cc:
+        opts = F.OFOptions(min_level=3, iterations=8, update_lag=4, buffer_size=5, cc_initialization=True,
+                           cc_hw=(20, 24), cc_up=10, output_typename=None)
+        v, r = v[..., :1], r[..., :1]
     reg1, w1 = F.compensate_arr_3D(v, r, opts)
     seen = []
     for rank in range(world):
