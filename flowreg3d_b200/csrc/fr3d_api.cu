@@ -670,6 +670,10 @@ int fr3d_set_option(fr3d_ctx* ctx, int option, int64_t value)
         FR3D_REQUIRE(value >= 0 && value <= 32, "FR3D_OPT_SOR_CTAS_PER_SM: %lld", (long long)value);
         _c->dev.sor_ctas_per_sm = (int)value;
         break;
+    case FR3D_OPT_CC_BLOCK_SCANS:
+        FR3D_REQUIRE(value == 0 || value == 1, "FR3D_OPT_CC_BLOCK_SCANS: %lld", (long long)value);
+        _c->dev.cc_block_scans = (int)value;
+        break;
     default: FR3D_THROW(FR3D_ERR_ARG, "unknown option %d", option);
     }
     FR3D_API_END()
@@ -1356,7 +1360,10 @@ int fr3d_cc_window(fr3d_ctx* ctx, const float* p, int B, int H, int W, const flo
     FR3D_API_BEGIN(ctx)
     FR3D_REQUIRE(p && hy && hx && out && B >= 1 && H > 0 && W > 0, "bad argument");
     float* mean = _c->cc_f32.ensure(_c->dev, (size_t)B);
-    launch(_c->dev, CcPlaneMeanK{p, mean, (int64_t)H * W}, B);
+    if (_c->dev.cc_block_scans)
+        launch_tiles(_c->dev, CcPlaneMeanTileK{p, mean, (int64_t)H * W}, B, 256, (size_t)256 * sizeof(double));
+    else
+        launch(_c->dev, CcPlaneMeanK{p, mean, (int64_t)H * W}, B);
     launch(_c->dev, CcWindowK{p, mean, hy, hx, out, H, W}, (int64_t)B * H * W);
     FR3D_API_END()
 }
@@ -1384,7 +1391,10 @@ int fr3d_cc_abs_argmax(fr3d_ctx* ctx, const double* cc, int64_t n, int nbatch, i
 {
     FR3D_API_BEGIN(ctx)
     FR3D_REQUIRE(cc && idx && n > 0 && nbatch >= 1, "bad argument");
-    launch(_c->dev, CcAbsArgmaxK{cc, idx, n}, nbatch);
+    if (_c->dev.cc_block_scans)
+        launch_tiles(_c->dev, CcAbsArgmaxTileK{cc, idx, n}, nbatch, 256, (size_t)256 * 2 * sizeof(double));
+    else
+        launch(_c->dev, CcAbsArgmaxK{cc, idx, n}, nbatch);
     FR3D_API_END()
 }
 
@@ -1420,7 +1430,11 @@ int fr3d_cc_tile_sums(fr3d_ctx* ctx, const double* ref_c, const double* shifted,
     FR3D_API_BEGIN(ctx)
     FR3D_REQUIRE(ref_c && shifted && split_host && out && B >= 1 && H > 0 && W > 0, "bad argument");
     int* dsplit = _c->cc_int.upload(_c->dev, split_host, (size_t)2 * B);
-    launch(_c->dev, CcTileSumsK{ref_c, shifted, dsplit, out, H, W}, (int64_t)B * 4);
+    if (_c->dev.cc_block_scans)
+        launch_tiles(_c->dev, CcTileSumsTileK{ref_c, shifted, dsplit, out, H, W}, (int64_t)B * 4, 256,
+                     (size_t)256 * 6 * sizeof(double));
+    else
+        launch(_c->dev, CcTileSumsK{ref_c, shifted, dsplit, out, H, W}, (int64_t)B * 4);
     FR3D_API_END()
 }
 

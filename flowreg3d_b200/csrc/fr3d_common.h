@@ -79,6 +79,7 @@ struct Device {
     int64_t bytes = 0;
     int sm_count = 1;
     int sor_ctas_per_sm = 0; // 0 = as many as fit
+    int cc_block_scans = 0;  // FR3D_OPT_CC_BLOCK_SCANS
 
     // Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline
     // figures).  Off by default; when on, every launch is bracketed by two event records.

@@ -300,6 +300,122 @@ struct CcTileSumsK {
     }
 };
 
+// ---- block-cooperative versions of the three plane scans (FR3D_OPT_CC_BLOCK_SCANS) ---------------------------
+// Two phases (tile-kernel contract, fr3d_common.h): every thread reduces a strided subset into shared memory,
+// thread 0 combines the partials in thread order -- deterministic, and for the arg-max identical to the serial scan
+// (largest |.|, smallest index among equals).
+struct CcPlaneMeanTileK {
+    static constexpr int PHASES = 2;
+    const float* p;
+    float* mean;
+    int64_t n;
+    FR3D_HD void phase(int ph, int64_t b, int tid, int nthreads, double* sm) const
+    {
+        if (ph == 0) {
+            const float* q = p + b * n;
+            double s = 0.0;
+            for (int64_t i = tid; i < n; i += nthreads)
+                s += (double)q[i];
+            sm[tid] = s;
+            return;
+        }
+        if (tid != 0)
+            return;
+        double s = 0.0;
+        for (int k = 0; k < nthreads; ++k)
+            s += sm[k];
+        mean[b] = (float)(s / (double)n);
+    }
+};
+
+struct CcAbsArgmaxTileK {
+    static constexpr int PHASES = 2;
+    const double* cc;
+    int64_t* idx;
+    int64_t n;
+    FR3D_HD void phase(int ph, int64_t b, int tid, int nthreads, double* sm) const
+    {
+        if (ph == 0) {
+            const double* q = cc + 2 * b * n;
+            double best = -1.0;
+            int64_t at = 0;
+            for (int64_t i = tid; i < n; i += nthreads) {
+                const double re = q[2 * i], im = q[2 * i + 1];
+                const double m = sqrt(re * re + im * im);
+                if (m > best) {
+                    best = m;
+                    at = i;
+                }
+            }
+            sm[2 * tid] = best;
+            sm[2 * tid + 1] = (double)at; // exact: plane sizes are far below 2^53
+            return;
+        }
+        if (tid != 0)
+            return;
+        double best = -1.0;
+        int64_t at = 0;
+        for (int k = 0; k < nthreads; ++k) {
+            const double v = sm[2 * k];
+            const int64_t a = (int64_t)sm[2 * k + 1];
+            if (v > best || (v == best && v >= 0.0 && a < at)) {
+                best = v;
+                at = a;
+            }
+        }
+        idx[b] = at;
+    }
+};
+
+struct CcTileSumsTileK {
+    static constexpr int PHASES = 2;
+    const double* ref;
+    const double* shifted;
+    const int* split;
+    double* out;
+    int H, W;
+    FR3D_HD void phase(int ph, int64_t item, int tid, int nthreads, double* sm) const
+    {
+        const int tile = (int)(item & 3);
+        const int64_t b = item >> 2;
+        if (ph == 0) {
+            const int sy = split[2 * b], sx = split[2 * b + 1];
+            const int y0 = (tile >> 1) ? sy : 0, y1 = (tile >> 1) ? H : sy;
+            const int x0 = (tile & 1) ? sx : 0, x1 = (tile & 1) ? W : sx;
+            const int w = x1 - x0;
+            const int64_t cnt = w > 0 && y1 > y0 ? (int64_t)(y1 - y0) * w : 0;
+            double n = 0.0, sa = 0.0, sb = 0.0, saa = 0.0, sbb = 0.0, sab = 0.0;
+            for (int64_t q = tid; q < cnt; q += nthreads) {
+                const int y = y0 + (int)(q / w), x = x0 + (int)(q % w);
+                const double a = ref[2 * ((int64_t)y * W + x)];
+                const double v = shifted[(b * H + y) * (int64_t)W + x];
+                n += 1.0;
+                sa += a;
+                sb += v;
+                saa += a * a;
+                sbb += v * v;
+                sab += a * v;
+            }
+            double* o = sm + (size_t)tid * 6;
+            o[0] = n;
+            o[1] = sa;
+            o[2] = sb;
+            o[3] = saa;
+            o[4] = sbb;
+            o[5] = sab;
+            return;
+        }
+        if (tid != 0)
+            return;
+        double t[6] = {0, 0, 0, 0, 0, 0};
+        for (int k = 0; k < nthreads; ++k)
+            for (int e = 0; e < 6; ++e)
+                t[e] += sm[(size_t)k * 6 + e];
+        for (int e = 0; e < 6; ++e)
+            out[item * 6 + e] = t[e];
+    }
+};
+
 // w_combined = w_init + w_cross (sequential_3d.py:117-121): float32 add of the frame's rigid offset
 // to every voxel of the shared initial field.  item = (b, voxel, component).
 struct CcRigidFlowK {

@@ -122,8 +122,11 @@ int64_t fr3d_device_bytes(const fr3d_ctx* ctx);
 
 /* Tuning knobs (do not change results). */
 typedef enum {
-    FR3D_OPT_SOR_CTAS_PER_SM = 1 /* resident CTAs per SM the persistent solver kernel may claim (0 = all it can
-                                  * get; 1 leaves room for a second stream's kernels on every SM) */
+    FR3D_OPT_SOR_CTAS_PER_SM = 1, /* resident CTAs per SM the persistent solver kernel may claim (0 = all it can
+                                   * get; 1 leaves room for a second stream's kernels on every SM) */
+    FR3D_OPT_CC_BLOCK_SCANS = 2   /* rigid pre-alignment: 1 = block-cooperative plane scans (arg-max, tile sums,
+                                   * plane mean: one CTA per plane) instead of one thread per plane (0, default until
+                                   * the block versions have been timed on a B200) */
 } fr3d_option;
 int fr3d_set_option(fr3d_ctx* ctx, int option, int64_t value);
 

@@ -141,3 +141,26 @@ def test_sequence_with_cc_initialization(backend):
         assert e.mean() <= 1e-4 and e.max() <= 5e-3, (t, e.mean(), e.max())
     with pytest.raises(ValueError):
         F.compensate_arr_3D(np.repeat(video, 2, -1), np.stack([ref, ref], -1), opts)
+
+
+def test_block_scan_option_gives_the_same_estimates(emu_backend):
+    """FR3D_OPT_CC_BLOCK_SCANS = 1 (block-cooperative arg-max / tile sums / plane mean; off by default until it has
+    been timed on a B200) changes no estimate.  Kernel-logic emulator only: the option is not yet exercised on a GPU."""
+    from flowreg3d_b200 import _lib, core, xcorr as PX
+    rng = np.random.default_rng(3)
+    shp = (20, 60, 70)
+    z, y, x = np.ogrid[:shp[0], :shp[1], :shp[2]]
+    ref = (rng.random(shp) * 0.5 + 5 * np.exp(-((z - 10) ** 2 + (y - 30) ** 2 + (x - 33) ** 2) / 120)).astype(np.float32)
+    mov = (ndi.shift(ref, shift=(1.5, -2.5, 3.75), order=1, mode="nearest")
+           + 0.05 * rng.standard_normal(shp)).astype(np.float32)
+    ctx = core.bare_context()
+    base = [PX.estimate_rigid_xcorr_3d(ref, mov, **kw) for kw in (dict(target_hw=(40, 48), up=10), dict(target_hw=None, up=1))]
+    core._check(ctx.h, ctx.lib.fr3d_set_option(ctx.h, _lib.OPT_CC_BLOCK_SCANS, 1))
+    try:
+        blk = [PX.estimate_rigid_xcorr_3d(ref, mov, **kw) for kw in (dict(target_hw=(40, 48), up=10), dict(target_hw=None, up=1))]
+    finally:
+        core._check(ctx.h, ctx.lib.fr3d_set_option(ctx.h, _lib.OPT_CC_BLOCK_SCANS, 0))
+    for a, b, kw in zip(base, blk, ("down-sampled", "integer")):
+        assert np.array_equal(a, b), (kw, a, b)
+        assert np.array_equal(a, OX.estimate_rigid_xcorr_3d(ref, mov, **(dict(target_hw=(40, 48), up=10)
+                                                                       if kw == "down-sampled" else dict(target_hw=None, up=1))))
