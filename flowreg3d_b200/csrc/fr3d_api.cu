@@ -336,7 +336,11 @@ static void launch_gather(fr3d_ctx* c, WarpGatherK g)
     const int tx = tile.tx, ty = tile.ty, tz = tile.tz;
     g.set_tile(tx, ty, tz);
     const int64_t n = g.items();
-    if (g.order == 3 && g.C == 2)
+    if (g.order == 3 && g.C == 2 && c->dev.warp_factored)
+        launch_occ<4>(c->dev, WarpGatherLeanK<2, 0, 1>{g}, n);
+    else if (g.order == 3 && g.C == 1 && c->dev.warp_factored)
+        launch_occ<4>(c->dev, WarpGatherLeanK<1, 0, 1>{g}, n);
+    else if (g.order == 3 && g.C == 2)
         launch_occ<4>(c->dev, WarpGatherLeanK<2, 0>{g}, n);
     else if (g.order == 3 && g.C == 1)
         launch_occ<4>(c->dev, WarpGatherLeanK<1, 0>{g}, n);
@@ -669,6 +673,10 @@ int fr3d_set_option(fr3d_ctx* ctx, int option, int64_t value)
     case FR3D_OPT_SOR_CTAS_PER_SM:
         FR3D_REQUIRE(value >= 0 && value <= 32, "FR3D_OPT_SOR_CTAS_PER_SM: %lld", (long long)value);
         _c->dev.sor_ctas_per_sm = (int)value;
+        break;
+    case FR3D_OPT_WARP_FACTORED:
+        FR3D_REQUIRE(value == 0 || value == 1, "FR3D_OPT_WARP_FACTORED: %lld", (long long)value);
+        _c->dev.warp_factored = (int)value;
         break;
     case FR3D_OPT_CC_BLOCK_SCANS:
         FR3D_REQUIRE(value == 0 || value == 1, "FR3D_OPT_CC_BLOCK_SCANS: %lld", (long long)value);

@@ -80,6 +80,7 @@ struct Device {
     int sm_count = 1;
     int sor_ctas_per_sm = 0; // 0 = as many as fit
     int cc_block_scans = 0;  // FR3D_OPT_CC_BLOCK_SCANS
+    int warp_factored = 0;   // FR3D_OPT_WARP_FACTORED
 
     // Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline
     // figures).  Off by default; when on, every launch is bracketed by two event records.
@@ -101,6 +102,15 @@ struct Device {
         }
         cudaEventCreate(&e);
         return e;
+    }
+#endif
+#ifdef FR3D_EMU
+    // kernel-logic emulator: no timing, but the profile report still lists WHICH functors ran (tests assert on it)
+    std::map<std::string, int64_t> emu_counts;
+    void emu_count(const char* name)
+    {
+        if (profiling)
+            emu_counts[name] += 1;
     }
 #endif
     void span_begin(const char* name)
@@ -138,6 +148,10 @@ struct Device {
             pool.push_back(s.b);
         }
         spans.clear();
+#else
+        for (auto& kv : emu_counts)
+            out[kv.first] = std::make_pair(kv.second, 0.0);
+        emu_counts.clear();
 #endif
         return out;
     }
@@ -282,6 +296,7 @@ void launch_occ(Device& dev, const K& k, int64_t n)
     if (n <= 0)
         return;
 #ifdef FR3D_EMU
+    dev.emu_count(typeid(K).name());
     for (int64_t i = 0; i < n; ++i)
         k(i);
 #else
@@ -302,6 +317,7 @@ void launch_occ2(Device& dev, const K& k, int64_t n)
     if (n <= 0)
         return;
 #ifdef FR3D_EMU
+    dev.emu_count(typeid(K).name());
     for (int64_t i = 0; i < n; ++i)
         k(i);
 #else
@@ -356,6 +372,7 @@ void launch(Device& dev, const K& k, int64_t n)
     if (n <= 0)
         return;
 #ifdef FR3D_EMU
+    dev.emu_count(typeid(K).name());
     for (int64_t i = 0; i < n; ++i)
         k(i);
 #else
@@ -478,6 +495,7 @@ void launch_tiles(Device& dev, const K& k, int64_t nblocks, int threads, size_t 
     if (nblocks <= 0)
         return;
 #ifdef FR3D_EMU
+    dev.emu_count(typeid(K).name());
     std::vector<double> smem(smem_bytes / sizeof(double) + 1);
     for (int64_t b = 0; b < nblocks; ++b)
         for (int ph = 0; ph < K::PHASES; ++ph)

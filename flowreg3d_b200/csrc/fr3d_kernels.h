@@ -957,7 +957,12 @@ struct WarpGatherK {
 // flight at the same occupancy) and the z-plane loop rolled (UNROLL_A == 0: 4*CH..16*CH loads live
 // instead of 64: fewer registers, more resident warps -- the kernel is latency-bound).  Same
 // reference lines, same arithmetic and tap order per channel as WarpGatherK, bit for bit.
-template <int CH, int UNROLL_A>
+// FACT == 1 (FR3D_OPT_WARP_FACTORED, off by default): the separable sum is factored,
+// sum_a wz (sum_b wy (sum_c wx c)), 21 fused multiply-adds per plane and channel instead of 64
+// float64 operations.  That changes the association of the 64-term sum: the float32 result differs
+// from scipy's in the last bit on a ~1e-7 fraction of the voxels -- inside every tolerance of the
+// path but not the bit-equality the default keeps.
+template <int CH, int UNROLL_A, int FACT = 0>
 struct WarpGatherLeanK {
     WarpGatherK g; // order == 3, g.C == CH
 
@@ -1048,18 +1053,34 @@ struct WarpGatherLeanK {
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc)
                     v[c][bb][cc] = p[c * cvol + bb * rowlen + cc];
+        if (FACT) {
 #pragma unroll
-        for (int bb = 0; bb < 4; ++bb)
+            for (int c = 0; c < CH; ++c) {
+                double s = 0.0;
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc)
+                for (int bb = 0; bb < 4; ++bb) {
+                    double r = v[c][bb][0] * wx[0];
 #pragma unroll
-                for (int c = 0; c < CH; ++c) {
-                    double q = v[c][bb][cc];
-                    q *= wza;
-                    q *= wy[bb];
-                    q *= wx[cc];
-                    t[c] += q;
+                    for (int cc = 1; cc < 4; ++cc)
+                        r = fma(v[c][bb][cc], wx[cc], r);
+                    s = fma(r, wy[bb], s);
                 }
+                t[c] = fma(s, wza, t[c]);
+            }
+        } else {
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb)
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) {
+                        double q = v[c][bb][cc];
+                        q *= wza;
+                        q *= wy[bb];
+                        q *= wx[cc];
+                        t[c] += q;
+                    }
+        }
     }
 };
 

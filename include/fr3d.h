@@ -120,10 +120,14 @@ int64_t fr3d_launch_count(const fr3d_ctx* ctx);
 /* bytes of device memory currently held by the context */
 int64_t fr3d_device_bytes(const fr3d_ctx* ctx);
 
-/* Tuning knobs (do not change results). */
+/* Tuning knobs (do not change results, except FR3D_OPT_WARP_FACTORED as documented). */
 typedef enum {
     FR3D_OPT_SOR_CTAS_PER_SM = 1, /* resident CTAs per SM the persistent solver kernel may claim (0 = all it can
                                    * get; 1 leaves room for a second stream's kernels on every SM) */
+    FR3D_OPT_WARP_FACTORED = 3,   /* cubic warps of 1-2 channels: 1 = factored separable sum (3x fewer float64
+                                   * operations; float32 results differ from scipy's association in the last bit on
+                                   * ~1e-7 of the voxels), 0 (default) = scipy's ((c*wz)*wy)*wx accumulate, bit-equal.
+                                   * THE ONE KNOB THAT CAN CHANGE RESULTS (by <= 1 float32 ulp). */
     FR3D_OPT_CC_BLOCK_SCANS = 2   /* rigid pre-alignment: 1 = block-cooperative plane scans (arg-max, tile sums,
                                    * plane mean: one CTA per plane) instead of one thread per plane (0, default until
                                    * the block versions have been timed on a B200) */

@@ -244,3 +244,35 @@ def test_preprocess_temporal_filter(backend, golden):
     spatial_only = O.preprocess(batch[:1], np.concatenate([sigma[:, :3], np.full((2, 1), 0.1)], 1), ref.astype(np.float64))
     assert np.array_equal(one, spatial_only.astype(np.float32))
     reg.ctx.close()
+
+
+def test_warp_factored_option_within_one_ulp(emu_backend):
+    """FR3D_OPT_WARP_FACTORED = 1 (off by default; the only knob that may change results): the factored separable sum
+    agrees with scipy's association to <= 1 float32 ulp on a vanishing fraction of the voxels; integer sources stay
+    exact.  Kernel-logic emulator only: the option has not been exercised on a GPU yet."""
+    import flowreg3d_b200 as F
+    from flowreg3d_b200 import _lib, core
+    from tests_inputs import smooth_flow
+    rng = np.random.default_rng(2)
+    shp = (9, 40, 64)
+    f2, f1 = rng.random(shp + (2,)), rng.random(shp + (2,))
+    g = smooth_flow(shp, 5, 3.0, 4.0).astype(np.float64)
+    raw = rng.integers(0, 60000, shp + (1,)).astype(np.uint16)
+    ctx = core.bare_context()
+    base = F.imregister_wrapper(f2, g[..., 0], g[..., 1], g[..., 2], f1, "cubic")
+    core._check(ctx.h, ctx.lib.fr3d_set_option(ctx.h, _lib.OPT_WARP_FACTORED, 1))
+    ctx.profile(True)
+    try:
+        fact = F.imregister_wrapper(f2, g[..., 0], g[..., 1], g[..., 2], f1, "cubic")
+        ran = list(ctx.profile_report())
+        assert any("WarpGatherLeanK" in k and ("Li1EEE" in k or "0, 1>" in k) for k in ran), ran   # the factored functor
+        fraw = F.imregister_wrapper(raw, g[..., 0].astype(np.float32), g[..., 1].astype(np.float32),
+                                    g[..., 2].astype(np.float32), raw, "cubic")
+    finally:
+        core._check(ctx.h, ctx.lib.fr3d_set_option(ctx.h, _lib.OPT_WARP_FACTORED, 0))
+        ctx.profile(False)
+    d = ulp_diff(fact, base)
+    assert d.max() <= 1 and (d > 0).mean() <= 1e-4, (d.max(), (d > 0).mean())
+    assert np.array_equal(fraw, O.imregister_wrapper(raw, g[..., 0].astype(np.float32), g[..., 1].astype(np.float32),
+                                                     g[..., 2].astype(np.float32), raw, "cubic"))
+    assert np.array_equal(F.imregister_wrapper(f2, g[..., 0], g[..., 1], g[..., 2], f1, "cubic"), base)  # off again

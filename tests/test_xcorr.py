@@ -156,10 +156,15 @@ def test_block_scan_option_gives_the_same_estimates(emu_backend):
     ctx = core.bare_context()
     base = [PX.estimate_rigid_xcorr_3d(ref, mov, **kw) for kw in (dict(target_hw=(40, 48), up=10), dict(target_hw=None, up=1))]
     core._check(ctx.h, ctx.lib.fr3d_set_option(ctx.h, _lib.OPT_CC_BLOCK_SCANS, 1))
+    ctx.profile(True)
     try:
         blk = [PX.estimate_rigid_xcorr_3d(ref, mov, **kw) for kw in (dict(target_hw=(40, 48), up=10), dict(target_hw=None, up=1))]
+        ran = list(ctx.profile_report())
+        for name in ("CcAbsArgmaxTileK", "CcTileSumsTileK", "CcPlaneMeanTileK"):
+            assert any(name in k for k in ran), (name, ran)
     finally:
         core._check(ctx.h, ctx.lib.fr3d_set_option(ctx.h, _lib.OPT_CC_BLOCK_SCANS, 0))
+        ctx.profile(False)
     for a, b, kw in zip(base, blk, ("down-sampled", "integer")):
         assert np.array_equal(a, b), (kw, a, b)
         assert np.array_equal(a, OX.estimate_rigid_xcorr_3d(ref, mov, **(dict(target_hw=(40, 48), up=10)
