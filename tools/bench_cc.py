@@ -1,5 +1,5 @@
 """Cost of the rigid cross-correlation pre-alignment: one batch of single-channel 32x512x512 frames through
-SequenceCorrector.process_batch with and without OFOptions.cc_initialization.   python tools/bench_cc.py [B]"""
+SequenceCorrector.process_batch with and without OFOptions.cc_initialization.   python tools/bench_cc.py [B] [--block-scans]"""
 import sys
 import time
 from pathlib import Path
@@ -12,7 +12,9 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 import flowreg3d_b200 as F  # noqa: E402
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+BLOCK_SCANS = "--block-scans" in sys.argv      # FR3D_OPT_CC_BLOCK_SCANS (not yet timed on a B200)
+B = int(args[0]) if args else 10
 shape = (32, 512, 512)
 rng = np.random.default_rng(0)
 z, y, x = np.ogrid[:shape[0], :shape[1], :shape[2]]
@@ -21,6 +23,9 @@ frames = np.stack([np.roll(ref, (b % 3, 2 * b + 1, -b - 2), (0, 1, 2)) for b in 
 dev_frames = torch.from_numpy(frames).cuda()
 for cc in (False, True):
     seq = F.SequenceCorrector(ref, F.OFOptions(buffer_size=B, cc_initialization=cc), max_batch=B)
+    if BLOCK_SCANS:
+        from flowreg3d_b200 import _lib, core
+        core._check(seq.reg.ctx.h, seq.reg.ctx.lib.fr3d_set_option(seq.reg.ctx.h, _lib.OPT_CC_BLOCK_SCANS, 1))
     seq.process_batch(dev_frames)          # bootstrap + first batch (tables, spectra of the reference)
     seq.reg.sync()
     seq.reg.ctx.profile(True)

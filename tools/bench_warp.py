@@ -1,4 +1,4 @@
-"""Kernel times of the compensation warp alone (config 2 frames, B = 16): python tools/bench_warp.py"""
+"""Kernel times of the compensation warp alone (config 2 frames, B = 16): python tools/bench_warp.py [--factored]"""
 import sys
 from pathlib import Path
 
@@ -19,6 +19,9 @@ gen = torch.Generator(device="cuda").manual_seed(0)
 flow = (torch.rand((B,) + shape + (3,), device="cuda", generator=gen) * 0.1 +
         torch.linspace(-2, 2, shape[2], device="cuda")[None, None, None, :, None]).float().contiguous()
 refd = torch.from_numpy(ref).cuda()
+if "--factored" in sys.argv:   # FR3D_OPT_WARP_FACTORED (<= 1 float32 ulp from the default; not yet timed on a B200)
+    from flowreg3d_b200 import _lib, core
+    core._check(reg.ctx.h, reg.ctx.lib.fr3d_set_option(reg.ctx.h, _lib.OPT_WARP_FACTORED, 1))
 for _ in range(2):
     reg.compensate(frames, flow, ref_raw=refd)
 reg.sync()
