@@ -169,3 +169,21 @@ def test_block_scan_option_gives_the_same_estimates(emu_backend):
         assert np.array_equal(a, b), (kw, a, b)
         assert np.array_equal(a, OX.estimate_rigid_xcorr_3d(ref, mov, **(dict(target_hw=(40, 48), up=10)
                                                                        if kw == "down-sampled" else dict(target_hw=None, up=1))))
+
+
+def test_estimate_edge_cases_equal_oracle(emu_backend):
+    """Odd / small / wide volumes, zero shift (empty disambiguation tiles), shifts beyond half the projection (wrap
+    candidates), targets larger than the volume (no resize), coarse targets, z down-sampling, integer estimates."""
+    from flowreg3d_b200 import xcorr as PX
+    rng = np.random.default_rng(1)
+    for shp in [(7, 33, 41), (16, 64, 64), (5, 20, 130)]:
+        z, y, x = np.ogrid[:shp[0], :shp[1], :shp[2]]
+        ref = (rng.random(shp) * 0.5 + 3 * np.exp(-((z - shp[0] / 2) ** 2 + (y - shp[1] / 2) ** 2
+                                                    + (x - shp[2] / 2) ** 2) / 60)).astype(np.float32)
+        for d in [(0, 0, 0), (1, 0, 0), (-7.5, 3.25, 1.0), (12.0, -9.0, 2.0)]:
+            mov = ndi.shift(ref, shift=(d[2], d[1], d[0]), order=1, mode="nearest").astype(np.float32)
+            for kw in (dict(target_hw=(256, 256), up=10), dict(target_hw=(16, 24), up=4),
+                       dict(target_hw=None, up=1, target_z=4)):
+                eo = OX.estimate_rigid_xcorr_3d(ref, mov, **kw)
+                ep = PX.estimate_rigid_xcorr_3d(ref, mov, **kw)
+                assert np.array_equal(eo, ep), (shp, d, kw, eo, ep)
