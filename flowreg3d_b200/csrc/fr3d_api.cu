@@ -461,9 +461,13 @@ static void sor_prepare(fr3d_ctx* c, int state_dtype, const HPGeom& hp, int B, i
 
 // Run sweeps [t0,t1) x waves [q0,q1) of the prepared solve (negative bounds: the whole range).
 template <class ST>
-static void sor_launch_t(fr3d_ctx* c, int t0, int t1, int q0, int q1)
+static void sor_launch_t(fr3d_ctx* c, int t0, int t1, int q0, int q1, int k0 = 0, int k1 = 0)
 {
     SorParams<ST> P = sor_params<ST>(c);
+    if (k1 > 0) {
+        FR3D_REQUIRE(!P.redblack && P.a_smooth == 1.0, "z-slab sweeps need the lexicographic sweep with a_smooth == 1");
+        FR3D_REQUIRE(k0 >= 0 && k0 < k1 && k1 <= P.g.p, "bad plane range [%d, %d) of %d", k0, k1, P.g.p);
+    }
     const int nw = sor_num_waves(P);
     const bool partial = !(t0 <= 0 && (t1 < 0 || t1 >= P.T) && q0 <= 0 && (q1 < 0 || q1 >= nw));
     if (partial) {
@@ -478,16 +482,25 @@ static void sor_launch_t(fr3d_ctx* c, int t0, int t1, int q0, int q1)
         if (q0 == q1)
             return;
     }
-    sor_run(c->dev, P, c->bar.ensure(c->dev, 4), c->sp_hp->pe_host.data());
+    c->dev.sor_k0 = k0;
+    c->dev.sor_k1 = k1 > 0 ? k1 : 0;
+    try {
+        sor_run(c->dev, P, c->bar.ensure(c->dev, 4), c->sp_hp->pe_host.data());
+    } catch (...) {
+        c->dev.sor_k0 = c->dev.sor_k1 = 0;
+        throw;
+    }
+    c->dev.sor_k0 = c->dev.sor_k1 = 0;
 }
 
-static void sor_launch(fr3d_ctx* c, int state_dtype, int t0 = -1, int t1 = -1, int q0 = -1, int q1 = -1)
+static void sor_launch(fr3d_ctx* c, int state_dtype, int t0 = -1, int t1 = -1, int q0 = -1, int q1 = -1, int k0 = 0,
+                       int k1 = 0)
 {
     FR3D_REQUIRE(c->sp_hp != nullptr, "no level solve has been prepared");
     if (state_dtype == FR3D_F64)
-        sor_launch_t<double>(c, t0, t1, q0, q1);
+        sor_launch_t<double>(c, t0, t1, q0, q1, k0, k1);
     else
-        sor_launch_t<float>(c, t0, t1, q0, q1);
+        sor_launch_t<float>(c, t0, t1, q0, q1, k0, k1);
 }
 
 static void run_sor(fr3d_ctx* c, int state_dtype, const HPGeom& hp, int B, int C, const float* f1, const float* f2,
@@ -1041,6 +1054,30 @@ int fr3d_level_sweeps(fr3d_ctx* ctx, int level, int t_begin, int t_end, int q_be
     FR3D_API_BEGIN(ctx)
     FR3D_REQUIRE(_c->run_level == level, "level %d is not open", level);
     sor_launch(_c, _c->state_dtype, t_begin, t_end, q_begin, q_end);
+    FR3D_API_END()
+}
+
+int fr3d_level_sweeps_slab(fr3d_ctx* ctx, int level, int q_begin, int q_end, int k_begin, int k_end)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(_c->run_level == level, "level %d is not open", level);
+    FR3D_REQUIRE(k_end > 0, "empty plane range");
+    sor_launch(_c, _c->state_dtype, 0, _c->iterations, q_begin, q_end, k_begin, k_end);
+    FR3D_API_END()
+}
+
+int fr3d_level_planes(fr3d_ctx* ctx, int level, int direction, void* ext, int k_begin, int k_end)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(_c->run_level == level, "level %d is not open", level);
+    FR3D_REQUIRE(ext && (direction == 0 || direction == 1), "bad argument");
+    const HPGeom& hp = _c->levels[level]->hp;
+    FR3D_REQUIRE(k_begin >= 0 && k_begin < k_end && k_end <= hp.p, "bad plane range");
+    const int64_t n = (int64_t)_c->run_B * (k_end - k_begin) * hp.m * hp.n;
+    if (_c->state_dtype == FR3D_F64)
+        launch(_c->dev, SlabPlanesK<double>{(Vec4<double>*)_c->d.p, (Vec4<double>*)ext, hp.view(), k_begin, k_end, direction}, n);
+    else
+        launch(_c->dev, SlabPlanesK<float>{(Vec4<float>*)_c->d.p, (Vec4<float>*)ext, hp.view(), k_begin, k_end, direction}, n);
     FR3D_API_END()
 }
 

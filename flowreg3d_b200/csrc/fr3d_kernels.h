@@ -1353,6 +1353,30 @@ struct FromHPK {
     }
 };
 
+// Planes [k0, k1) of the increments in solver storage <-> a dense buffer (B, k1-k0, m, n) of 4-vectors
+// (dir 0: out of the state, 1: into it): the halo / slab exchange of the z-slab multi-GPU solve.
+// item = (b, k - k0, j, i)
+template <class ST>
+struct SlabPlanesK {
+    Vec4<ST>* d;
+    Vec4<ST>* ext;
+    HPView hp;
+    int k0, k1, dir;
+    FR3D_HD void operator()(int64_t item) const
+    {
+        const int i = (int)(item % hp.n);
+        const int j = (int)((item / hp.n) % hp.m);
+        const int64_t r = item / ((int64_t)hp.n * hp.m);
+        const int k = k0 + (int)(r % (k1 - k0));
+        const int64_t b = r / (k1 - k0);
+        Vec4<ST>* slot = d + b * hp.npad + hp.addr(k, j, i);
+        if (dir == 0)
+            ext[item] = *slot;
+        else
+            *slot = ext[item];
+    }
+};
+
 // ------------------------------------------------------------------------------------------
 // 5x5x5 median, scipy.ndimage.median_filter(mode="mirror") (core/optical_flow_3d.py:517-526).
 // Exact order statistic of float64 data through float32 keys: rounding to float32 is monotone,

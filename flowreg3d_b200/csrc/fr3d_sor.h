@@ -301,11 +301,18 @@ FR3D_HD void sor_load(const SorParams<ST>& P, const SorLoc& L, int b, bool with_
 }
 
 // Update the lane's voxel in every frame of the item.
-template <class ST, int C>
-FR3D_HD void sor_process(const SorParams<ST>& P, const SorLoc& L)
+// SLAB (z-slab multi-GPU solve): only voxels of the planes kb <= k < ke are updated.  It is a separate
+// instantiation (and the plane range travels outside SorParams) so that the full solve's kernel is untouched.
+template <class ST, int C, bool SLAB = false>
+FR3D_HD void sor_process(const SorParams<ST>& P, const SorLoc& L, int kb = 0, int ke = 0)
 {
     if (L.n0 < 0)
         return; // pad slot
+    if (SLAB) {
+        const int k = P.g.perm[L.a] / (P.g.m * P.g.n); // perm = natural index (k*m + j)*n + i
+        if (k < kb || k >= ke)
+            return; // another rank's plane
+    }
     const int64_t np = P.g.npad;
     const int64_t a = L.a;
     if (L.refresh) {
@@ -617,10 +624,14 @@ __device__ __forceinline__ void fr3d_grid_barrier(unsigned* ctr, unsigned target
 // Persistent cooperative kernel: all waves of one level solve, one grid barrier per wave.
 // Dynamic shared memory: copies of the pe / start tables (tabs_in_smem) so that locating an item
 // costs shared-memory latency only.
-template <class ST, int C>
+template <class ST, int C, bool SLAB = false>
 __global__ void __launch_bounds__(FR3D_SOR_THREADS, SorTune<ST>::kMinBlocks)
 fr3d_sor_wavefront(const SorParams<ST> P, unsigned* bar, int tabs_in_smem)
 {
+    // SLAB: the plane range rides in the upper bits of the flag word (tabs | k_begin << 1 | k_end << 16)
+    const int kb = SLAB ? ((tabs_in_smem >> 1) & 0x7fff) : 0, ke = SLAB ? (tabs_in_smem >> 16) : 0;
+    if (SLAB)
+        tabs_in_smem &= 1;
     extern __shared__ int32_t fr3d_sor_smem[];
     SorTabs tb{P.g.pe, P.g.start};
     if (tabs_in_smem) {
@@ -648,7 +659,7 @@ fr3d_sor_wavefront(const SorParams<ST> P, unsigned* bar, int tabs_in_smem)
                 SorLoc nxt;
                 if (more)
                     nxt = sor_locate(P, tb, q, w, next, lane); // neighbour-table loads fly during the update below
-                sor_process<ST, C>(P, cur);
+                sor_process<ST, C, SLAB>(P, cur, kb, ke);
                 if (!more)
                     break;
                 cur = nxt;
@@ -711,8 +722,11 @@ inline void sor_run_c(Device& dev, const SorParams<ST>& P, unsigned* bar, int pe
     const size_t smem = (size_t)(2 * P.g.S + 1) * sizeof(int32_t);
     const int tabs_in_smem = smem <= 40 * 1024;
     const size_t dyn = tabs_in_smem ? smem : 0;
+    const bool slab = dev.sor_k1 > 0;
+    FR3D_REQUIRE(!slab || dev.sor_k1 < 32768, "z-slab solve: more than 32767 planes");
+    const void* kern = slab ? (const void*)fr3d_sor_wavefront<ST, C, true> : (const void*)fr3d_sor_wavefront<ST, C>;
     int per_sm = 0;
-    FR3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fr3d_sor_wavefront<ST, C>,
+    FR3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern,
                                                             FR3D_SOR_THREADS, dyn));
     FR3D_REQUIRE(per_sm >= 1, "SOR kernel does not fit on an SM");
     if (dev.sor_ctas_per_sm > 0 && per_sm > dev.sor_ctas_per_sm)
@@ -725,10 +739,10 @@ inline void sor_run_c(Device& dev, const SorParams<ST>& P, unsigned* bar, int pe
         grid = (int)(want < 1 ? 1 : want);
     FR3D_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), dev.stream));
     SorParams<ST> Pc = P;
-    int tis = tabs_in_smem;
+    int tis = tabs_in_smem | (slab ? ((dev.sor_k0 << 1) | (dev.sor_k1 << 16)) : 0);
     void* args[] = {(void*)&Pc, (void*)&bar, (void*)&tis};
     dev.span_begin("fr3d_sor_wavefront");
-    FR3D_CUDA(cudaLaunchCooperativeKernel((void*)fr3d_sor_wavefront<ST, C>, dim3(grid), dim3(FR3D_SOR_THREADS),
+    FR3D_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(FR3D_SOR_THREADS),
                                           args, dyn, dev.stream));
     dev.span_end();
     dev.launches++;

@@ -211,3 +211,99 @@ def _split(n: int, world: int, rank: int) -> Tuple[int, int]:
 
 def _global_rank(group, r: int) -> int:
     return r if group is None else dist.get_global_rank(group, r)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# z-slab decomposition with halo exchange (the decomposition SURVEY.md 8(e) / the north star names).
+# ------------------------------------------------------------------------------------------------------------------
+def get_displacement_zslab(reg: Registration, moving_proc, uvw=None, group=None, out_dtype=np.float32,
+                           min_slots: int = 1 << 21, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """get_displacement for B frames with every large level solved on z-slabs: rank r owns the planes
+    [z_r, z_{r+1}) of the level and runs, wave by wave, the sweeps of its planes only
+    (`fr3d_level_sweeps_slab`).  A voxel of wave q = (k+j+i) + 2t reads nothing newer than wave q-1, so after every
+    wave the ranks trade the two boundary planes they own with their z-neighbours (`fr3d_level_planes`,
+    send/recv over NCCL; gloo in the CPU tests) -- S + 2(T-1) exchanges per level, both directions.  At the end of
+    the level the slabs are gathered, the 5^3 median runs on the same z-slabs and the flow slabs are exchanged as in
+    the sweep-pipelined solve.  The update order is the reference's: the result is bit-identical to one GPU.
+
+    This is the straightforward version (whole boundary planes per wave, one kernel launch per wave); it exists for
+    levels whose state does not fit one GPU and as the baseline for a fused exchange.  For volumes that do fit,
+    `get_displacement_pipelined` needs ~8 messages per level instead of ~2 400 and is the faster choice today
+    (DESIGN.md section 6).  Every rank must call with identical arguments; every rank returns the full result."""
+    lib, h = reg.ctx.lib, reg.ctx.h
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    mv = reg._as_dev(moving_proc, np.float32, None)
+    if mv.dim() == 4:
+        mv = mv[None]
+    B = mv.shape[0]
+    uv = None if uvw is None else reg._as_dev(uvw, np.float32, reg.shape + (3,))
+    if out is None:
+        out = dev.empty((B,) + reg.shape + (3,), out_dtype, reg.device)
+    T = int(reg.plan.plan.iterations)
+    state_dt = np.float64 if reg.plan.plan.state_dtype == _lib.F64 else np.float32
+    slabbable = reg.plan.plan.sweep == 0 and float(reg.plan.plan.a_smooth) == 1.0
+    nl = lib.fr3d_level_count(h)
+    keep = []
+    for li in range(nl):
+        _check(h, lib.fr3d_level_begin(h, li, dev.ptr(mv), dev.ptr(uv), B))
+        (pz, py, px), S, nslots, _ = _level_info(reg, li)
+        if world == 1 or not slabbable or pz < world or nslots * B < min_slots:
+            _check(h, lib.fr3d_level_sweeps(h, li, -1, -1, -1, -1))      # redundant on every rank, no exchange
+            _check(h, lib.fr3d_level_end(h, li))
+            continue
+        bounds = [_split(pz, world, r) for r in range(world)]
+        z0, z1 = bounds[rank]
+        plane = py * px
+
+        def planes_out(k0, k1):
+            buf = dev.empty((B, (k1 - k0) * plane, 4), state_dt, reg.device)
+            _check(h, lib.fr3d_level_planes(h, li, 0, dev.ptr(buf), k0, k1))
+            reg.sync()                                       # the buffer leaves through torch.distributed
+            return buf
+
+        def planes_in(buf, k0, k1):
+            _check(h, lib.fr3d_level_planes(h, li, 1, dev.ptr(buf), k0, k1))
+
+        lo = _global_rank(group, rank - 1) if rank > 0 else None
+        hi = _global_rank(group, rank + 1) if rank + 1 < world else None
+        for q in range(S + 2 * (T - 1)):
+            _check(h, lib.fr3d_level_sweeps_slab(h, li, q, q + 1, z0, z1))
+            ops, recvs = [], []
+            if lo is not None:
+                sb = planes_out(z0, z0 + 1)
+                rb = dev.empty((B, plane, 4), state_dt, reg.device)
+                ops += [dist.P2POp(dist.isend, sb, lo, group), dist.P2POp(dist.irecv, rb, lo, group)]
+                recvs.append((rb, z0 - 1))
+                keep.append(sb)
+            if hi is not None:
+                sb = planes_out(z1 - 1, z1)
+                rb = dev.empty((B, plane, 4), state_dt, reg.device)
+                ops += [dist.P2POp(dist.isend, sb, hi, group), dist.P2POp(dist.irecv, rb, hi, group)]
+                recvs.append((rb, z1))
+                keep.append(sb)
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            for rb, k in recvs:
+                planes_in(rb, k, k + 1)
+            keep = keep[-8:]
+        # gather the slabs of the finished increments: every rank needs them around its planes for the median
+        for r, (a, b) in enumerate(bounds):
+            buf = planes_out(a, b) if r == rank else dev.empty((B, (b - a) * plane, 4), state_dt, reg.device)
+            dist.broadcast(buf, src=_global_rank(group, r), group=group)
+            if r != rank:
+                planes_in(buf, a, b)
+            keep.append(buf)
+        _check(h, lib.fr3d_level_end_range(h, li, z0, z1))
+        for r, (a, b) in enumerate(bounds):
+            slab = dev.empty((B, 3, b - a, py, px), np.float64, reg.device)
+            if r == rank:
+                _check(h, lib.fr3d_flow_slab(h, li, 0, dev.ptr(slab), a, b))
+                reg.sync()
+            dist.broadcast(slab, src=_global_rank(group, r), group=group)
+            if r != rank:
+                _check(h, lib.fr3d_flow_slab(h, li, 1, dev.ptr(slab), a, b))
+            keep.append(slab)
+    _check(h, lib.fr3d_flow_finish(h, dev.ptr(out), reg._code(out)))
+    reg._keep = [mv, uv, keep]
+    return out

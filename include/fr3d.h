@@ -187,6 +187,13 @@ int fr3d_level_begin(fr3d_ctx* ctx, int level, const float* moving_proc, const f
 int fr3d_level_sweeps(fr3d_ctx* ctx, int level, int t_begin, int t_end, int q_begin, int q_end);
 int fr3d_level_state(fr3d_ctx* ctx, int level, int direction, void* ext, int64_t slot_begin,
                      int64_t slot_end);
+/* z-slab variant of the seam (flowreg3d_b200/multigpu.py, mode "zslab"): rank r owns the planes [k_begin, k_end)
+ * of the level.  fr3d_level_sweeps_slab runs the waves [q_begin, q_end) of ALL sweeps restricted to those planes
+ * (a voxel of wave q reads nothing newer than wave q-1, so the ranks exchange, after every wave, the boundary planes
+ * they own); fr3d_level_planes copies whole planes of the increments out of (direction 0) or into (1) `ext`
+ * (device, B x (k_end-k_begin) x py x px 4-vectors {du,dv,dw,-} of the state dtype). */
+int fr3d_level_sweeps_slab(fr3d_ctx* ctx, int level, int q_begin, int q_end, int k_begin, int k_end);
+int fr3d_level_planes(fr3d_ctx* ctx, int level, int direction, void* ext, int k_begin, int k_end);
 int fr3d_level_end(fr3d_ctx* ctx, int level);
 /* fr3d_level_end restricted to the planes z_begin <= z < z_end of the level's flow (the median of a plane needs
  * the increments of two planes on either side, which every rank holds); the other planes of the flow are then

@@ -72,7 +72,7 @@ def test_two_rank_sharding_matches_single_process(emu_backend, tmp_path, cc):
     assert len(np.load(tmp_path / "r0.npz")["idx"]) == 4 and len(np.load(tmp_path / "r1.npz")["idx"]) == 3
 
 
-def _pipeline_worker(rank, world, port, emu_path, tmp):
+def _pipeline_worker(rank, world, port, emu_path, tmp, zslab=False):
     os.environ["FR3D_LIBRARY_OVERRIDE"] = emu_path
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -90,7 +90,11 @@ def _pipeline_worker(rank, world, port, emu_path, tmp):
     reg = F.Registration(fixed.shape[:3], fixed.shape[3], fp, max_batch=2)
     reg.set_reference(fixed)
     mv = np.stack([moving, np.roll(moving, 1, 2)], 0)
-    flow = get_displacement_pipelined(reg, mv, min_slots=0, n_chunks=5)      # pipeline every level
+    if zslab:
+        from flowreg3d_b200.multigpu import get_displacement_zslab
+        flow = get_displacement_zslab(reg, mv, min_slots=0)                  # z-slabs + halo exchange on every level
+    else:
+        flow = get_displacement_pipelined(reg, mv, min_slots=0, n_chunks=5)  # pipeline every level
     reg.sync()
     np.save(os.path.join(tmp, f"p{rank}.npy"), dev.to_host(flow))
     dist.barrier()
@@ -129,6 +133,28 @@ def test_sweep_pipelined_solve_is_bit_identical(emu_backend, tmp_path, world):
             assert [s[0] for s in st if s[0]] == [s[3] for s in sched[active[i - 1]] if s[3]]
     emu = str(build())
     mp.spawn(_pipeline_worker, args=(world, _free_port(), emu, str(tmp_path)), nprocs=world, join=True)
+    g = np.load(ROOT / "tests" / "golden" / "flow_small.npz")
+    fixed, moving = g["fixed"][:16, :28, :32].astype(np.float32), g["moving"][:16, :28, :32].astype(np.float32)
+    fp = F.FlowParams(alpha=(0.25, 0.3, 0.2), update_lag=3, iterations=14, min_level=0, levels=100, eta=0.8,
+                      a_smooth=1.0, a_data=0.45)
+    reg = F.Registration(fixed.shape[:3], fixed.shape[3], fp, max_batch=2)
+    reg.set_reference(fixed)
+    ref = dev.to_host(reg.get_displacement(np.stack([moving, np.roll(moving, 1, 2)], 0)))
+    for rank in range(world):
+        assert np.array_equal(np.load(tmp_path / f"p{rank}.npy"), ref), rank
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_zslab_solve_with_halo_exchange_is_bit_identical(emu_backend, tmp_path, world):
+    """One volume on several ranks, z-slab decomposition: every rank sweeps its own planes wave by wave and trades
+    its boundary planes with both z-neighbours after every wave (S + 2(T-1) exchanges per level).  Same update order
+    as one process -> bit-identical flows on every rank (16 planes over 3 ranks gives uneven slabs 6/5/5; the
+    coarsest levels have fewer planes than ranks on some configurations and are then solved redundantly)."""
+    from emu.build_emu import build
+    import flowreg3d_b200 as F
+    from flowreg3d_b200 import device as dev
+    emu = str(build())
+    mp.spawn(_pipeline_worker, args=(world, _free_port(), emu, str(tmp_path), True), nprocs=world, join=True)
     g = np.load(ROOT / "tests" / "golden" / "flow_small.npz")
     fixed, moving = g["fixed"][:16, :28, :32].astype(np.float32), g["moving"][:16, :28, :32].astype(np.float32)
     fp = F.FlowParams(alpha=(0.25, 0.3, 0.2), update_lag=3, iterations=14, min_level=0, levels=100, eta=0.8,
