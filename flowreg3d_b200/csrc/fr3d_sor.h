@@ -582,8 +582,12 @@ inline void sor_run_c(Device& dev, const SorParams<ST>& P, unsigned*)
     for (int q = P.q_begin; q < P.q_end; ++q) {
         const SorWave w = sor_wave(P, tb, q);
         for (int item = 0; item < w.items; ++item)
-            for (int lane = 0; lane < 32; ++lane)
-                sor_process<ST, C>(P, sor_locate(P, tb, q, w, item, lane));
+            for (int lane = 0; lane < 32; ++lane) {
+                if (dev.sor_k1 > 0)
+                    sor_process<ST, C, true>(P, sor_locate(P, tb, q, w, item, lane), dev.sor_k0, dev.sor_k1);
+                else
+                    sor_process<ST, C>(P, sor_locate(P, tb, q, w, item, lane));
+            }
     }
     dev.launches++;
 }

@@ -1,4 +1,5 @@
-"""Single large volume on several GPUs: the sweep-pipelined level solve.
+"""Single large volume on several GPUs: the sweep-pipelined level solve (get_displacement_pipelined) and the
+z-slab decomposition with halo exchange (get_displacement_zslab, at the end of the file).
 
 Frames of a recording shard trivially (compensate.py).  ONE volume that is too slow on one GPU does
 not: the reference's solver is a lexicographic Gauss-Seidel sweep, so a z-slab decomposition has to

@@ -276,3 +276,63 @@ def test_warp_factored_option_within_one_ulp(emu_backend):
     assert np.array_equal(fraw, O.imregister_wrapper(raw, g[..., 0].astype(np.float32), g[..., 1].astype(np.float32),
                                                      g[..., 2].astype(np.float32), raw, "cubic"))
     assert np.array_equal(F.imregister_wrapper(f2, g[..., 0], g[..., 1], g[..., 2], f1, "cubic"), base)  # off again
+
+
+def test_slab_restricted_sweeps(emu_backend, golden):
+    """fr3d_level_sweeps_slab (the z-slab multi-GPU seam): a call updates the voxels of its planes only, and running
+    every wave slab by slab reproduces the full solve bit for bit -- within a wave no voxel reads a value written in
+    that wave, so the slabs of one wave commute.  (The 2-/3-rank gloo tests cannot see a mask that lets everything
+    through: redundant work gives the same answer.  Kernel-logic emulator only; the plane range reaches the CUDA
+    kernel through its flag word, which no GPU run has exercised yet.)"""
+    import flowreg3d_b200 as F
+    from flowreg3d_b200 import device as dev
+    from flowreg3d_b200.core import _check
+    from flowreg3d_b200.multigpu import _level_info
+    g = golden("flow_small")
+    fixed, moving = g["fixed"][:9, :15, :17].astype(np.float32), g["moving"][:9, :15, :17].astype(np.float32)
+    T = 7
+    fp = F.FlowParams(alpha=(0.25, 0.3, 0.2), update_lag=3, iterations=T, min_level=0, levels=100, eta=0.8,
+                      a_smooth=1.0, a_data=0.45)
+    reg = F.Registration(fixed.shape[:3], fixed.shape[3], fp, max_batch=2)
+    reg.set_reference(fixed)
+    mv = np.stack([moving, np.roll(moving, 1, 2)], 0)
+    ref = dev.to_host(reg.get_displacement(mv))
+    lib, h = reg.ctx.lib, reg.ctx.h
+    mvd = reg._as_dev(mv, np.float32, None)
+    B = 2
+    out = dev.empty((B,) + reg.shape + (3,), np.float32, reg.device)
+    checked_mask = False
+    for li in range(lib.fr3d_level_count(h)):
+        _check(h, lib.fr3d_level_begin(h, li, dev.ptr(mvd), None, B))
+        (pz, py, px), S, _, _ = _level_info(reg, li)
+        cuts = [0, max(1, pz // 3), max(2, (2 * pz) // 3), pz] if pz >= 3 else [0, pz]
+        for q in range(S + 2 * (T - 1)):
+            for a, b in zip(cuts, cuts[1:]):
+                if b > a:
+                    _check(h, lib.fr3d_level_sweeps_slab(h, li, q, q + 1, a, b))
+                if q == 0 and a == 0 and pz >= 3 and not checked_mask:
+                    # after the first slab's wave 0 only plane 0 .. cuts[1]-1 may be non-zero
+                    buf = dev.empty((B, pz * py * px, 4), np.float64, reg.device)
+                    _check(h, lib.fr3d_level_planes(h, li, 0, dev.ptr(buf), 0, pz))
+                    reg.sync()
+                    st = dev.to_host(buf).reshape(B, pz, py, px, 4)
+                    assert np.abs(st[:, 0, 0, 0, :3]).sum() > 0 and not np.abs(st[:, cuts[1]:]).any()
+                    checked_mask = True
+        _check(h, lib.fr3d_level_end(h, li))
+    _check(h, lib.fr3d_flow_finish(h, dev.ptr(out), reg._code(out)))
+    reg.sync()
+    assert checked_mask and np.array_equal(dev.to_host(out), ref)
+    # a later slab alone must not touch the first plane
+    _check(h, lib.fr3d_level_begin(h, 0, dev.ptr(mvd), None, B))
+    (pz, py, px), S, _, _ = _level_info(reg, 0)
+    _check(h, lib.fr3d_level_sweeps_slab(h, 0, 0, 1, pz // 2, pz))
+    buf = dev.empty((B, pz * py * px, 4), np.float64, reg.device)
+    _check(h, lib.fr3d_level_planes(h, 0, 0, dev.ptr(buf), 0, pz))
+    reg.sync()
+    assert not np.abs(dev.to_host(buf)).any()        # wave 0 is voxel (0,0,0): not in [pz/2, pz)
+    _check(h, lib.fr3d_level_sweeps(h, 0, -1, -1, -1, -1))
+    _check(h, lib.fr3d_level_end(h, 0))
+    for li in range(1, lib.fr3d_level_count(h)):
+        _check(h, lib.fr3d_level_begin(h, li, dev.ptr(mvd), None, B))
+        _check(h, lib.fr3d_level_sweeps(h, li, -1, -1, -1, -1))
+        _check(h, lib.fr3d_level_end(h, li))
