@@ -728,10 +728,13 @@ inline void sor_run_c(Device& dev, const SorParams<ST>& P, unsigned* bar, int pe
     const size_t dyn = tabs_in_smem ? smem : 0;
     const bool slab = dev.sor_k1 > 0;
     FR3D_REQUIRE(!slab || dev.sor_k1 < 32768, "z-slab solve: more than 32767 planes");
-    const void* kern = slab ? (const void*)fr3d_sor_wavefront<ST, C, true> : (const void*)fr3d_sor_wavefront<ST, C>;
     int per_sm = 0;
-    FR3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern,
-                                                            FR3D_SOR_THREADS, dyn));
+    if (slab)
+        FR3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fr3d_sor_wavefront<ST, C, true>,
+                                                                FR3D_SOR_THREADS, dyn));
+    else
+        FR3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fr3d_sor_wavefront<ST, C>,
+                                                                FR3D_SOR_THREADS, dyn));
     FR3D_REQUIRE(per_sm >= 1, "SOR kernel does not fit on an SM");
     if (dev.sor_ctas_per_sm > 0 && per_sm > dev.sor_ctas_per_sm)
         per_sm = dev.sor_ctas_per_sm;
@@ -746,8 +749,12 @@ inline void sor_run_c(Device& dev, const SorParams<ST>& P, unsigned* bar, int pe
     int tis = tabs_in_smem | (slab ? ((dev.sor_k0 << 1) | (dev.sor_k1 << 16)) : 0);
     void* args[] = {(void*)&Pc, (void*)&bar, (void*)&tis};
     dev.span_begin("fr3d_sor_wavefront");
-    FR3D_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(FR3D_SOR_THREADS),
-                                          args, dyn, dev.stream));
+    if (slab)
+        FR3D_CUDA(cudaLaunchCooperativeKernel((void*)fr3d_sor_wavefront<ST, C, true>, dim3(grid),
+                                              dim3(FR3D_SOR_THREADS), args, dyn, dev.stream));
+    else
+        FR3D_CUDA(cudaLaunchCooperativeKernel((void*)fr3d_sor_wavefront<ST, C>, dim3(grid), dim3(FR3D_SOR_THREADS),
+                                              args, dyn, dev.stream));
     dev.span_end();
     dev.launches++;
 }
