@@ -98,6 +98,7 @@ def load():
         "fr3d_level_state": (ci, [vp, ci, ci, vp, i64, i64]),
         "fr3d_level_sweeps_slab": (ci, [vp, ci, ci, ci, ci, ci]),
         "fr3d_level_planes": (ci, [vp, ci, ci, vp, ci, ci]),
+        "fr3d_level_wave_cells": (ci, [vp, ci, ci, vp, ci, ci]),
         "fr3d_level_end": (ci, [vp, ci]),
         "fr3d_level_end_range": (ci, [vp, ci, ci, ci]),
         "fr3d_flow_slab": (ci, [vp, ci, ci, vp, ci, ci]),
@@ -145,7 +146,7 @@ EXPORTED_SYMBOLS = [
     "fr3d_profile_report", "fr3d_fill_resize_table",
     "fr3d_warp_flow", "fr3d_cc_project", "fr3d_cc_window", "fr3d_cc_cgemm", "fr3d_cc_cross_power",
     "fr3d_cc_abs_argmax", "fr3d_cc_wrap_shift", "fr3d_cc_tile_sums", "fr3d_rigid_flow", "fr3d_add_flow",
-    "fr3d_level_sweeps_slab", "fr3d_level_planes",
+    "fr3d_level_sweeps_slab", "fr3d_level_planes", "fr3d_level_wave_cells",
 ]
 
 

@@ -1081,6 +1081,22 @@ int fr3d_level_planes(fr3d_ctx* ctx, int level, int direction, void* ext, int k_
     FR3D_API_END()
 }
 
+int fr3d_level_wave_cells(fr3d_ctx* ctx, int level, int direction, void* ext, int k, int q)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(_c->run_level == level, "level %d is not open", level);
+    FR3D_REQUIRE(ext && (direction == 0 || direction == 1), "bad argument");
+    const HPGeom& hp = _c->levels[level]->hp;
+    FR3D_REQUIRE(k >= 0 && k < hp.p && q >= 0, "bad plane / wave");
+    const int T = _c->iterations;
+    const int64_t n = (int64_t)_c->run_B * T * hp.m;
+    if (_c->state_dtype == FR3D_F64)
+        launch(_c->dev, SlabWaveCellsK<double>{(Vec4<double>*)_c->d.p, (Vec4<double>*)ext, hp.view(), k, q, T, direction}, n);
+    else
+        launch(_c->dev, SlabWaveCellsK<float>{(Vec4<float>*)_c->d.p, (Vec4<float>*)ext, hp.view(), k, q, T, direction}, n);
+    FR3D_API_END()
+}
+
 int fr3d_level_state(fr3d_ctx* ctx, int level, int direction, void* ext, int64_t slot_begin, int64_t slot_end)
 {
     FR3D_API_BEGIN(ctx)

@@ -1377,6 +1377,35 @@ struct SlabPlanesK {
     }
 };
 
+// The cells of plane k that wave q of the lexicographic schedule updates -- one anti-diagonal j + i = s - k per
+// sweep t in flight (s = q - 2t) -- <-> a dense buffer (B, T, m) of 4-vectors (entry (t, j) holds cell
+// (k, j, s-k-j); entries without a cell are left alone).  This is all a z-neighbour needs after wave q:
+// <= T*m cells instead of the m*n of the whole plane.  item = (b, t, j)
+template <class ST>
+struct SlabWaveCellsK {
+    Vec4<ST>* d;
+    Vec4<ST>* ext;
+    HPView hp;
+    int k, q, T, dir;
+    FR3D_HD void operator()(int64_t item) const
+    {
+        const int j = (int)(item % hp.m);
+        const int t = (int)((item / hp.m) % T);
+        const int64_t b = item / ((int64_t)hp.m * T);
+        const int s = q - 2 * t;
+        if (s < 0 || s >= hp.S)
+            return;
+        const int i = s - k - j;
+        if (i < 0 || i >= hp.n)
+            return;
+        Vec4<ST>* slot = d + b * hp.npad + hp.addr(k, j, i);
+        if (dir == 0)
+            ext[item] = *slot;
+        else
+            *slot = ext[item];
+    }
+};
+
 // ------------------------------------------------------------------------------------------
 // 5x5x5 median, scipy.ndimage.median_filter(mode="mirror") (core/optical_flow_3d.py:517-526).
 // Exact order statistic of float64 data through float32 keys: rounding to float32 is monotone,

@@ -222,12 +222,13 @@ def get_displacement_zslab(reg: Registration, moving_proc, uvw=None, group=None,
     """get_displacement for B frames with every large level solved on z-slabs: rank r owns the planes
     [z_r, z_{r+1}) of the level and runs, wave by wave, the sweeps of its planes only
     (`fr3d_level_sweeps_slab`).  A voxel of wave q = (k+j+i) + 2t reads nothing newer than wave q-1, so after every
-    wave the ranks trade the two boundary planes they own with their z-neighbours (`fr3d_level_planes`,
-    send/recv over NCCL; gloo in the CPU tests) -- S + 2(T-1) exchanges per level, both directions.  At the end of
+    wave the ranks trade, with both z-neighbours, the cells of their two boundary planes that the wave updated (one
+    anti-diagonal per sweep in flight, `fr3d_level_wave_cells`; send/recv over NCCL, gloo in the CPU tests) --
+    S + 2(T-1) exchanges per level, both directions.  At the end of
     the level the slabs are gathered, the 5^3 median runs on the same z-slabs and the flow slabs are exchanged as in
     the sweep-pipelined solve.  The update order is the reference's: the result is bit-identical to one GPU.
 
-    This is the straightforward version (whole boundary planes per wave, one kernel launch per wave); it exists for
+    This is the straightforward version (host-driven: one kernel launch and one message pair per wave); it exists for
     levels whose state does not fit one GPU and as the baseline for a fused exchange.  For volumes that do fit,
     `get_displacement_pipelined` needs ~8 messages per level instead of ~2 400 and is the faster choice today
     (DESIGN.md section 6).  Every rank must call with identical arguments; every rank returns the full result."""
@@ -266,27 +267,35 @@ def get_displacement_zslab(reg: Registration, moving_proc, uvw=None, group=None,
         def planes_in(buf, k0, k1):
             _check(h, lib.fr3d_level_planes(h, li, 1, dev.ptr(buf), k0, k1))
 
+        def cells_out(k, q):
+            buf = torch.zeros((B, T * py, 4), dtype=dev.torch_dtype(state_dt), device=reg.device)
+            _check(h, lib.fr3d_level_wave_cells(h, li, 0, dev.ptr(buf), k, q))
+            reg.sync()                                       # the buffer leaves through torch.distributed
+            return buf
+
         lo = _global_rank(group, rank - 1) if rank > 0 else None
         hi = _global_rank(group, rank + 1) if rank + 1 < world else None
         for q in range(S + 2 * (T - 1)):
             _check(h, lib.fr3d_level_sweeps_slab(h, li, q, q + 1, z0, z1))
+            # halo: only the cells of the boundary planes that this wave updated (one anti-diagonal per sweep in
+            # flight: <= T*py cells instead of py*px)
             ops, recvs = [], []
             if lo is not None:
-                sb = planes_out(z0, z0 + 1)
-                rb = dev.empty((B, plane, 4), state_dt, reg.device)
+                sb = cells_out(z0, q)
+                rb = dev.empty((B, T * py, 4), state_dt, reg.device)
                 ops += [dist.P2POp(dist.isend, sb, lo, group), dist.P2POp(dist.irecv, rb, lo, group)]
                 recvs.append((rb, z0 - 1))
                 keep.append(sb)
             if hi is not None:
-                sb = planes_out(z1 - 1, z1)
-                rb = dev.empty((B, plane, 4), state_dt, reg.device)
+                sb = cells_out(z1 - 1, q)
+                rb = dev.empty((B, T * py, 4), state_dt, reg.device)
                 ops += [dist.P2POp(dist.isend, sb, hi, group), dist.P2POp(dist.irecv, rb, hi, group)]
                 recvs.append((rb, z1))
                 keep.append(sb)
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
             for rb, k in recvs:
-                planes_in(rb, k, k + 1)
+                _check(h, lib.fr3d_level_wave_cells(h, li, 1, dev.ptr(rb), k, q))
             keep = keep[-8:]
         # gather the slabs of the finished increments: every rank needs them around its planes for the median
         for r, (a, b) in enumerate(bounds):

@@ -194,6 +194,9 @@ int fr3d_level_state(fr3d_ctx* ctx, int level, int direction, void* ext, int64_t
  * (device, B x (k_end-k_begin) x py x px 4-vectors {du,dv,dw,-} of the state dtype). */
 int fr3d_level_sweeps_slab(fr3d_ctx* ctx, int level, int q_begin, int q_end, int k_begin, int k_end);
 int fr3d_level_planes(fr3d_ctx* ctx, int level, int direction, void* ext, int k_begin, int k_end);
+/* The cells of plane k that wave q updated (one anti-diagonal per sweep in flight) out of (0) / into (1) `ext`
+ * (device, B x iterations x py 4-vectors; entries without a cell are not touched): the per-wave halo message. */
+int fr3d_level_wave_cells(fr3d_ctx* ctx, int level, int direction, void* ext, int k, int q);
 int fr3d_level_end(fr3d_ctx* ctx, int level);
 /* fr3d_level_end restricted to the planes z_begin <= z < z_end of the level's flow (the median of a plane needs
  * the increments of two planes on either side, which every rank holds); the other planes of the flow are then
