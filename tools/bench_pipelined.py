@@ -29,6 +29,8 @@ ap.add_argument("--channels", type=int, default=2)
 ap.add_argument("--min-level", type=int, default=0)
 ap.add_argument("--iterations", type=int, default=100)
 ap.add_argument("--chunks", type=int, default=8)
+ap.add_argument("--zslab", action="store_true", help="z-slab decomposition with per-wave halo exchange instead of the "
+                "sweep pipeline (not yet run on GPUs: expect it to be slow, it is host-driven)")
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -63,12 +65,16 @@ def timed(fn, reps):
 
 
 t1, single = timed(lambda: reg.get_displacement(mv), 2)
-tn, piped = timed(lambda: get_displacement_pipelined(reg, mv, n_chunks=args.chunks), 2)
+if args.zslab:
+    from flowreg3d_b200.multigpu import get_displacement_zslab
+    tn, piped = timed(lambda: get_displacement_zslab(reg, mv), 1)
+else:
+    tn, piped = timed(lambda: get_displacement_pipelined(reg, mv, n_chunks=args.chunks), 2)
 same = bool(torch.equal(single, piped))
 if rank == 0:
     print(json.dumps({"case": f"single volume {shape}x{C}, min_level {args.min_level}, {args.iterations} sweeps",
                       "levels": [list(s) for _, s in reg.plan.sched], "n_gpus": world,
-                      "ms_one_gpu": round(t1, 2), "ms_pipelined": round(tn, 2), "speedup": round(t1 / tn, 3),
+                      "mode": "zslab" if args.zslab else "sweep-pipelined", "ms_one_gpu": round(t1, 2), "ms_pipelined": round(tn, 2), "speedup": round(t1 / tn, 3),
                       "bit_identical": same}))
 if world > 1:
     dist.barrier()
