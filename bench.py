@@ -174,7 +174,7 @@ def algorithmic_bytes(name, plan_levels, B, C, iters, lag):
     """ALGORITHMIC HBM bytes of ONE launch of kernel `name`."""
     Z, Y, X = SHAPE
     NF = Z * Y * X
-    if name == "fr3d_sor_wavefront":
+    if name in ("fr3d_sor_wavefront", "fr3d_sor_staged"):
         # parity-safe storage: 108 B / voxel / sweep + (12C+84) B per psi refresh; mean over the levels
         per = [B * n * (108 * iters + (12 * C + 84) * -(-iters // lag)) for n in plan_levels]
         return float(np.mean(per))

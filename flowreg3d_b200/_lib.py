@@ -20,6 +20,8 @@ F32, F64, U8, U16, I16, I32 = range(6)
 OPT_SOR_CTAS_PER_SM = 1
 OPT_CC_BLOCK_SCANS = 2
 OPT_WARP_FACTORED = 3
+OPT_SOR_KERNEL = 4
+OPT_SOR_STAGES = 5
 _DTYPES = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.uint8): U8,
            np.dtype(np.uint16): U16, np.dtype(np.int16): I16, np.dtype(np.int32): I32}
 

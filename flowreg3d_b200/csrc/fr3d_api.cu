@@ -695,6 +695,14 @@ int fr3d_set_option(fr3d_ctx* ctx, int option, int64_t value)
         FR3D_REQUIRE(value == 0 || value == 1, "FR3D_OPT_CC_BLOCK_SCANS: %lld", (long long)value);
         _c->dev.cc_block_scans = (int)value;
         break;
+    case FR3D_OPT_SOR_KERNEL:
+        FR3D_REQUIRE(value == 0 || value == 1, "FR3D_OPT_SOR_KERNEL: %lld", (long long)value);
+        _c->dev.sor_kernel = (int)value;
+        break;
+    case FR3D_OPT_SOR_STAGES:
+        FR3D_REQUIRE(value >= 0 && value <= 16 && value != 1, "FR3D_OPT_SOR_STAGES: %lld", (long long)value);
+        _c->dev.sor_stages = (int)value;
+        break;
     default: FR3D_THROW(FR3D_ERR_ARG, "unknown option %d", option);
     }
     FR3D_API_END()

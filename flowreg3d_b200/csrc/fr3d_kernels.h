@@ -1189,10 +1189,14 @@ struct HPView {
     const int32_t* rowbase; // (S, p)
     const int32_t* start;   // (S+1): first slot of hyperplane s
     const int32_t* pe;      // (S): 32-slot chunks in hyperplanes s, s-2, s-4, ... (same-parity prefix sum)
-    const int32_t* nbr;     // (6, npad): slots of x-, y-, z-, x+, y+, z+ (own slot if outside); [0] = -1 on pad slots
+    const int32_t* nbr;     // (npad/32, 6, 32) CHUNK-MAJOR: slots of x-, y-, z-, x+, y+, z+ of the 32 slots of a chunk
+                            // (own slot if outside; [0] = -1 on pad slots).  One chunk's table is 768 contiguous
+                            // bytes = one bulk copy of the staged solver kernel (fr3d_sor.h)
     const int32_t* perm;    // (npad): natural linear index (k*m + j)*n + i, or -1 on pad slots
     FR3D_HD int64_t nvox() const { return (int64_t)p * m * n; }
     FR3D_HD int32_t addr(int k, int j, int i) const { return rowbase[(k + j + i) * p + k] + j; }
+    // index of neighbour q (0..5) of slot a in nbr
+    static FR3D_HD int64_t nbr_at(int q, int64_t a) { return ((a >> 5) * 6 + q) * 32 + (a & 31); }
 };
 
 // pad-slot defaults of the tables; item = slot
@@ -1203,9 +1207,9 @@ struct HPFillK {
     FR3D_HD void operator()(int64_t a) const
     {
         perm[a] = -1;
-        nbr[a] = -1;
+        nbr[HPView::nbr_at(0, a)] = -1;
         for (int q = 1; q < 6; ++q)
-            nbr[(int64_t)q * npad + a] = (int32_t)a;
+            nbr[HPView::nbr_at(q, a)] = (int32_t)a;
     }
 };
 
@@ -1220,14 +1224,13 @@ struct HPBuildK {
         const int j = (int)((item / g.n) % g.m);
         const int k = (int)(item / ((int64_t)g.n * g.m));
         const int32_t a = g.addr(k, j, i);
-        const int64_t np = g.npad;
         perm[a] = (int32_t)item;
-        nbr[a] = i > 0 ? g.addr(k, j, i - 1) : a;
-        nbr[np + a] = j > 0 ? g.addr(k, j - 1, i) : a;
-        nbr[2 * np + a] = k > 0 ? g.addr(k - 1, j, i) : a;
-        nbr[3 * np + a] = i < g.n - 1 ? g.addr(k, j, i + 1) : a;
-        nbr[4 * np + a] = j < g.m - 1 ? g.addr(k, j + 1, i) : a;
-        nbr[5 * np + a] = k < g.p - 1 ? g.addr(k + 1, j, i) : a;
+        nbr[HPView::nbr_at(0, a)] = i > 0 ? g.addr(k, j, i - 1) : a;
+        nbr[HPView::nbr_at(1, a)] = j > 0 ? g.addr(k, j - 1, i) : a;
+        nbr[HPView::nbr_at(2, a)] = k > 0 ? g.addr(k - 1, j, i) : a;
+        nbr[HPView::nbr_at(3, a)] = i < g.n - 1 ? g.addr(k, j, i + 1) : a;
+        nbr[HPView::nbr_at(4, a)] = j < g.m - 1 ? g.addr(k, j + 1, i) : a;
+        nbr[HPView::nbr_at(5, a)] = k < g.p - 1 ? g.addr(k + 1, j, i) : a;
     }
 };
 

@@ -72,7 +72,8 @@ struct SorParams {
     const double* wgt;    // (C, npad), shared by all frames
     const Vec4<ST>* L;    // (B, npad): alpha-weighted Laplacian of u, v, w
     Vec4<ST>* d;          // (B, npad): du, dv, dw (zero-initialised)
-    double* AB;           // (B, 9, npad): 1/den_u, 1/den_v, 1/den_w, A12, A13, A23, b1-Lu, b2-Lv, b3-Lw
+    double* AB;           // (B, npad/32, 9, 32) CHUNK-MAJOR: 1/den_u, 1/den_v, 1/den_w, A12, A13, A23, b1-Lu, b2-Lv, b3-Lw
+                          // of the 32 slots of a chunk are 2304 contiguous bytes (one bulk copy of the staged kernel)
                           // (nonlinear smoothness: A11, A22, A33 themselves -- the denominator changes per sweep)
     // nonlinear smoothness term (a_smooth != 1), see "Nonlinear smoothness" below
     double a_smooth, hx, hy, hz;
@@ -82,6 +83,13 @@ struct SorParams {
     double* psi_c;        // (B, npad): psi_s at the voxel
     double* psi_r;        // (B, 3, npad): psi_s at the ring voxel next to a boundary voxel along x / y / z
 };
+
+// element e (0..8) of the pre-combined system of slot a, frame b
+template <class ST>
+FR3D_HD int64_t sor_ab_at(const SorParams<ST>& P, int b, int64_t a, int e)
+{
+    return (((int64_t)b * (P.g.npad >> 5) + (a >> 5)) * 9 + e) * 32 + (a & 31);
+}
 
 // psi refresh + pre-combination for one voxel (sweeps with t % lag == 0)
 template <int C>
@@ -254,13 +262,13 @@ FR3D_HD SorLoc sor_locate(const SorParams<ST>& P, const SorTabs& tb, int q, cons
     const int t = P.redblack ? (q >> 1) : ((q - s) >> 1);
     SorLoc L;
     L.a = (int64_t)tb.start[s] + 32 * (f - before) + lane;
-    const int64_t np = g.npad;
-    L.n0 = g.nbr[L.a];
-    L.n1 = g.nbr[np + L.a];
-    L.n2 = g.nbr[2 * np + L.a];
-    L.n3 = g.nbr[3 * np + L.a];
-    L.n4 = g.nbr[4 * np + L.a];
-    L.n5 = g.nbr[5 * np + L.a];
+    const int32_t* nb = g.nbr + HPView::nbr_at(0, L.a);
+    L.n0 = nb[0];
+    L.n1 = nb[32];
+    L.n2 = nb[64];
+    L.n3 = nb[96];
+    L.n4 = nb[128];
+    L.n5 = nb[160];
     L.refresh = (t % P.lag) == 0;
     L.b0 = fgi * P.fg;
     L.b1 = L.b0 + P.fg < P.B ? L.b0 + P.fg : P.B;
@@ -291,10 +299,10 @@ FR3D_HD void sor_load(const SorParams<ST>& P, const SorLoc& L, int b, bool with_
     if (with_ab) {
         // plain sweep: the constant Laplacian term was folded into b1..b3 at the last refresh
         r.L.x = r.L.y = r.L.z = r.L.w = (ST)0;
-        const double* AB = P.AB + (int64_t)b * 9 * np + L.a;
+        const double* AB = P.AB + sor_ab_at(P, b, L.a, 0);
 #pragma unroll
         for (int k = 0; k < 9; ++k)
-            r.A[k] = FR3D_LDCG(AB + k * np);
+            r.A[k] = FR3D_LDCG(AB + k * 32);
     } else {
         r.L = ld4_cg(P.L + (int64_t)b * np + L.a);
     }
@@ -318,7 +326,7 @@ FR3D_HD void sor_process(const SorParams<ST>& P, const SorLoc& L, int kb = 0, in
     if (L.refresh) {
         const double den0 = 2.0 * P.ax + 2.0 * P.ay + 2.0 * P.az;
         for (int b = L.b0; b < L.b1; ++b) {
-            double* AB = P.AB + (int64_t)b * 9 * np + a;
+            double* AB = P.AB + sor_ab_at(P, b, a, 0);
             SorIn<ST> r;
             sor_load(P, L, b, false, r);
             sor_refresh<C>(P.a_data, P.J + (int64_t)b * C * 10 * np, P.wgt, np, a, (double)r.own.x, (double)r.own.y,
@@ -331,7 +339,7 @@ FR3D_HD void sor_process(const SorParams<ST>& P, const SorLoc& L, int kb = 0, in
             r.L.x = r.L.y = r.L.z = (ST)0;
 #pragma unroll
             for (int e = 0; e < 9; ++e)
-                FR3D_STCG(AB + e * np, r.A[e]);
+                FR3D_STCG(AB + e * 32, r.A[e]);
             st4_cg(P.d + (int64_t)b * np + a, sor_update(P, r));
         }
         return;
@@ -423,8 +431,8 @@ template <class ST>
 FR3D_HD void sor_nl_psi(const SorParams<ST>& P, int64_t a, int b)
 {
     const int64_t np = P.g.npad;
-    const int nb[6] = {P.g.nbr[a], P.g.nbr[np + a], P.g.nbr[2 * np + a], P.g.nbr[3 * np + a], P.g.nbr[4 * np + a],
-                       P.g.nbr[5 * np + a]};
+    const int32_t* nbt = P.g.nbr + HPView::nbr_at(0, a);
+    const int nb[6] = {nbt[0], nbt[32], nbt[64], nbt[96], nbt[128], nbt[160]};
     if (nb[0] < 0)
         return; // pad slot
     const Vec4<ST>* d = P.d + (int64_t)b * np;
@@ -489,8 +497,8 @@ template <class ST, int C>
 FR3D_HD void sor_nl_update(const SorParams<ST>& P, int64_t a, int b, int t)
 {
     const int64_t np = P.g.npad;
-    const int nb[6] = {P.g.nbr[a], P.g.nbr[np + a], P.g.nbr[2 * np + a], P.g.nbr[3 * np + a], P.g.nbr[4 * np + a],
-                       P.g.nbr[5 * np + a]};
+    const int32_t* nbt = P.g.nbr + HPView::nbr_at(0, a);
+    const int nb[6] = {nbt[0], nbt[32], nbt[64], nbt[96], nbt[128], nbt[160]};
     if (nb[0] < 0)
         return;
     Vec4<ST>* d = P.d + (int64_t)b * np;
@@ -517,17 +525,17 @@ FR3D_HD void sor_nl_update(const SorParams<ST>& P, int64_t a, int b, int t)
         den += tmp;
     }
     double A[9];
-    double* AB = P.AB + (int64_t)b * 9 * np + a;
+    double* AB = P.AB + sor_ab_at(P, b, a, 0);
     const double du = (double)own.x, dv = (double)own.y, dw = (double)own.z;
     if ((t % P.lag) == 0) {
         sor_refresh<C>(P.a_data, P.J + (int64_t)b * C * 10 * np, P.wgt, np, a, du, dv, dw, 0.0, A, false);
 #pragma unroll
         for (int e = 0; e < 9; ++e)
-            FR3D_STCG(AB + e * np, A[e]);
+            FR3D_STCG(AB + e * 32, A[e]);
     } else {
 #pragma unroll
         for (int e = 0; e < 9; ++e)
-            A[e] = FR3D_LDCG(AB + e * np);
+            A[e] = FR3D_LDCG(AB + e * 32);
     }
     const double om = FR3D_SOR_OMEGA, om1 = 1.0 - FR3D_SOR_OMEGA;
     const double den_u = den + A[0], den_v = den + A[1], den_w = den + A[2];
@@ -561,6 +569,34 @@ FR3D_HD void sor_nl_item(const SorParams<ST>& P, int q, const SorSet& wp, const 
         for (int b = 0; b < P.B; ++b)
             sor_nl_update<ST, C>(P, a, b, t);
     }
+}
+
+// peak number of warp items over all waves (host; pe_host = host copy of the chunk prefix)
+inline int sor_peak_items(int S, int T, int B, int fg, const int32_t* pe_host, int redblack)
+{
+    int peak = 0;
+    if (redblack) {
+        for (int c = 0; c < 2 && c < S; ++c) {
+            const int last = c + 2 * ((S - 1 - c) / 2);
+            peak = pe_host[last] > peak ? pe_host[last] : peak;
+        }
+        return peak * ((B + fg - 1) / fg);
+    }
+    const int nw = S + 2 * (T - 1);
+    for (int q = 0; q < nw; ++q) {
+        int tlo = q - (S - 1);
+        tlo = tlo > 0 ? (tlo + 1) / 2 : 0;
+        int thi = q / 2;
+        if (thi > T - 1)
+            thi = T - 1;
+        if (thi < tlo)
+            continue;
+        const int s_lo = q - 2 * thi;
+        const int c = pe_host[q - 2 * tlo] - (s_lo >= 2 ? pe_host[s_lo - 2] : 0);
+        if (c > peak)
+            peak = c;
+    }
+    return peak * ((B + fg - 1) / fg);
 }
 
 #ifdef FR3D_EMU
@@ -675,6 +711,373 @@ fr3d_sor_wavefront(const SorParams<ST> P, unsigned* bar, int tabs_in_smem)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// STAGED wavefront kernel (default for a_smooth == 1, full-volume solves).
+//
+// The plain wavefront kernel above is latency-bound: a warp issues the ~20 loads of one item, waits for
+// DRAM, computes, stores, and only then starts the next item (ncu, round 1: 25 % warps active, 48-57 %
+// long-scoreboard stalls, 3.9 TB/s).  Here every warp owns a ring of NS shared-memory stages that the TMA
+// engine fills with cp.async.bulk (SASS: UBLKCP) while the warp computes: the streamed inputs of an item
+// -- the chunk's neighbour table (768 B), the pre-combined system (2304 B per frame, chunk-major so that
+// it is ONE contiguous run) and the voxels' own increments (512 B per frame) -- are in flight NS items
+// ahead, signalled per stage by an mbarrier (complete_tx).  The sequence of items a warp will process is a
+// pure function of (block, warp, wave), so the prefetch runs ACROSS the grid barrier into the next wave:
+// what an item of wave q+1 streams (its system, its own value of sweep t-1) was last written in wave q-1
+// and is final once wave q has started.  Only the six neighbour increments (written in wave q) must wait
+// for the barrier; they are gathered with ordinary loads one item ahead of the arithmetic (LOOKAHEAD).
+// psi-refresh items (one sweep in `lag`) stream the neighbour table and the own value and read J directly.
+#ifndef FR3D_STG_FG
+#define FR3D_STG_FG 1      /* frames per warp item */
+#endif
+#ifndef FR3D_STG_LOOK
+#define FR3D_STG_LOOK 1    /* gather the neighbour increments of item i+1 before computing item i */
+#endif
+#ifndef FR3D_STG_MINB
+#define FR3D_STG_MINB 2    /* resident CTAs per SM the register allocation must allow */
+#endif
+#ifndef FR3D_STG_NS
+#define FR3D_STG_NS 3      /* default stages per warp (runtime-adjustable: FR3D_OPT_SOR_STAGES) */
+#endif
+#ifndef FR3D_STG_NBRCA
+#define FR3D_STG_NBRCA 0   /* neighbour gathers through L1 (1) or L2 only (0) */
+#endif
+
+namespace stg {
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    long long t0 = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+        if (!ok) {
+            // a stage that never completes is a bug (byte count / alignment): fail instead of hanging the GPU
+            if (t0 == 0)
+                t0 = clock64();
+            else if (clock64() - t0 > 8000000000LL)
+                __trap();
+        }
+    } while (!ok);
+}
+// global -> shared bulk copy (TMA engine, no tensor map); bytes, both addresses: multiples of 16
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// order this thread's generic-proxy accesses with async-proxy (bulk copy) accesses
+__device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+} // namespace stg
+
+template <class ST, int FG>
+struct SorStage {
+    static constexpr int kNbr = 6 * 32 * 4;
+    static constexpr int kAB = 9 * 32 * 8;
+    static constexpr int kOwn = 32 * (int)sizeof(Vec4<ST>);
+    static constexpr int kFrame = kAB + kOwn;
+    static constexpr int kBytes = kNbr + FG * kFrame;
+};
+
+// Warp-uniform description of one item: the chunk (first slot), its frames, whether the sweep refreshes psi.
+struct SorItem {
+    int32_t a0;
+    int b0, nb;
+    bool refresh;
+};
+template <class ST, int FG>
+__device__ __forceinline__ SorItem sor_item(const SorParams<ST>& P, const SorTabs& tb, int q, const SorWave& w, int item)
+{
+    const int fgi = item / w.chunks;
+    const int f = item - fgi * w.chunks;
+    int lo = 0, hi = w.nT - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (tb.pe[w.s_lo + 2 * mid] - w.base > f)
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    const int s = w.s_lo + 2 * lo;
+    const int before = (s >= 2 ? tb.pe[s - 2] : 0) - w.base;
+    const int t = P.redblack ? (q >> 1) : ((q - s) >> 1);
+    SorItem I;
+    I.a0 = tb.start[s] + 32 * (f - before);
+    I.refresh = (t % P.lag) == 0;
+    I.b0 = fgi * FG;
+    I.nb = P.B - I.b0 < FG ? P.B - I.b0 : FG;
+    return I;
+}
+
+template <class ST, int FG>
+struct SorNbrs {
+    Vec4<ST> v[FG][6];
+    int n0; // < 0: pad slot
+};
+
+template <class ST, int C, int FG>
+__global__ void __launch_bounds__(FR3D_SOR_THREADS, FR3D_STG_MINB)
+fr3d_sor_staged(const SorParams<ST> P, unsigned* bar, int tabs_in_smem, int NS)
+{
+    typedef SorStage<ST, FG> SG;
+    extern __shared__ __align__(128) unsigned char fr3d_stg_smem[];
+    const int wpb = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* const stages = fr3d_stg_smem + (size_t)warp * NS * SG::kBytes;
+    uint64_t* const mb = reinterpret_cast<uint64_t*>(fr3d_stg_smem + (size_t)wpb * NS * SG::kBytes) + warp * NS;
+    int32_t* const tabs = reinterpret_cast<int32_t*>(fr3d_stg_smem + (size_t)wpb * NS * (SG::kBytes + 8));
+    SorTabs tb{P.g.pe, P.g.start};
+    if (tabs_in_smem) {
+        const int S = P.g.S;
+        for (int i = threadIdx.x; i < S; i += blockDim.x)
+            tabs[i] = P.g.pe[i];
+        for (int i = threadIdx.x; i <= S; i += blockDim.x)
+            tabs[S + i] = P.g.start[i];
+        tb.pe = tabs;
+        tb.start = tabs + S;
+    }
+    if (lane == 0) {
+        for (int i = 0; i < NS; ++i)
+            stg::mbar_init(stg::s32(mb + i), 1);
+        stg::fence_barrier_init();
+    }
+    __syncthreads();
+
+    const int64_t np = P.g.npad;
+    const int64_t nch = np >> 5;
+    const int first = blockIdx.x * wpb + warp;
+    const int stride = gridDim.x * wpb;
+
+    // ---- producer cursor: the next item of this warp's sequence that has not been requested yet
+    int pq = P.q_begin, pitem = first, pst = 0;
+    bool pvalid = pq < P.q_end;
+    SorWave pw;
+    if (pvalid)
+        pw = sor_wave(P, tb, pq);
+    int inflight = 0; // stages requested and not yet released
+    auto p_norm = [&]() {
+        while (pvalid && pitem >= pw.items) {
+            ++pq;
+            if (pq >= P.q_end) {
+                pvalid = false;
+                break;
+            }
+            pw = sor_wave(P, tb, pq);
+            pitem = first;
+        }
+    };
+    p_norm();
+    auto produce = [&](int q_now) {
+        while (pvalid && inflight < NS && pq <= q_now + 1) {
+            const SorItem I = sor_item<ST, FG>(P, tb, pq, pw, pitem);
+            if (lane == 0) {
+                const uint32_t ba = stg::s32(mb + pst);
+                const uint32_t dst = stg::s32(stages + (size_t)pst * SG::kBytes);
+                const uint32_t bytes = SG::kNbr + I.nb * SG::kOwn + (I.refresh ? 0 : I.nb * SG::kAB);
+                stg::fence_async_shared(); // the stage's previous contents were read through the generic proxy
+                stg::mbar_expect_tx(ba, bytes);
+                stg::bulk_g2s(dst, P.g.nbr + (int64_t)(I.a0 >> 5) * 192, SG::kNbr, ba);
+                for (int e = 0; e < I.nb; ++e) {
+                    const int b = I.b0 + e;
+                    const uint32_t fd = dst + SG::kNbr + e * SG::kFrame;
+                    if (!I.refresh)
+                        stg::bulk_g2s(fd, P.AB + ((int64_t)b * nch + (I.a0 >> 5)) * 288, SG::kAB, ba);
+                    stg::bulk_g2s(fd + SG::kAB, P.d + (int64_t)b * np + I.a0, SG::kOwn, ba);
+                }
+            }
+            ++inflight;
+            pst = pst + 1 == NS ? 0 : pst + 1;
+            pitem += stride;
+            p_norm();
+        }
+    };
+
+    // ---- consumer
+    int cst = 0;
+    uint32_t cph = 0;
+    auto gather = [&](const unsigned char* sg, const SorItem& I, SorNbrs<ST, FG>& N) {
+        const int32_t* nb = reinterpret_cast<const int32_t*>(sg) + lane;
+        const int n0 = nb[0];
+        N.n0 = n0;
+        const int i0 = n0 < 0 ? I.a0 + lane : n0;
+        const int i1 = nb[32], i2 = nb[64], i3 = nb[96], i4 = nb[128], i5 = nb[160];
+#pragma unroll
+        for (int e = 0; e < FG; ++e) {
+            if (e < I.nb) {
+                const Vec4<ST>* d = P.d + (int64_t)(I.b0 + e) * np;
+                if (FR3D_STG_NBRCA) {
+                    N.v[e][0] = ld4_ca(d + i0);
+                    N.v[e][1] = ld4_ca(d + i1);
+                    N.v[e][2] = ld4_ca(d + i2);
+                    N.v[e][3] = ld4_ca(d + i3);
+                    N.v[e][4] = ld4_ca(d + i4);
+                    N.v[e][5] = ld4_ca(d + i5);
+                } else {
+                    N.v[e][0] = ld4_cg(d + i0);
+                    N.v[e][1] = ld4_cg(d + i1);
+                    N.v[e][2] = ld4_cg(d + i2);
+                    N.v[e][3] = ld4_cg(d + i3);
+                    N.v[e][4] = ld4_cg(d + i4);
+                    N.v[e][5] = ld4_cg(d + i5);
+                }
+            }
+        }
+    };
+    auto compute = [&](const unsigned char* sg, const SorItem& I, const SorNbrs<ST, FG>& N) {
+        if (N.n0 < 0)
+            return; // pad slot
+        const int64_t a = I.a0 + lane;
+#pragma unroll
+        for (int e = 0; e < FG; ++e) {
+            if (e >= I.nb)
+                break;
+            const int b = I.b0 + e;
+            const unsigned char* fr = sg + SG::kNbr + e * SG::kFrame;
+            SorIn<ST> r;
+            r.own = reinterpret_cast<const Vec4<ST>*>(fr + SG::kAB)[lane];
+            r.xm = N.v[e][0];
+            r.ym = N.v[e][1];
+            r.zm = N.v[e][2];
+            r.xp = N.v[e][3];
+            r.yp = N.v[e][4];
+            r.zp = N.v[e][5];
+            if (I.refresh) {
+                const double den0 = 2.0 * P.ax + 2.0 * P.ay + 2.0 * P.az;
+                r.L = ld4_cg(P.L + (int64_t)b * np + a);
+                sor_refresh<C>(P.a_data, P.J + (int64_t)b * C * 10 * np, P.wgt, np, a, (double)r.own.x, (double)r.own.y,
+                               (double)r.own.z, den0, r.A);
+                r.A[6] -= (double)r.L.x;
+                r.A[7] -= (double)r.L.y;
+                r.A[8] -= (double)r.L.z;
+                r.L.x = r.L.y = r.L.z = (ST)0;
+                double* AB = P.AB + sor_ab_at(P, b, a, 0);
+#pragma unroll
+                for (int k = 0; k < 9; ++k)
+                    FR3D_STCG(AB + k * 32, r.A[k]);
+            } else {
+                r.L.x = r.L.y = r.L.z = r.L.w = (ST)0;
+                const double* A = reinterpret_cast<const double*>(fr) + lane;
+#pragma unroll
+                for (int k = 0; k < 9; ++k)
+                    r.A[k] = A[k * 32];
+            }
+            st4_cg(P.d + (int64_t)b * np + a, sor_update(P, r));
+        }
+    };
+
+    unsigned gen = 0;
+    for (int q = P.q_begin; q < P.q_end; ++q) {
+        const SorWave w = sor_wave(P, tb, q);
+        produce(q);
+        int item = first;
+        if (item < w.items) {
+            SorItem I = sor_item<ST, FG>(P, tb, q, w, item);
+            SorNbrs<ST, FG> cur;
+            stg::mbar_wait(stg::s32(mb + cst), cph);
+            gather(stages + (size_t)cst * SG::kBytes, I, cur);
+            for (;;) {
+                const int next = item + stride;
+                const bool more = next < w.items;
+                const int nst = cst + 1 == NS ? 0 : cst + 1;
+                const uint32_t nph = nst == 0 ? cph ^ 1u : cph;
+                SorItem In = I;
+                SorNbrs<ST, FG> nx;
+                if (more) {
+                    In = sor_item<ST, FG>(P, tb, q, w, next);
+                    if (FR3D_STG_LOOK) {
+                        stg::mbar_wait(stg::s32(mb + nst), nph);
+                        gather(stages + (size_t)nst * SG::kBytes, In, nx);
+                    }
+                }
+                compute(stages + (size_t)cst * SG::kBytes, I, cur);
+                __syncwarp();
+                --inflight;
+                cst = nst;
+                cph = nph;
+                produce(q);
+                if (!more)
+                    break;
+                if (!FR3D_STG_LOOK) {
+                    stg::mbar_wait(stg::s32(mb + cst), cph);
+                    gather(stages + (size_t)cst * SG::kBytes, In, nx);
+                }
+                I = In;
+                cur = nx;
+                item = next;
+            }
+        }
+        ++gen;
+        stg::fence_async_global(); // this wave's stores (generic proxy) before other SMs' bulk copies of them
+        fr3d_grid_barrier(bar, gen * gridDim.x);
+        stg::fence_async_global();
+    }
+}
+
+template <class ST, int C>
+inline bool sor_run_staged(Device& dev, const SorParams<ST>& Pin, unsigned* bar, const int32_t* pe_host)
+{
+    constexpr int FG = FR3D_STG_FG;
+    typedef SorStage<ST, FG> SG;
+    SorParams<ST> P = Pin;
+    P.fg = FG;
+    const int peak = sor_peak_items(P.g.S, P.T, P.B, P.fg, pe_host, P.redblack);
+    const int wpb = FR3D_SOR_THREADS / 32;
+    int NS = dev.sor_stages > 0 ? dev.sor_stages : FR3D_STG_NS;
+    const size_t tab_bytes = (size_t)(2 * P.g.S + 1) * sizeof(int32_t);
+    const int tabs_in_smem = tab_bytes <= 40 * 1024;
+    static bool configured = false; // per instantiation
+    if (!configured) {
+        FR3D_CUDA(cudaFuncSetAttribute(fr3d_sor_staged<ST, C, FG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       227 * 1024));
+        configured = true;
+    }
+    int per_sm = 0;
+    size_t dyn = 0;
+    const int want_per_sm = dev.sor_ctas_per_sm > 0 ? dev.sor_ctas_per_sm : FR3D_STG_MINB;
+    for (; NS >= 2; --NS) {
+        dyn = (size_t)wpb * NS * (SG::kBytes + 8) + (tabs_in_smem ? tab_bytes : 0);
+        if (dyn > 227 * 1024)
+            continue;
+        FR3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fr3d_sor_staged<ST, C, FG>, FR3D_SOR_THREADS, dyn));
+        if (per_sm >= want_per_sm || NS == 2)
+            break;
+    }
+    if (per_sm < 1)
+        return false; // does not fit: the caller falls back to the direct-load kernel
+    if (per_sm > want_per_sm)
+        per_sm = want_per_sm;
+    int64_t want = ((int64_t)peak + wpb - 1) / wpb;
+    int grid = dev.sm_count * per_sm;
+    if (want < grid)
+        grid = (int)(want < 1 ? 1 : want);
+    FR3D_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), dev.stream));
+    int tis = tabs_in_smem;
+    void* args[] = {(void*)&P, (void*)&bar, (void*)&tis, (void*)&NS};
+    dev.span_begin("fr3d_sor_staged");
+    FR3D_CUDA(cudaLaunchCooperativeKernel((void*)fr3d_sor_staged<ST, C, FG>, dim3(grid), dim3(FR3D_SOR_THREADS), args,
+                                          dyn, dev.stream));
+    dev.span_end();
+    dev.launches++;
+    return true;
+}
+
 // Nonlinear-smoothness variant: psi and sweep tasks of a wave, one grid barrier per wave.
 template <class ST, int C>
 __global__ void __launch_bounds__(FR3D_SOR_THREADS, 2) fr3d_sor_wavefront_nl(const SorParams<ST> P, unsigned* bar)
@@ -717,12 +1120,14 @@ inline void sor_run_nl(Device& dev, const SorParams<ST>& P, unsigned* bar)
 }
 
 template <class ST, int C>
-inline void sor_run_c(Device& dev, const SorParams<ST>& P, unsigned* bar, int peak_items)
+inline void sor_run_c(Device& dev, const SorParams<ST>& P, unsigned* bar, int peak_items, const int32_t* pe_host)
 {
     if (P.a_smooth != 1.0) {
         sor_run_nl<ST, C>(dev, P, bar);
         return;
     }
+    if (dev.sor_kernel == 1 && dev.sor_k1 <= 0 && sor_run_staged<ST, C>(dev, P, bar, pe_host))
+        return;
     const size_t smem = (size_t)(2 * P.g.S + 1) * sizeof(int32_t);
     const int tabs_in_smem = smem <= 40 * 1024;
     const size_t dyn = tabs_in_smem ? smem : 0;
@@ -760,34 +1165,6 @@ inline void sor_run_c(Device& dev, const SorParams<ST>& P, unsigned* bar, int pe
 }
 #endif
 
-// peak number of warp items over all waves (host; pe_host = host copy of the chunk prefix)
-inline int sor_peak_items(int S, int T, int B, int fg, const int32_t* pe_host, int redblack)
-{
-    int peak = 0;
-    if (redblack) {
-        for (int c = 0; c < 2 && c < S; ++c) {
-            const int last = c + 2 * ((S - 1 - c) / 2);
-            peak = pe_host[last] > peak ? pe_host[last] : peak;
-        }
-        return peak * ((B + fg - 1) / fg);
-    }
-    const int nw = S + 2 * (T - 1);
-    for (int q = 0; q < nw; ++q) {
-        int tlo = q - (S - 1);
-        tlo = tlo > 0 ? (tlo + 1) / 2 : 0;
-        int thi = q / 2;
-        if (thi > T - 1)
-            thi = T - 1;
-        if (thi < tlo)
-            continue;
-        const int s_lo = q - 2 * thi;
-        const int c = pe_host[q - 2 * tlo] - (s_lo >= 2 ? pe_host[s_lo - 2] : 0);
-        if (c > peak)
-            peak = c;
-    }
-    return peak * ((B + fg - 1) / fg);
-}
-
 template <class ST>
 inline void sor_run(Device& dev, const SorParams<ST>& P, unsigned* bar, const int32_t* pe_host)
 {
@@ -796,7 +1173,7 @@ inline void sor_run(Device& dev, const SorParams<ST>& P, unsigned* bar, const in
 #define FR3D_SOR_GO(C_) sor_run_c<ST, C_>(dev, P, bar)
 #else
     const int peak = sor_peak_items(P.g.S, P.T, P.B, P.fg, pe_host, P.redblack);
-#define FR3D_SOR_GO(C_) sor_run_c<ST, C_>(dev, P, bar, peak)
+#define FR3D_SOR_GO(C_) sor_run_c<ST, C_>(dev, P, bar, peak, pe_host)
 #endif
     switch (P.C) {
     case 1: FR3D_SOR_GO(1); break;

@@ -128,9 +128,12 @@ typedef enum {
                                    * operations; float32 results differ from scipy's association in the last bit on
                                    * ~1e-7 of the voxels), 0 (default) = scipy's ((c*wz)*wy)*wx accumulate, bit-equal.
                                    * THE ONE KNOB THAT CAN CHANGE RESULTS (by <= 1 float32 ulp). */
-    FR3D_OPT_CC_BLOCK_SCANS = 2   /* rigid pre-alignment: 1 = block-cooperative plane scans (arg-max, tile sums,
-                                   * plane mean: one CTA per plane) instead of one thread per plane (0, default until
-                                   * the block versions have been timed on a B200) */
+    FR3D_OPT_CC_BLOCK_SCANS = 2,  /* rigid pre-alignment: 1 = block-cooperative plane scans (arg-max, tile sums,
+                                   * plane mean: one CTA per plane) instead of one thread per plane (0) */
+    FR3D_OPT_SOR_KERNEL = 4,      /* level solver kernel: 1 (default) = staged (cp.async.bulk + mbarrier ring per warp,
+                                   * prefetch across the wave barrier), 0 = direct-load wavefront kernel.  Same
+                                   * arithmetic in the same order: results are bit-identical */
+    FR3D_OPT_SOR_STAGES = 5       /* shared-memory stages per warp of the staged solver kernel (0 = built-in default) */
 } fr3d_option;
 int fr3d_set_option(fr3d_ctx* ctx, int option, int64_t value);
 
