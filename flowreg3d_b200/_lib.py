@@ -1,13 +1,13 @@
 """ctypes binding of libfr3d.so (the C ABI declared in include/fr3d.h).
 
 There is no CPU fallback: if the CUDA library is missing or no B200 is visible the package raises.
-(tests/emu builds a CPU emulation of the kernel logic for the not-gpu tests; it is selected only by
-the test-suite through FR3D_LIBRARY_OVERRIDE and is never shipped.)
+The library that is loaded is ALWAYS flowreg3d_b200/libfr3d.so: no environment variable redirects the loader.
+(tests/emu builds a CPU emulation of the kernel logic for the not-gpu tests; only test code can install it, by
+calling _select_for_tests() in its own process -- it is never shipped and never reachable from the product.)
 """
 from __future__ import annotations
 
 import ctypes as C
-import os
 from pathlib import Path
 
 import numpy as np
@@ -22,6 +22,7 @@ OPT_CC_BLOCK_SCANS = 2
 OPT_WARP_FACTORED = 3
 OPT_SOR_KERNEL = 4
 OPT_SOR_STAGES = 5
+OPT_SOR_TILE = 6
 _DTYPES = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.uint8): U8,
            np.dtype(np.uint16): U16, np.dtype(np.int16): I16, np.dtype(np.int32): I32}
 
@@ -62,11 +63,11 @@ class Fr3dError(RuntimeError):
 
 
 _lib = None
+_test_library = None     # (path, is_emulator) installed by _select_for_tests(); None in the product
 
 
 def library_path() -> Path:
-    ov = os.environ.get("FR3D_LIBRARY_OVERRIDE") or os.environ.get("FR3D_LIBRARY_VARIANT")
-    return Path(ov) if ov else HERE / "libfr3d.so"
+    return Path(_test_library[0]) if _test_library is not None else HERE / "libfr3d.so"
 
 
 def load():
@@ -153,17 +154,15 @@ EXPORTED_SYMBOLS = [
 
 
 def is_emulator() -> bool:
-    return bool(os.environ.get("FR3D_LIBRARY_OVERRIDE"))
+    return _test_library is not None and bool(_test_library[1])
 
 
-def _select_for_tests(path) -> None:
-    """tests/conftest.py only: point the binding at the kernel-logic emulator (or back at the CUDA
-    library with None) and drop everything cached from the previous choice."""
-    global _lib
-    if path is None:
-        os.environ.pop("FR3D_LIBRARY_OVERRIDE", None)
-    else:
-        os.environ["FR3D_LIBRARY_OVERRIDE"] = str(path)
+def _select_for_tests(path, emulator: bool = True) -> None:
+    """tests/ and tools/ only: point the binding of THIS process at the kernel-logic emulator (emulator=True: CPU
+    tensors, tests/emu) or at a tuning build of the CUDA library (emulator=False, tools/variants.sh), or back at
+    flowreg3d_b200/libfr3d.so with None, and drop everything cached from the previous choice."""
+    global _lib, _test_library
+    _test_library = None if path is None else (str(path), bool(emulator))
     _lib = None
     from . import core
     for c in core._bare.values():

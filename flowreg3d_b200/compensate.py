@@ -70,7 +70,8 @@ class SequenceCorrector:
     """Stateful batch processor: owns the Registration, the fixed volume and the w_init chain."""
 
     def __init__(self, reference_raw: np.ndarray, options, max_batch: Optional[int] = None,
-                 device: Optional[torch.device] = None, group=None, streams: int = 1, statistics: bool = False):
+                 device: Optional[torch.device] = None, group=None, streams: int = 1, statistics: bool = False,
+                 cc_prealign: bool = False):
         self.options = options
         ref = np.asarray(reference_raw)
         if ref.ndim == 3:
@@ -92,8 +93,15 @@ class SequenceCorrector:
         else:
             self.reg = Registration(self.shape, Cn, fp, max_batch=mb, device=device, **kw)
         self.device = self.reg.device
-        # rigid cross-correlation pre-alignment (OFOptions.cc_initialization / cc_hw / cc_up)
-        self.cc = bool(getattr(options, "cc_initialization", False))
+        # OFOptions.cc_initialization / cc_hw / cc_up.  What the REFERENCE pipeline does with the option (checked
+        # against the live reference, tests/golden/xcorr_sequence.npz): BatchMotionCorrector starts the w_init chain
+        # from a zero field instead of the bootstrap solve (compensate_recording_3D.py:346-356) -- and that is all,
+        # because _process_batch_parallel builds flow_params WITHOUT the cc_* keys (:301-315), so its executors never
+        # see cc_initialization (sequential_3d.py:63) and run the plain flow.  That is the default here too
+        # (cc_zero_start).  cc_prealign=True additionally runs the rigid pre-alignment the executors implement
+        # (sequential_3d.py:89-145) for every frame, i.e. what the option is documented to do.
+        self.cc_zero_start = bool(getattr(options, "cc_initialization", False))
+        self.cc = self.cc_zero_start and bool(cc_prealign)
         self.cc_hw = getattr(options, "cc_hw", 256)
         self.cc_up = int(getattr(options, "cc_up", 10))
         if self.cc and Cn != 1:
@@ -136,8 +144,7 @@ class SequenceCorrector:
     # -- helpers ------------------------------------------------------------------------
     def _flows(self, proc: torch.Tensor, uvw: Optional[torch.Tensor], proc64: Optional[torch.Tensor] = None) -> torch.Tensor:
         if self.cc:
-            # sequential_3d.py:89-145 -- also for the w_init bootstrap (the reference's bootstrap goes through the
-            # same executor call with a zero field); the warps read the float64 pre-processed frames as there
+            # sequential_3d.py:89-145; the warps read the float64 pre-processed frames as there
             Z, Y, X = self.shape
             w0 = uvw if uvw is not None else torch.zeros((Z, Y, X, 3), dtype=torch.float32, device=self.device)
             src = proc64 if proc64 is not None else proc
@@ -173,6 +180,11 @@ class SequenceCorrector:
         proc64 = (dev.empty(tuple(raw.shape), np.float64, self.device)
                   if ((self.update_reference or self.cc) and t > 0) else None)
         proc = self.reg.preprocess(raw, self.lo, self.den, out64=proc64) if t > 0 else None
+        if self.w_init is None and self.cc_zero_start:
+            # compensate_recording_3D.py:346-356: with cc_initialization the chain starts from a ZERO field and no
+            # bootstrap frames are solved (the rigid estimate of every frame replaces the bootstrap)
+            Z, Y, X = self.shape
+            self.w_init = torch.zeros((Z, Y, X, 3), dtype=torch.float32, device=self.device)
         if self.w_init is None:
             # bootstrap (compensate_recording_3D.py:359-388): first min(22, G) frames from zero flow
             n_init = min(22, G)
@@ -345,9 +357,10 @@ class SequenceCorrector:
 
 def compensate_arr_3D(c1: np.ndarray, c_ref: np.ndarray, options=None,
                       progress_callback: Optional[Callable[[int, int], None]] = None,
-                      device: Optional[torch.device] = None):
+                      device: Optional[torch.device] = None, cc_prealign: bool = False):
     """Drop-in for flowreg3d.motion_correction.compensate_arr_3D: returns (registered, flow) with
-    registered shaped like c1 and flow (T,Z,Y,X,3) float32."""
+    registered shaped like c1 and flow (T,Z,Y,X,3) float32.  cc_prealign: see SequenceCorrector (not a reference
+    argument; False reproduces what the reference pipeline computes for OFOptions.cc_initialization)."""
     c1 = np.asarray(c1)
     c_ref = np.asarray(c_ref)
     squeezed = False
@@ -365,7 +378,7 @@ def compensate_arr_3D(c1: np.ndarray, c_ref: np.ndarray, options=None,
         squeezed = True
     options = OFOptions() if options is None else options.copy()
     T = c1.shape[0]
-    seq = SequenceCorrector(c_ref, options, device=device)
+    seq = SequenceCorrector(c_ref, options, device=device, cc_prealign=cc_prealign)
     registered = np.empty_like(c1)
     w = np.empty((T,) + seq.shape + (3,), np.float32)
     bs = int(options.buffer_size)
@@ -401,7 +414,7 @@ def compensate_arr_3D(c1: np.ndarray, c_ref: np.ndarray, options=None,
 
 
 def compensate_arr_3D_sharded(c1: np.ndarray, c_ref: np.ndarray, options=None, group=None,
-                              device: Optional[torch.device] = None):
+                              device: Optional[torch.device] = None, cc_prealign: bool = False):
     """Multi-GPU variant: every rank passes the same (T,Z,Y,X,C) array (or a memory map of it) and
     gets back ITS shard: (registered, flow, frame_indices).  Results are identical in layout to
     compensate_arr_3D restricted to frame_indices."""
@@ -412,7 +425,7 @@ def compensate_arr_3D_sharded(c1: np.ndarray, c_ref: np.ndarray, options=None, g
     if c_ref.ndim == 3:
         c_ref = c_ref[..., None]
     options = OFOptions() if options is None else options.copy()
-    seq = SequenceCorrector(c_ref, options, device=device, group=group)
+    seq = SequenceCorrector(c_ref, options, device=device, group=group, cc_prealign=cc_prealign)
     regs, flows, idx = [], [], []
     T = c1.shape[0]
     try:

@@ -696,9 +696,21 @@ int fr3d_set_option(fr3d_ctx* ctx, int option, int64_t value)
         _c->dev.cc_block_scans = (int)value;
         break;
     case FR3D_OPT_SOR_KERNEL:
-        FR3D_REQUIRE(value == 0 || value == 1, "FR3D_OPT_SOR_KERNEL: %lld", (long long)value);
+        FR3D_REQUIRE(value >= 0 && value <= 2, "FR3D_OPT_SOR_KERNEL: %lld", (long long)value);
         _c->dev.sor_kernel = (int)value;
         break;
+    case FR3D_OPT_SOR_TILE: {
+        const int tb = (int)(value & 0xff), tk = (int)((value >> 8) & 0xff), tj = (int)((value >> 16) & 0xff),
+                  ti = (int)((value >> 24) & 0xff);
+        FR3D_REQUIRE(value >= 0 && (value >> 32) == 0 && tb <= 32 && (tk == 0 || tk >= 2) && (tj == 0 || tj >= 2) &&
+                         (ti == 0 || ti >= 2),
+                     "FR3D_OPT_SOR_TILE: %lld", (long long)value);
+        _c->dev.sor_tile_sweeps = tb;
+        _c->dev.sor_tile_k = tk;
+        _c->dev.sor_tile_j = tj;
+        _c->dev.sor_tile_i = ti;
+        break;
+    }
     case FR3D_OPT_SOR_STAGES:
         FR3D_REQUIRE(value >= 0 && value <= 16 && value != 1, "FR3D_OPT_SOR_STAGES: %lld", (long long)value);
         _c->dev.sor_stages = (int)value;

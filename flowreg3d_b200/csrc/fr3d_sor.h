@@ -599,10 +599,55 @@ inline int sor_peak_items(int S, int T, int B, int fg, const int32_t* pe_host, i
     return peak * ((B + fg - 1) / fg);
 }
 
+} // namespace fr3d
+#include "fr3d_sor_tile.h"
+namespace fr3d {
+
+// Which levels the time-blocked tile kernel takes (FR3D_OPT_SOR_KERNEL = 2, the default): the plain lexicographic
+// full solve.  Partial sweep ranges (sweep-pipelined multi-GPU solve), z-slab launches, the red-black order and the
+// nonlinear smoothness term keep the wavefront kernels.
+template <class ST>
+inline bool sor_tile_applicable(const Device& dev, const SorParams<ST>& P)
+{
+    return dev.sor_kernel == 2 && dev.sor_k1 <= 0 && !P.redblack && P.a_smooth == 1.0 && P.t_begin == 0 &&
+           P.t_end == P.T && P.q_begin == 0 && P.q_end == sor_num_waves(P);
+}
+inline SorTileGeom sor_tile_geom_for(const Device& dev, int p, int m, int n, int T, int lag)
+{
+    // sweeps per time block: the update lag when a tile can hold it (psi refreshes then fall on local sweep 0 and run
+    // as one parallel pass), else its largest divisor <= 8, else 5 with the refresh inside the waves
+    int Tb = dev.sor_tile_sweeps;
+    if (Tb <= 0) {
+        Tb = 5;
+        for (int d = 8; d >= 2; --d)
+            if (lag % d == 0) {
+                Tb = d;
+                break;
+            }
+    }
+    const int tk = dev.sor_tile_k > 0 ? dev.sor_tile_k : 8, tj = dev.sor_tile_j > 0 ? dev.sor_tile_j : 8,
+              ti = dev.sor_tile_i > 0 ? dev.sor_tile_i : 8;
+    return sor_tile_geom(p, m, n, T, lag, Tb, tk, tj, ti);
+}
+
 #ifdef FR3D_EMU
+template <class ST, int C>
+inline void sor_run_tiles(Device& dev, const SorParams<ST>& P)
+{
+    const SorTileGeom G = sor_tile_geom_for(dev, P.g.p, P.g.m, P.g.n, P.T, P.lag);
+    std::vector<unsigned char> smem(sor_tile_smem<ST>(G) + 16);
+    sor_tile_run_block<ST, C>(P, G, smem.data(), 0, 1, SorSerialPar(), [](int) {});
+    dev.emu_count("fr3d_sor_tiles");
+    dev.launches++;
+}
+
 template <class ST, int C>
 inline void sor_run_c(Device& dev, const SorParams<ST>& P, unsigned*)
 {
+    if (sor_tile_applicable(dev, P)) {
+        sor_run_tiles<ST, C>(dev, P);
+        return;
+    }
     if (P.a_smooth != 1.0) {
         const int nw = sor_nl_num_waves(P);
         for (int q = 0; q < nw; ++q) {
@@ -1078,6 +1123,90 @@ inline bool sor_run_staged(Device& dev, const SorParams<ST>& Pin, unsigned* bar,
     return true;
 }
 
+// ------------------------------------------------------------------------------------------------
+// TIME-BLOCKED TILE kernel (fr3d_sor_tile.h): persistent cooperative grid, one task per thread block at a time,
+// one grid barrier per TILE wave.
+#ifndef FR3D_TILE_THREADS
+#define FR3D_TILE_THREADS 128
+#endif
+#ifndef FR3D_TILE_MINB
+#define FR3D_TILE_MINB 3
+#endif
+template <class ST, int C>
+__global__ void __launch_bounds__(FR3D_TILE_THREADS, FR3D_TILE_MINB)
+fr3d_sor_tiles(const SorParams<ST> P, const SorTileGeom G, unsigned* bar)
+{
+    extern __shared__ __align__(16) unsigned char fr3d_tile_smem[];
+    unsigned gen = 0;
+    sor_tile_run_block<ST, C>(P, G, fr3d_tile_smem, (int)blockIdx.x, (int)gridDim.x, SorBlockPar(), [&](int) {
+        ++gen;
+        fr3d_grid_barrier(bar, gen * gridDim.x);
+    });
+}
+
+template <class ST, int C>
+inline bool sor_run_tiles(Device& dev, const SorParams<ST>& P, unsigned* bar)
+{
+    const SorTileGeom G = sor_tile_geom_for(dev, P.g.p, P.g.m, P.g.n, P.T, P.lag);
+    const size_t dyn = sor_tile_smem<ST>(G);
+    if (dyn > 227 * 1024)
+        return false;
+    static bool configured = false; // per instantiation
+    if (!configured) {
+        FR3D_CUDA(cudaFuncSetAttribute(fr3d_sor_tiles<ST, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    int per_sm = 0;
+    FR3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fr3d_sor_tiles<ST, C>, FR3D_TILE_THREADS, dyn));
+    if (per_sm < 1)
+        return false;
+    if (dev.sor_ctas_per_sm > 0 && per_sm > dev.sor_ctas_per_sm)
+        per_sm = dev.sor_ctas_per_sm;
+    // the widest tile wave bounds the useful grid
+    int64_t widest = 0;
+    for (int w = 0; w < G.nwaves; ++w) {
+        int64_t cnt = 0;
+        for (int tau = 0; tau < G.ntau; ++tau) {
+            const int e = w - G.D * tau;
+            if (e >= 0 && e < G.ne)
+                cnt += sor_tile_count3(G, e);
+        }
+        widest = cnt > widest ? cnt : widest;
+    }
+    widest *= P.B;
+    int grid = dev.sm_count * per_sm;
+    if (widest < grid)
+        grid = (int)(widest < 1 ? 1 : widest);
+    FR3D_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), dev.stream));
+    SorParams<ST> Pc = P;
+    SorTileGeom Gc = G;
+    void* args[] = {(void*)&Pc, (void*)&Gc, (void*)&bar};
+    dev.span_begin("fr3d_sor_tiles");
+    FR3D_CUDA(cudaLaunchCooperativeKernel((void*)fr3d_sor_tiles<ST, C>, dim3(grid), dim3(FR3D_TILE_THREADS), args, dyn,
+                                          dev.stream));
+    dev.span_end();
+    dev.launches++;
+#ifdef FR3D_TILE_TIMING
+    {
+        unsigned long long clk[8];
+        FR3D_CUDA(cudaStreamSynchronize(dev.stream));
+        FR3D_CUDA(cudaMemcpyFromSymbol(clk, fr3d_tile_clk, sizeof(clk)));
+        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        FR3D_CUDA(cudaMemcpyToSymbol(fr3d_tile_clk, z, sizeof(z)));
+        double tot = 0;
+        for (int q = 0; q < 7; ++q)
+            tot += (double)clk[q];
+        fprintf(stderr,
+                "[tile timing] level %dx%dx%d B=%d grid=%d x %d/SM tile %dx%dx%d Tb=%d waves=%d: rowbase %.1f%% box %.1f%% "
+                "prepass %.1f%% waves %.1f%% writeback %.1f%% decode %.1f%% barrier %.1f%%  (%.0f kcycles per block)\n",
+                P.g.p, P.g.m, P.g.n, P.B, grid, per_sm, G.K, G.J, G.I, G.Tb, G.nwaves, 100 * clk[0] / tot, 100 * clk[1] / tot,
+                100 * clk[2] / tot, 100 * clk[3] / tot, 100 * clk[4] / tot, 100 * clk[5] / tot, 100 * clk[6] / tot,
+                tot / grid / 1e3);
+    }
+#endif
+    return true;
+}
+
 // Nonlinear-smoothness variant: psi and sweep tasks of a wave, one grid barrier per wave.
 template <class ST, int C>
 __global__ void __launch_bounds__(FR3D_SOR_THREADS, 2) fr3d_sor_wavefront_nl(const SorParams<ST> P, unsigned* bar)
@@ -1126,6 +1255,8 @@ inline void sor_run_c(Device& dev, const SorParams<ST>& P, unsigned* bar, int pe
         sor_run_nl<ST, C>(dev, P, bar);
         return;
     }
+    if (sor_tile_applicable(dev, P) && sor_run_tiles<ST, C>(dev, P, bar))
+        return;
     if (dev.sor_kernel == 1 && dev.sor_k1 <= 0 && sor_run_staged<ST, C>(dev, P, bar, pe_host))
         return;
     const size_t smem = (size_t)(2 * P.g.S + 1) * sizeof(int32_t);

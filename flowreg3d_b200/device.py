@@ -1,8 +1,8 @@
 """Device-memory plumbing: PyTorch tensors own the buffers, libfr3d gets raw pointers.
 
 torch is used for allocation, host<->device copies and streams only -- no torch op touches the
-data.  Under the test-suite's kernel-logic emulator (FR3D_LIBRARY_OVERRIDE, CPU-only containers)
-the same code runs with CPU tensors.
+data.  Under the test-suite's kernel-logic emulator (installed by tests/conftest.py through
+_lib._select_for_tests; CPU-only containers) the same host code runs with CPU tensors.
 """
 from __future__ import annotations
 

@@ -130,10 +130,13 @@ typedef enum {
                                    * THE ONE KNOB THAT CAN CHANGE RESULTS (by <= 1 float32 ulp). */
     FR3D_OPT_CC_BLOCK_SCANS = 2,  /* rigid pre-alignment: 1 = block-cooperative plane scans (arg-max, tile sums,
                                    * plane mean: one CTA per plane) instead of one thread per plane (0) */
-    FR3D_OPT_SOR_KERNEL = 4,      /* level solver kernel: 1 (default) = staged (cp.async.bulk + mbarrier ring per warp,
-                                   * prefetch across the wave barrier), 0 = direct-load wavefront kernel.  Same
-                                   * arithmetic in the same order: results are bit-identical */
-    FR3D_OPT_SOR_STAGES = 5       /* shared-memory stages per warp of the staged solver kernel (0 = built-in default) */
+    FR3D_OPT_SOR_KERNEL = 4,      /* level solver kernel: 2 (default) = time-blocked skewed tiles, increments resident in
+                                   * shared memory for Tb sweeps; 1 = staged wavefront (cp.async.bulk + mbarrier ring
+                                   * per warp); 0 = direct-load wavefront.  Same arithmetic, same update order:
+                                   * results are bit-identical */
+    FR3D_OPT_SOR_STAGES = 5,      /* shared-memory stages per warp of the staged solver kernel (0 = built-in default) */
+    FR3D_OPT_SOR_TILE = 6         /* tile kernel geometry: Tb | K << 8 | J << 16 | I << 24 (sweeps per time block and
+                                   * tile extents; a 0 field keeps its default: 5 sweeps, 8 x 8 x 8) */
 } fr3d_option;
 int fr3d_set_option(fr3d_ctx* ctx, int option, int64_t value);
 

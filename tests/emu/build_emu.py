@@ -3,8 +3,8 @@
 The CUDA kernels of flowreg3d_b200/csrc are functors executed one item per thread; compiled with
 -DFR3D_EMU by g++ the very same functors run as serial loops on the host.  The not-gpu tests use it
 to check kernel logic and the host-side driver against the oracle in containers without a GPU.
-The product never loads it: flowreg3d_b200/_lib.py only honours FR3D_LIBRARY_OVERRIDE, which is set
-by tests/conftest.py alone.
+The product never loads it: flowreg3d_b200/_lib.py loads flowreg3d_b200/libfr3d.so and nothing else; the emulator
+is installed by test code calling _lib._select_for_tests() in its own process (no environment variable).
 """
 import subprocess
 from pathlib import Path

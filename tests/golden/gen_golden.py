@@ -279,12 +279,82 @@ def gen_config1():
     save("config1", **d)
 
 
-def gen_xcorr():
-    """Rigid cross-correlation pre-alignment (util/xcorr_prealignment.py, sequential_3d.py:89-145).
-    scikit-image is absent here, so the live reference is run with `skimage.registration` STUBBED by the oracle's
-    restatement of phase_cross_correlation (oracle/xcorr.py): the golden pins everything the reference itself
-    does around that call (projections, 2-D resize, whitening, Hann window, scaling, sign, the six executor
-    steps), not scikit-image's arithmetic."""
+def gen_schedule():
+    """Level schedules of the LIVE reference driver (core/optical_flow_3d.py:389-408, 485-490): get_displacement is
+    run with its per-level work patched out (resize -> zeros of the requested size, warp / motion tensor / median ->
+    trivial, level_solver -> records the level size and the scaled alpha it was handed)."""
+    import json
+    rec = []
+
+    def fake_solver(J11, *a):
+        alpha_tmp = a[13]
+        rec.append((tuple(int(x) - 2 for x in J11.shape[:3]), [float(x) for x in alpha_tmp]))
+        z = np.zeros(J11.shape[:3])
+        return z, z.copy(), z.copy()
+
+    def fake_resize(img, size):
+        return np.zeros(tuple(size) + tuple(np.shape(img)[3:]), np.float64)
+
+    saved = {k: getattr(R, k) for k in ("level_solver", "resize", "imregister_wrapper", "get_motion_tensor_gc",
+                                        "median_filter")}
+    R.level_solver = fake_solver
+    R.resize = fake_resize
+    R.imregister_wrapper = lambda f2, u, v, w, f1, *a, **k: f2
+    R.get_motion_tensor_gc = lambda f1, f2, hz, hy, hx: [np.zeros(tuple(x + 2 for x in f1.shape))] * 10
+    R.median_filter = lambda a, **k: a
+    out = []
+    try:
+        cases = [((32, 512, 512), 0.8, 100, ml) for ml in (0, 2, 5, 6, 9)]
+        cases += [((64, 128, 128), 0.8, 100, ml) for ml in (0, 2, 5)]
+        cases += [((64, 256, 256), 0.8, 100, ml) for ml in (0, 5)]
+        cases += [((128, 1024, 1024), 0.8, 100, ml) for ml in (0, 2, 5)]
+        cases += [((24, 48, 56), 0.8, 100, 0), ((24, 48, 56), 0.5, 3, 0), ((16, 40, 44), 0.8, 100, 2),
+                  ((9, 9, 200), 0.8, 100, 0), ((33, 31, 17), 0.7, 100, 1), ((12, 300, 20), 0.9, 7, 3)]
+        for shape, eta, levels, ml in cases:
+            rec.clear()
+            z = np.zeros(shape + (1,))
+            R.get_displacement(z, z, alpha=(1.0, 2.0, 3.0), update_lag=1, iterations=1, min_level=ml, levels=levels,
+                               eta=eta, a_smooth=1.0, a_data=0.45)
+            out.append({"shape": list(shape), "eta": eta, "levels": levels, "min_level": ml,
+                        "sizes": [list(r[0]) for r in rec], "alpha": [r[1] for r in rec]})
+            print(shape, eta, levels, ml, "->", len(rec), "levels, finest", rec[-1][0])
+    finally:
+        for k, v in saved.items():
+            setattr(R, k, v)
+    (OUT / "schedule.json").write_text(json.dumps(out, indent=0))
+
+
+def gen_config2():
+    """BASELINE config 2: ONE frame of the 2-channel 32x512x512 recording through the live reference at OFOptions
+    defaults (normalise + Gaussian pre-filter, get_displacement with min_level 5 -> levels 8x134x134 and 10x168x168,
+    100 iterations, then the cubic compensation warp of the raw frame).  Inputs are rebuilt by the test from
+    tests_inputs (synth_volume seeds 10, 11; smooth_flow seed 1000; noise default_rng(2000)); outputs are stored on
+    every second z plane and every fourth y / x sample."""
+    sys.path.insert(0, str(OUT.parent))
+    from tests_inputs import smooth_flow
+    Z, Y, X, C = 32, 512, 512, 2
+    ref = np.stack([synth_volume((Z, Y, X), 10 + c) for c in range(C)], -1)
+    g = smooth_flow((Z, Y, X), 1000, 2.0, 12.0)
+    r64 = ref.astype(np.float64)
+    mov = R.imregister_wrapper(r64, -g[..., 0], -g[..., 1], -g[..., 2], r64, "linear")
+    mov = (mov + 0.01 * np.random.default_rng(2000).standard_normal(mov.shape)).astype(np.float32)
+    sigma = np.array([[1.0, 1.0, 1.0, 0.1]] * C)
+    fp = im3d.apply_gaussian_filter(im3d.normalize(r64, ref=None), sigma)
+    mp = im3d.apply_gaussian_filter(im3d.normalize(mov.astype(np.float64), ref=r64), sigma)
+    flow = R.get_displacement(fp, mp, alpha=(0.25,) * 3, levels=100, min_level=5, eta=0.8, update_lag=5,
+                              iterations=100, a_smooth=1.0, a_data=0.45, weight=np.full((Z, Y, X, C), 0.5))
+    f32 = flow.astype(np.float32)
+    reg = R.imregister_wrapper(mov, f32[..., 0], f32[..., 1], f32[..., 2], r64, "cubic")
+    epe = np.sqrt(((flow - g) ** 2).sum(-1))
+    print("config2: EPE of the reference vs ground truth mean %.4f max %.4f" % (epe.mean(), epe.max()))
+    save("config2", flow_s=f32[::2, ::4, ::4], reg_s=np.asarray(reg, np.float32)[::2, ::4, ::4],
+         moving_checksum=np.array([mov.astype(np.float64).sum(), float(mov[7, 11, 13, 1])]),
+         proc_s=mp[::4, ::8, ::8].astype(np.float32),
+         stats=np.array([epe.mean(), epe.max(), np.abs(flow).max()]))
+
+
+def _stub_skimage():
+    """scikit-image is absent here: stub skimage.registration.phase_cross_correlation with the oracle's restatement."""
     sys.path.insert(0, str(OUT.parent.parent))
     from oracle import xcorr as OX
     sk = types.ModuleType("skimage")
@@ -293,6 +363,50 @@ def gen_xcorr():
     sk.registration = skr
     sys.modules["skimage"] = sk
     sys.modules["skimage.registration"] = skr
+
+
+def gen_xcorr_sequence():
+    """compensate_arr_3D of the LIVE reference with cc_initialization=True over two batches (sequential executor,
+    skimage stubbed as in gen_xcorr): pins the w_init bookkeeping of that mode -- a ZERO field for the first batch, no
+    bootstrap solve (compensate_recording_3D.py:346-356), then the mean of the previous batch's flows (:481-485)."""
+    _stub_skimage()
+    from flowreg3d.motion_correction.OF_options_3D import OFOptions
+    from flowreg3d.motion_correction.compensate_recording_3D import BatchMotionCorrector, RegistrationConfig
+    import flowreg3d.motion_correction.compensate_arr_3D as mod
+    sys.path.insert(0, str(OUT.parent))
+    from scipy.ndimage import shift as ndi_shift
+    Z, Y, X, T = 12, 40, 48, 4
+    ref = synth_volume((Z, Y, X), 3)
+    rng = np.random.default_rng(7)
+    shifts = [(4.0, -3.0, 1.0), (3.5, -2.5, 0.5), (-2.0, 1.5, -1.0), (1.0, 2.0, 0.0)]
+    video = np.stack([ndi_shift(ref, shift=(s[2], s[1], s[0]), order=1, mode="nearest")
+                      + 0.002 * rng.standard_normal(ref.shape).astype(np.float32) for s in shifts], 0)
+    video = video.astype(np.float32)[..., None]
+    opts = OFOptions(alpha=(0.25, 0.25, 0.25), levels=100, min_level=2, iterations=10, update_lag=5, buffer_size=2,
+                     cc_initialization=True, cc_hw=64, cc_up=10, save_meta_info=False, output_typename=None)
+    orig = mod.BatchMotionCorrector
+
+    class _Seq(BatchMotionCorrector):
+        def __init__(self, options, config=None):
+            super().__init__(options, RegistrationConfig(parallelization="sequential", verbose=True))
+
+    mod.BatchMotionCorrector = _Seq
+    try:
+        reg, w = mod.compensate_arr_3D(video, ref[..., None], opts)
+    finally:
+        mod.BatchMotionCorrector = orig
+    print("xcorr_sequence: mean flow per frame", np.asarray(w).reshape(T, -1, 3).mean(1))
+    save("xcorr_sequence", video=video, shifts=np.array(shifts), registered=np.asarray(reg, np.float32),
+         w=np.asarray(w, np.float32))
+
+
+def gen_xcorr():
+    """Rigid cross-correlation pre-alignment (util/xcorr_prealignment.py, sequential_3d.py:89-145).
+    scikit-image is absent here, so the live reference is run with `skimage.registration` STUBBED by the oracle's
+    restatement of phase_cross_correlation (oracle/xcorr.py): the golden pins everything the reference itself
+    does around that call (projections, 2-D resize, whitening, Hann window, scaling, sign, the six executor
+    steps), not scikit-image's arithmetic."""
+    _stub_skimage()
     from flowreg3d.util.xcorr_prealignment import estimate_rigid_xcorr_3d
     from flowreg3d.motion_correction.parallelization.sequential_3d import SequentialExecutor3D
     from scipy.ndimage import shift as ndi_shift
@@ -350,6 +464,6 @@ def gen_xcorr():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["tables", "resize", "warp", "motion_tensor", "solver", "flow_small",
-                             "preprocess", "preprocess_t", "sequence", "sequence_update_ref", "config1", "xcorr"]
+                             "preprocess", "preprocess_t", "sequence", "sequence_update_ref", "config1", "config2", "schedule", "xcorr", "xcorr_sequence"]
     for w in which:
         globals()[f"gen_{w}"]()

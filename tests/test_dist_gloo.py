@@ -19,13 +19,14 @@ def _free_port():
 
 
 def _worker(rank, world, port, emu_path, tmp, cc=False):
-    os.environ["FR3D_LIBRARY_OVERRIDE"] = emu_path
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     sys.path.insert(0, str(ROOT))
     sys.path.insert(0, str(ROOT / "tests"))
     import torch.distributed as dist
     import flowreg3d_b200 as F
+    from flowreg3d_b200 import _lib
+    _lib._select_for_tests(emu_path)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     g = np.load(ROOT / "tests" / "golden" / "sequence.npz")
     opts = F.OFOptions(min_level=3, iterations=8, update_lag=4, buffer_size=5, weight=[0.5, 0.5])
@@ -35,7 +36,7 @@ def _worker(rank, world, port, emu_path, tmp, cc=False):
         opts = F.OFOptions(min_level=3, iterations=8, update_lag=4, buffer_size=5, cc_initialization=True,
                            cc_hw=(20, 24), cc_up=10)
         v, r = v[..., :1], r[..., :1]
-    reg, w, idx = F.compensate_arr_3D_sharded(v, r, opts)
+    reg, w, idx = F.compensate_arr_3D_sharded(v, r, opts, cc_prealign=cc)
     np.savez(os.path.join(tmp, f"r{rank}.npz"), reg=reg, w=w, idx=idx)
     dist.barrier()
     dist.destroy_process_group()
@@ -57,7 +58,7 @@ def test_two_rank_sharding_matches_single_process(emu_backend, tmp_path, cc):
         opts = F.OFOptions(min_level=3, iterations=8, update_lag=4, buffer_size=5, cc_initialization=True,
                            cc_hw=(20, 24), cc_up=10, output_typename=None)
         v, r = v[..., :1], r[..., :1]
-    reg1, w1 = F.compensate_arr_3D(v, r, opts)
+    reg1, w1 = F.compensate_arr_3D(v, r, opts, cc_prealign=cc)
     seen = []
     for rank in range(world):
         d = np.load(tmp_path / f"r{rank}.npz")
@@ -73,15 +74,15 @@ def test_two_rank_sharding_matches_single_process(emu_backend, tmp_path, cc):
 
 
 def _pipeline_worker(rank, world, port, emu_path, tmp, zslab=False):
-    os.environ["FR3D_LIBRARY_OVERRIDE"] = emu_path
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     sys.path.insert(0, str(ROOT))
     sys.path.insert(0, str(ROOT / "tests"))
     import torch.distributed as dist
     import flowreg3d_b200 as F
-    from flowreg3d_b200 import device as dev
+    from flowreg3d_b200 import _lib, device as dev
     from flowreg3d_b200.multigpu import get_displacement_pipelined
+    _lib._select_for_tests(emu_path)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     g = np.load(ROOT / "tests" / "golden" / "flow_small.npz")
     fixed, moving = g["fixed"][:16, :28, :32].astype(np.float32), g["moving"][:16, :28, :32].astype(np.float32)

@@ -107,9 +107,11 @@ def test_executor_with_cc_initialization_matches_live_reference(backend, golden)
 
 
 def test_sequence_with_cc_initialization(backend):
-    """compensate_arr_3D with OFOptions(cc_initialization=True): a rigid offset beyond the reach of a shallow pyramid
-    is recovered; the result equals the oracle's per-frame restatement of the executor steps chained with the
-    reference's w_init bookkeeping (bootstrap from zero, then the mean of the batch's flows)."""
+    """compensate_arr_3D with OFOptions(cc_initialization=True) and cc_prealign=True (the pre-alignment the
+    reference's executors implement, run for every frame): a rigid offset beyond the reach of a shallow pyramid is
+    recovered; the result equals the oracle's per-frame restatement of the executor steps chained with the
+    reference's w_init bookkeeping (zero field for the first batch -- no bootstrap solve --, then the mean of the
+    previous batch's flows; the chaining itself is pinned by test_sequence_with_cc_initialization_live_golden)."""
     import flowreg3d_b200 as F
     from tests_inputs import synth_volume
     shape = (12, 40, 48)
@@ -121,26 +123,43 @@ def test_sequence_with_cc_initialization(backend):
     video = np.stack([mov + 0.002 * rng.standard_normal(shape).astype(np.float32) for _ in range(3)], 0)[..., None]
     opts = F.OFOptions(alpha=(0.25, 0.25, 0.25), levels=100, min_level=2, iterations=10, update_lag=5, buffer_size=3,
                        cc_initialization=True, cc_hw=64, cc_up=10)
-    reg, w = F.compensate_arr_3D(video, ref, opts)
+    reg, w = F.compensate_arr_3D(video, ref, opts, cc_prealign=True)
     assert reg.shape == video.shape and w.shape == (3,) + shape + (3,)
     core = (slice(None), slice(3, -3), slice(8, -8), slice(8, -8))
     assert np.abs(w[core].reshape(-1, 3).mean(0) - d).max() < 0.5
-    # the same through the oracle: bootstrap (first min(22, T) frames from a zero field), then the batch
+    # the same through the oracle
     sigma = np.array([[1.0, 1.0, 1.0, 0.1]])
     ref4 = r64[..., None]
     rp = O.preprocess(ref4, sigma)
     bp = O.preprocess(video.astype(np.float64), sigma, ref4)
     params = dict(alpha=(0.25,) * 3, update_lag=5, iterations=10, min_level=2, levels=100, eta=0.8, a_smooth=1.0,
                   a_data=0.45, weight=np.ones(shape + (1,)))
-    zero = np.zeros(shape + (3,), np.float32)
-    boot = [OX.flow_with_cc_initialization(rp, bp[t], zero, params, cc_hw=64, cc_up=10)[0] for t in range(3)]
-    w_init = np.mean(np.stack(boot, 0), axis=0)
+    # compensate_recording_3D.py:346-356: with cc_initialization the first batch starts from w_init = 0 (no bootstrap)
+    w_init = np.zeros(shape + (3,), np.float32)
     for t in range(3):
         fo, _ = OX.flow_with_cc_initialization(rp, bp[t], w_init.astype(np.float32), params, cc_hw=64, cc_up=10)
         e = np.sqrt(((w[t] - fo) ** 2).sum(-1))
         assert e.mean() <= 1e-4 and e.max() <= 5e-3, (t, e.mean(), e.max())
     with pytest.raises(ValueError):
-        F.compensate_arr_3D(np.repeat(video, 2, -1), np.stack([ref, ref], -1), opts)
+        F.compensate_arr_3D(np.repeat(video, 2, -1), np.stack([ref, ref], -1), opts, cc_prealign=True)
+
+
+def test_sequence_with_cc_initialization_live_golden(backend, golden):
+    """compensate_arr_3D(cc_initialization=True) over two batches against the LIVE reference's BatchMotionCorrector
+    (tests/golden/xcorr_sequence.npz): first batch from w_init = 0 with NO bootstrap solve
+    (compensate_recording_3D.py:346-356), second batch from the mean of the first batch's flows -- and NO rigid
+    pre-alignment, because the reference pipeline never hands the cc_* keys to its executors (:301-315)."""
+    import flowreg3d_b200 as F
+    from tests_inputs import synth_volume
+    g = golden("xcorr_sequence")
+    video = g["video"]
+    ref = synth_volume(video.shape[1:4], 3)
+    opts = F.OFOptions(alpha=(0.25, 0.25, 0.25), levels=100, min_level=2, iterations=10, update_lag=5, buffer_size=2,
+                       cc_initialization=True, cc_hw=64, cc_up=10)
+    reg, w = F.compensate_arr_3D(video, ref[..., None], opts)
+    e = np.sqrt(((w.astype(np.float64) - g["w"]) ** 2).sum(-1))
+    assert e.mean() <= 1e-4 and e.max() <= 5e-3, (e.mean(), e.max())     # tolerance: 0.01 / 0.05
+    assert np.linalg.norm(reg - g["registered"]) <= 1e-5 * np.linalg.norm(g["registered"])
 
 
 def test_block_scan_option_gives_the_same_estimates(emu_backend):

@@ -30,7 +30,12 @@ ap.add_argument("--states", nargs="*", default=["f64", "f32"])
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--iterations", type=int, default=100)
 ap.add_argument("--ctas", type=int, nargs="*", default=[0])
+ap.add_argument("--kernels", type=int, nargs="*", default=[0, 2], help="0 direct wavefront, 1 staged wavefront, 2 tiles")
+ap.add_argument("--tiles", nargs="*", default=["0"], help="FR3D_OPT_SOR_TILE values Tb,K,J,I (e.g. 5,8,8,8) for kernel 2")
+ap.add_argument("--library", default=None, help="a tuning build of libfr3d.so (CUDA) instead of the in-tree one")
 args = ap.parse_args()
+if args.library:
+    _lib._select_for_tests(args.library, emulator=False)
 
 B, shape, Cn = args.batch, tuple(args.shape), args.channels
 ref = np.stack([synth_volume(shape, 10 + c) for c in range(Cn)], -1)
@@ -43,13 +48,21 @@ fp = F.FlowParams(min_level=args.min_level, a_smooth=1.0, iterations=args.iterat
 lag = 5
 
 
-def run(state, kernel, stages, ctas):
+def tile_code(spec):
+    if spec in ("0", 0):
+        return 0
+    tb, k, j, i = (int(x) for x in spec.split(","))
+    return tb | (k << 8) | (j << 16) | (i << 24)
+
+
+def run(state, kernel, stages, ctas, tile="0"):
     reg = F.Registration(shape, Cn, fp, max_batch=B, state_dtype=np.float32 if state == "f32" else np.float64)
     reg.set_reference(ref, weight=np.full(Cn, 1.0 / Cn))
     h, lib = reg.ctx.h, reg.ctx.lib
     core._check(h, lib.fr3d_set_option(h, _lib.OPT_SOR_KERNEL, kernel))
     core._check(h, lib.fr3d_set_option(h, _lib.OPT_SOR_STAGES, stages))
     core._check(h, lib.fr3d_set_option(h, _lib.OPT_SOR_CTAS_PER_SM, ctas))
+    core._check(h, lib.fr3d_set_option(h, _lib.OPT_SOR_TILE, tile_code(tile)))
     flow = reg.get_displacement(dev_frames)
     reg.sync()
     reg.ctx.profile(True)
@@ -71,20 +84,21 @@ def run(state, kernel, stages, ctas):
 
 base = {}
 for state in args.states:
-    for kernel in (0, 1):
-        for stages in (args.stages if kernel == 1 else [0]):
+    for kernel in args.kernels:
+        variants = [(st, "0") for st in args.stages] if kernel == 1 else [(0, tl) for tl in args.tiles] if kernel == 2 else [(0, "0")]
+        for stages, tile in variants:
             for ctas in args.ctas:
                 try:
-                    ms, total, gbs, flow, names, level_n = run(state, kernel, stages, ctas)
+                    ms, total, gbs, flow, names, level_n = run(state, kernel, stages, ctas, tile)
                 except Exception as e:  # report and go on: a failing variant must not hide the others
-                    print(json.dumps({"state": state, "kernel": kernel, "stages": stages, "ctas": ctas, "error": str(e)}),
-                          flush=True)
+                    print(json.dumps({"state": state, "kernel": kernel, "stages": stages, "ctas": ctas, "tile": tile,
+                                      "error": str(e)}), flush=True)
                     continue
                 if kernel == 0 and state not in base:
                     base[state] = flow
                 same = bool(np.array_equal(flow, base[state])) if state in base else None
                 dmax = float(np.abs(flow - base[state]).max()) if state in base else None
-                print(json.dumps({"state": state, "kernel": kernel, "stages": stages, "ctas": ctas,
+                print(json.dumps({"state": state, "kernel": kernel, "stages": stages, "ctas": ctas, "tile": tile,
                                   "sor_ms": round(ms, 3), "all_kernels_ms": round(total, 3),
                                   "alg_gbs": round(gbs, 1), "frac_of_6453": round(gbs / 6453.1, 4),
                                   "bit_identical_to_direct": same, "max_abs_diff": dmax, "names": names,
