@@ -56,27 +56,54 @@ def lowres_flow(seed, magnitude=2.0):
     return f * (magnitude / np.abs(f).max())
 
 
+FRAMES = ("frame_t = backwarp(R, -g_t, linear) + 0.01 N(0,1); g_t = a 4x8x8 random field (<= 2 voxels, numpy "
+          "default_rng(1000 + t)) brought to 32x512x512 by the reference's fused Gauss-cubic resize; noise from the torch "
+          "CPU generator seeded 3000 + t -- the same recipe, seeds and frame indices in both arms")
+
+
+def frame_noise(seed):
+    """0.01 N(0,1) of one frame, identical in both arms (torch CPU generator)."""
+    import torch
+    g = torch.Generator(device="cpu")
+    g.manual_seed(3000 + seed)
+    return 0.01 * torch.randn(SHAPE + (CHANNELS,), generator=g, dtype=torch.float32)
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference path, one frame per worker process
 # ------------------------------------------------------------------------------------------------
 _CPU = {}
 
 
-def _cpu_init(ref, frame):
+def _cpu_init(ref, tmpdir):
     os.environ.setdefault("OMP_NUM_THREADS", "1")
+    import torch
+    torch.set_num_threads(1)
     from oracle import oracle as O
     O.build()
     _CPU["O"] = O
     _CPU["ref"] = ref
-    _CPU["frame"] = frame
+    _CPU["tmp"] = tmpdir
     sigma = np.array([[1.0, 1.0, 1.0, 0.1]] * CHANNELS)
     _CPU["sigma"] = sigma
     _CPU["ref_proc"] = O.preprocess(ref, sigma)          # once per recording, as the reference does
 
 
-def _cpu_frame(_):
+def _cpu_prepare(t):
+    """Frame t of the workload (untimed): the recipe of FRAMES with the oracle's resize and linear warp."""
+    O, ref = _CPU["O"], _CPU["ref"]
+    lr = lowres_flow(1000 + t)
+    g = [O.imresize_fused_gauss_cubic3D(lr[q].astype(np.float64), SHAPE) for q in range(3)]
+    frame = O.imregister_wrapper(ref, -g[0], -g[1], -g[2], ref, "linear")
+    frame = (np.asarray(frame, np.float32) + frame_noise(1000 + t).numpy()).astype(np.float32)
+    np.save(os.path.join(_CPU["tmp"], f"frame{t}.npy"), frame)
+    return t
+
+
+def _cpu_frame(t):
     O = _CPU["O"]
-    ref, frame = _CPU["ref"], _CPU["frame"]
+    ref = _CPU["ref"]
+    frame = np.load(os.path.join(_CPU["tmp"], f"frame{t}.npy"))
     mp_ = O.preprocess(frame[None], _CPU["sigma"], ref)[0]
     flow = O.get_displacement(_CPU["ref_proc"], mp_, alpha=(0.25,) * 3, update_lag=5, iterations=100,
                               min_level=5, levels=100, eta=0.8, a_smooth=1.0, a_data=0.45,
@@ -95,27 +122,25 @@ def cpu_cores():
     return max(1, min(n, 64))
 
 
-def cpu_frame_inputs():
-    from oracle import oracle as O
-    from tests_inputs import smooth_flow
-    ref = make_reference().astype(np.float64)
-    g = smooth_flow(SHAPE, 1000, 2.0, 12.0)
-    frame = O.imregister_wrapper(ref, -g[..., 0], -g[..., 1], -g[..., 2], ref, "linear")
-    return ref, frame
-
-
 def run_cpu(steps, warmup, cores=None):
-    """Returns (frames/s, cores, seconds per step).  Each step: `cores` frames, one per worker."""
+    """Returns (frames/s, cores, seconds per step).  Each step: frames 0 .. cores-1 of the workload, one per worker."""
+    import shutil
+    import tempfile
     cores = cores or cpu_cores()
-    ref, frame = cpu_frame_inputs()
+    ref = make_reference().astype(np.float64)
+    tmp = tempfile.mkdtemp(prefix="fr3d_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores, initializer=_cpu_init, initargs=(ref, frame)) as pool:
-        for _ in range(warmup):
-            pool.map(_cpu_frame, range(cores))
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            pool.map(_cpu_frame, range(cores))
-        dt = time.perf_counter() - t0
+    try:
+        with ctx.Pool(cores, initializer=_cpu_init, initargs=(ref, tmp)) as pool:
+            pool.map(_cpu_prepare, range(cores))             # synthetic inputs, not timed
+            for _ in range(warmup):
+                pool.map(_cpu_frame, range(cores))
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                pool.map(_cpu_frame, range(cores))
+            dt = time.perf_counter() - t0
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
     return cores * steps / dt, cores, dt / max(steps, 1)
 
 
@@ -194,11 +219,18 @@ def algorithmic_bytes(name, plan_levels, B, C, iters, lag):
     return None
 
 
-# ncu `dram__bytes_read.sum + dram__bytes_write.sum` of the two fr3d_sor_wavefront<double,2> launches of a step at
-# B = 16 (profiles/r01_sor_dram_traffic_b16_f64.csv: 8x134x134 level 32.50 + 9.68 GB in 14.08 ms, 10x168x168 level
-# 70.47 + 20.28 GB in 24.05 ms), per frame and level voxel.  Valid for the default solver (100 sweeps, lag 5,
-# float64 state, lexicographic order) only.
-SOR_NCU_DRAM_BYTES_PER_FRAME_VOXEL = (32.505e9 + 9.676e9 + 70.472e9 + 20.279e9) / (16 * (8 * 134 * 134 + 10 * 168 * 168))
+def measured_traffic(kernel, state, B, level_n):
+    """ncu `dram__bytes_read.sum + dram__bytes_write.sum` per launch of the dominant kernel, from the summary of an
+    `ncu --set full` capture of THIS build (profiles/r02_sor_traffic.json, written by tools/ncu_traffic.py from the
+    .ncu-rep): bytes per frame and level voxel for the kernel / solver state it was captured with; None if the
+    profile does not match what is being benched."""
+    f = ROOT / "profiles" / "r02_sor_traffic.json"
+    if not f.exists():
+        return None, None
+    t = json.loads(f.read_text())
+    if t.get("kernel") != kernel or t.get("state") != state:
+        return None, None
+    return round(t["dram_bytes_per_frame_voxel"] * B * float(np.mean(level_n))), t.get("source")
 
 
 def run_gpu(args):
@@ -237,7 +269,7 @@ def run_gpu(args):
     B = args.batch
     Z, Y, X = SHAPE
     C = CHANNELS
-    core.STATE_DTYPE = np.float32 if args.state == "f32" else np.float64
+    core.STATE_DTYPE = {"f32": np.float32, "f64": np.float64, "auto": "auto"}[args.state]
     core.SWEEP = 1 if args.sweep == "redblack" else 0
     ref = make_reference()
     opts = F.OFOptions(buffer_size=B)        # defaults: alpha .25, 100 it, lag 5, min_level 5, cubic, weight [.5,.5]
@@ -260,26 +292,25 @@ def run_gpu(args):
                 merged[name] = (a_ + cnt, b_ + tot)
         return merged
 
-    # synthetic frames, generated ON the GPU with the library's own resize + linear warp (not timed):
-    # frame_t = backwarp(R, -g_t) + 0.01 N(0,1), g_t a smooth random field of <= 2 voxels
+    # synthetic frames (not timed), the recipe of FRAMES: the resize and the linear warp run through the library's own
+    # kernels (bit-equal / <= 1 ulp to the oracle's, which the CPU arm uses), the noise comes from the same torch CPU
+    # generator in both arms; frame index t = rank * 7919 + set * B + b
     ctxb = core.bare_context(device)
     ref_dev = dev.to_device(ref, device)
     n_sets = 2
     sets = []
-    gen = torch.Generator(device=device)
     for s in range(n_sets):
         frames = torch.empty((B, Z, Y, X, C), dtype=torch.float32, device=device)
         for b in range(B):
-            seed = 1000 + 7919 * rank + s * B + b
-            lr = lowres_flow(seed)
-            g = np.stack([core.resize(lr[q], SHAPE) for q in range(3)], 0).astype(np.float64)
+            t_idx = 7919 * rank + s * B + b
+            lr = lowres_flow(1000 + t_idx)
+            g = np.stack([core.resize(lr[q].astype(np.float64), SHAPE) for q in range(3)], 0).astype(np.float64)
             u, v, w = (dev.to_device(-g[q], device) for q in range(3))
             out = frames[b]
             core._check(ctxb.h, ctxb.lib.fr3d_warp(ctxb.h, dev.ptr(ref_dev), 0, dev.ptr(u), dev.ptr(v), dev.ptr(w),
                                                    dev.ptr(ref_dev), 0, Z, Y, X, C, 1, dev.ptr(out)))
             ctxb.sync()
-            gen.manual_seed(2000 + seed)
-            frames[b] += 0.01 * torch.randn(frames[b].shape, generator=gen, device=device)
+            frames[b] += frame_noise(1000 + t_idx).to(device)
         sets.append(frames)
     host_sets = [s.cpu().pin_memory() for s in sets]
     out_reg = [torch.empty((B, Z, Y, X, C), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -332,13 +363,56 @@ def run_gpu(args):
     barrier()
     ms_e2e = e0.elapsed_time(e1)
 
-    t = torch.tensor([ms, ms_e2e, float(launches)], dtype=torch.float64, device=device)
+    # ---- copy ceiling: the same pinned buffers and byte counts, both directions concurrently, NO compute --------
+    # (what e2e could reach at best on this box; on multi-GPU nodes the host memory / PCIe path is shared)
+    s_ci, s_co = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    d_reg = torch.empty((B, Z, Y, X, C), dtype=torch.float32, device=device)
+    d_flow = torch.empty((B, Z, Y, X, 3), dtype=torch.float32, device=device)
+    d_in = torch.empty((B, Z, Y, X, C), dtype=torch.float32, device=device)
+
+    def copy_steps(n):
+        main_s = torch.cuda.current_stream(device)
+        s_ci.wait_stream(main_s)
+        s_co.wait_stream(main_s)
+        for i in range(n):
+            with torch.cuda.stream(s_ci):
+                d_in.copy_(host_sets[i % n_sets], non_blocking=True)
+            with torch.cuda.stream(s_co):
+                out_flow[i % 2].copy_(d_flow, non_blocking=True)
+                out_reg[i % 2].copy_(d_reg, non_blocking=True)
+        main_s.wait_stream(s_ci)
+        main_s.wait_stream(s_co)
+
+    copy_steps(1)
+    barrier()
+    e0.record()
+    copy_steps(args.steps)
+    e1.record()
+    barrier()
+    ms_copy = e0.elapsed_time(e1)
+    del d_reg, d_flow, d_in
+
+    # ---- the one-call public entry point with PAGEABLE numpy in / out (single GPU only: host memory) ------------
+    arr_api = None
+    if world == 1 and not args.no_arr_api:
+        video = np.concatenate([h.numpy() for h in host_sets], 0)          # (2B, Z, Y, X, C) pageable copy
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        reg_np, w_np = F.compensate_arr_3D(video, ref, F.OFOptions(buffer_size=B))
+        dt = time.perf_counter() - t0
+        arr_api = {"value": round(video.shape[0] / dt, 3), "unit": "volumes/s", "frames": int(video.shape[0]),
+                   "what": "flowreg3d_b200.compensate_arr_3D(video, reference, OFOptions(buffer_size=B)) with pageable "
+                           "numpy in and out, wall clock of the whole call (context + reference pyramid + w_init "
+                           "bootstrap + internal pinned staging + results copied into fresh numpy arrays)"}
+        del reg_np, w_np, video
+
+    t = torch.tensor([ms, ms_e2e, float(launches), ms_copy], dtype=torch.float64, device=device)
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms, ms_e2e, launches = float(tmax[0]), float(tmax[1]), int(tsum[2])
+        ms, ms_e2e, launches, ms_copy = float(tmax[0]), float(tmax[1]), int(tsum[2]), float(tmax[3])
     frames_total = B * world * args.steps
 
     if rank == 0:
@@ -360,6 +434,8 @@ def run_gpu(args):
         top_name = [n for n in prof if n.replace("fr3d::", "") == top["kernel"]][0]
         ab = algorithmic_bytes(top_name, level_n, B, C, opts.iterations, opts.update_lag)
         ach = None if ab is None else ab / (prof[top_name][1] / prof[top_name][0] * 1e-3) / 1e9
+        state_used = "f64" if reg.plan.plan.state_dtype == 1 else "f32"
+        traffic, traffic_src = measured_traffic(top["kernel"], state_used, B, level_n)
         line = {
             "metric": "volumes/s (32x512x512, 2 channels)", "value": round(frames_total / (ms * 1e-3), 3),
             "unit": "volumes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -370,7 +446,8 @@ def run_gpu(args):
                        "sharding": f"frames x{world}, one all-reduce of w_init per batch" if world > 1 else "single GPU",
                        "solver_sweep": "lexicographic (wavefront schedule, reference order)" if args.sweep == "lexicographic"
                                        else "red-black (opt-in; NOT the reference order, outside its parity tolerance)",
-                       "solver_state": f"{args.state} increments, f64 system matrix",
+                       "solver_state": f"{state_used} increments ({args.state}), f64 system matrix and arithmetic",
+                       "frames": FRAMES,
                        "streams": f"{len(ctxs)} (batch split into {len(ctxs)} concurrent parts; per-kernel times in "
                                   "'kernels' are event-bracketed on each part's stream and include time shared with the other part)"
                                   if len(ctxs) > 1 else "1",
@@ -379,17 +456,21 @@ def run_gpu(args):
                        "host_affinity": f"rank 0 bound to {len(bound)} GPU-local cores" if bound else "unchanged"},
             "e2e": {"value": round(frames_total / (ms_e2e * 1e-3), 3), "unit": "volumes/s",
                     "h2d_bytes_per_step": int(B * Z * Y * X * C * 4),
-                    "d2h_bytes_per_step": int(B * Z * Y * X * (C + 3) * 4)},
+                    "d2h_bytes_per_step": int(B * Z * Y * X * (C + 3) * 4),
+                    "api": "SequenceCorrector.run_pipelined (the streaming call compensate_arr_3D is built on), pinned "
+                           "host batches in, pinned host results out, copies inside the timed region",
+                    "copy_ceiling_volumes_per_s": round(frames_total / (ms_copy * 1e-3), 3),
+                    "frac_of_copy_ceiling": round(ms_copy / ms_e2e, 4),
+                    "copy_ceiling": "the same buffers and bytes per step copied H2D and D2H concurrently with no "
+                                    "compute, max over ranks (the node's host path is shared by all GPUs)",
+                    "compensate_arr_3D_pageable": arr_api},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": top["kernel"], "achieved": None if ach is None else round(ach, 1),
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": None if ach is None else round(ach / peak, 4),
                          "frac_of_nominal_8TBs": None if ach is None else round(ach / 8000.0, 4),
-                         "traffic": (round(SOR_NCU_DRAM_BYTES_PER_FRAME_VOXEL * B * float(np.mean(level_n)))
-                                     if top["kernel"].startswith("fr3d_sor_wavefront") and args.state == "f64"
-                                     and args.sweep == "lexicographic" and opts.iterations == 100 else None),
-                         "traffic_source": "ncu dram bytes per launch (profiles/r01_sor_dram_traffic_b16_f64.csv), mean of the two levels",
+                         "traffic": traffic, "traffic_source": traffic_src,
                          "share_of_step": top["share"]},
             "kernels": table[:8],
             "cpu_baseline": cpu,
@@ -410,7 +491,7 @@ def run_reference_arm(args):
         "unit": "volumes/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(sec * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step": cores},
+        "config": {"workload": WORKLOAD, "frames_per_step": cores, "frames": FRAMES},
         "cpu_baseline": {"value": round(v, 4), "unit": "volumes/s", "cores": cores, "kind": "port",
                          "sample": f"each step = {cores} frames of the workload, one per worker process "
                                    "(oracle port of the reference CPU path: pre-filter + get_displacement + cubic warp)"},
@@ -429,11 +510,13 @@ def main():
                     help="frames per GPU per step (OFOptions.buffer_size; 25 = the 200-frame recording of config 2 "
                          "in 8 batches, or one batch per GPU at 8 GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-arr-api", action="store_true", help="skip the pageable compensate_arr_3D measurement")
     ap.add_argument("--streams", type=int, default=1, help="concurrent half-batch pipelines per GPU")
     ap.add_argument("--sweep", default="lexicographic", choices=["lexicographic", "redblack"],
                     help="solver sweep order; only lexicographic reproduces the reference")
-    ap.add_argument("--state", default="f64", choices=["f64", "f32"],
-                    help="storage precision of the solver increments (f64 = strict parity mode)")
+    ap.add_argument("--state", default="auto", choices=["auto", "f64", "f32"],
+                    help="storage precision of the solver increments: auto (the package default: f32 when min_level "
+                         ">= 2, i.e. here), f64 (reference to float64 rounding), f32")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -101,6 +101,10 @@ def load():
         "fr3d_level_state": (ci, [vp, ci, ci, vp, i64, i64]),
         "fr3d_level_sweeps_slab": (ci, [vp, ci, ci, ci, ci, ci]),
         "fr3d_level_planes": (ci, [vp, ci, ci, vp, ci, ci]),
+        "fr3d_ipc_export": (ci, [vp, ci, vp]),
+        "fr3d_ipc_open": (ci, [vp, vp, C.POINTER(vp)]),
+        "fr3d_ipc_close": (ci, [vp, vp]),
+        "fr3d_level_sweeps_slab_p2p": (ci, [vp, ci, ci, ci, vp, vp, vp, vp, i64]),
         "fr3d_level_wave_cells": (ci, [vp, ci, ci, vp, ci, ci]),
         "fr3d_level_end": (ci, [vp, ci]),
         "fr3d_level_end_range": (ci, [vp, ci, ci, ci]),
@@ -150,6 +154,7 @@ EXPORTED_SYMBOLS = [
     "fr3d_warp_flow", "fr3d_cc_project", "fr3d_cc_window", "fr3d_cc_cgemm", "fr3d_cc_cross_power",
     "fr3d_cc_abs_argmax", "fr3d_cc_wrap_shift", "fr3d_cc_tile_sums", "fr3d_rigid_flow", "fr3d_add_flow",
     "fr3d_level_sweeps_slab", "fr3d_level_planes", "fr3d_level_wave_cells",
+    "fr3d_ipc_export", "fr3d_ipc_open", "fr3d_ipc_close", "fr3d_level_sweeps_slab_p2p",
 ]
 
 

@@ -19,11 +19,31 @@ from . import _lib, device as dev
 from .plan import FlowParams, PlanHolder, SWEEP_LEXICOGRAPHIC, make_tables
 
 
-# Storage precision of the solver state (du,dv,dw and the constant Laplacian term) used when a caller
-# does not choose.  float64 (default) reproduces the reference to float64 rounding; float32 is the
-# reduced-traffic mode: measured 1e-5 / 4e-4 voxel mean / max EPE against the reference at
-# min_level 2 and 1e-4 / 1.1e-2 at min_level 0 (tolerance 0.01 / 0.05).
-STATE_DTYPE = np.float64
+# Storage precision of the solver state (du,dv,dw and the constant Laplacian term) used when a caller does not
+# choose: "auto" | numpy.float64 | numpy.float32.  The arithmetic and the system matrix are float64 either way.
+#   float64 reproduces the reference to float64 rounding (0.0 EPE against the live reference at config 2);
+#   float32 is the storage SURVEY 7.3-D calls parity-safe and 8(d) budgets (108 B / voxel / sweep): it moves 24 %
+#   fewer bytes (solver 53 -> 44 ms per 25 config-2 frames).  Measured against the LIVE reference at the published
+#   sizes (tests/test_gpu_published_sizes.py): config 2 (min_level 5) mean 2.3e-6 / max 2.6e-3 voxel, corrected volume
+#   1.7e-6 relative L2; config 4 reduced (min_level 2) 7.2e-5 / 4.5e-3 -- tolerance 0.01 / 0.05 / 1e-4.  With the
+#   pyramid solved down to full resolution the rounding accumulates over more and finer levels (min_level 0 at
+#   32x512x512: max 0.048 against the float64 state), so
+#   "auto" = float32 when the effective min_level is >= 2 (the OFOptions default is 5), float64 below.
+STATE_DTYPE = "auto"
+AUTO_F32_FROM_MIN_LEVEL = 2
+
+
+def resolve_state_dtype(choice, shape, params: FlowParams):
+    """numpy dtype of the solver state for `choice` (None = the module default)."""
+    if choice is None:
+        choice = STATE_DTYPE
+    if isinstance(choice, str) and choice == "auto":
+        from .plan import level_schedule
+        _, eff_min_level = level_schedule(tuple(int(s) for s in shape), params.eta, params.levels, params.min_level)
+        return np.float32 if eff_min_level >= AUTO_F32_FROM_MIN_LEVEL else np.float64
+    return np.dtype(choice).type
+
+
 # Sweep order of the level solver used when a caller does not choose: SWEEP_LEXICOGRAPHIC (wavefront
 # schedule, reproduces the reference) or plan.SWEEP_REDBLACK (checkerboard; opt-in, not reference-exact).
 SWEEP = SWEEP_LEXICOGRAPHIC
@@ -50,8 +70,9 @@ class Context:
         self.plan = plan
         h = C.c_void_p()
         idx = self.device.index if self.device.type == "cuda" else 0
+        self.stream_handle = _stream_handle(self.device)   # the library launches everything on this stream
         rc = self.lib.fr3d_create(C.byref(h), idx or 0, C.byref(plan.plan) if plan is not None else None,
-                                  _stream_handle(self.device))
+                                  self.stream_handle)
         if rc != 0:
             msg = self.lib.fr3d_last_error(None)
             raise _lib.Fr3dError(rc, msg.decode() if msg else "?")
@@ -70,6 +91,18 @@ class Context:
 
     def sync(self):
         _check(self.h, self.lib.fr3d_synchronize(self.h))
+
+    def order_with_torch(self):
+        """Make work that torch (NCCL collectives, copies) enqueues next see the library's kernels, and vice versa.
+        The library launches on the stream that was current when the context was created; when that is still torch's
+        current stream, stream order already does it and nothing happens -- otherwise fall back to a synchronisation
+        of both streams."""
+        if self.device.type != "cuda":
+            return
+        cur = torch.cuda.current_stream(self.device)
+        if cur.cuda_stream != self.stream_handle:
+            cur.synchronize()
+            self.sync()
 
     def profile(self, on: bool):
         _check(self.h, self.lib.fr3d_profile_enable(self.h, 1 if on else 0))
@@ -126,7 +159,7 @@ class Registration:
         self.plan = PlanHolder(self.shape, self.C, params, max_batch=max_batch,
                                interp=3 if meth == "cubic" else 1, sigma=sigma,
                                sweep=SWEEP if sweep is None else sweep,
-                               state_dtype=STATE_DTYPE if state_dtype is None else state_dtype)
+                               state_dtype=resolve_state_dtype(state_dtype, self.shape, params))
         self.ctx = Context(self.plan, device)
         self.device = self.ctx.device
         self._ref_raw = None
@@ -537,7 +570,7 @@ def _pair_registration(shape, Cn, fp: FlowParams) -> Registration:
     device = dev.default_device()
     key = (shape, Cn, tuple(float(a) for a in fp.alpha), int(fp.update_lag), int(fp.iterations), int(fp.min_level),
            int(fp.levels), float(fp.eta), float(fp.a_smooth), tuple(np.asarray(fp.a_data, float).ravel().tolist()),
-           np.dtype(STATE_DTYPE).str, int(SWEEP), str(device), str(_lib.library_path()))
+           np.dtype(resolve_state_dtype(None, shape, fp)).str, int(SWEEP), str(device), str(_lib.library_path()))
     reg = _PAIR_CACHE.pop(key, None)
     if reg is None or reg.ctx.h is None:
         reg = Registration(shape, Cn, fp, max_batch=1, device=device)

@@ -128,6 +128,7 @@ struct fr3d_ctx {
     Buf<char> L, d, U, dold; // (B, npad) Vec4 of the state dtype
     Buf<double> psi_c, psi_r;
     Buf<unsigned> bar;
+    Buf<unsigned> p2p_flags; // z-slab halo flags written by the z-neighbours (fr3d_ipc_export which = 1)
     DevTable stage_tab[3];
     std::unique_ptr<HPGeom> stage_hp; // geometry cache of fr3d_sor_level
     // level-by-level execution state (fr3d_level_begin / _sweeps / _end / fr3d_flow_finish)
@@ -502,6 +503,28 @@ static void sor_launch(fr3d_ctx* c, int state_dtype, int t0 = -1, int t1 = -1, i
     else
         sor_launch_t<float>(c, t0, t1, q0, q1, k0, k1);
 }
+
+#ifndef FR3D_EMU
+template <class ST>
+static void sor_launch_p2p_t(fr3d_ctx* c, int k0, int k1, void* lo_d, void* hi_d, void* lo_flags, void* hi_flags,
+                             int64_t flag_base)
+{
+    SorParams<ST> P = sor_params<ST>(c);
+    FR3D_REQUIRE(!P.redblack && P.a_smooth == 1.0, "z-slab sweeps need the lexicographic sweep with a_smooth == 1");
+    FR3D_REQUIRE(k0 >= 0 && k0 < k1 && k1 <= P.g.p, "bad plane range [%d, %d) of %d", k0, k1, P.g.p);
+    FR3D_REQUIRE((lo_d == nullptr) == (lo_flags == nullptr) && (hi_d == nullptr) == (hi_flags == nullptr),
+                 "a neighbour needs both its increment array and its flag words");
+    FR3D_REQUIRE(c->p2p_flags.p != nullptr, "export the flag words first (fr3d_ipc_export which = 1)");
+    SorPeers<ST> pr;
+    pr.lo_d = (Vec4<ST>*)lo_d;
+    pr.hi_d = (Vec4<ST>*)hi_d;
+    pr.lo_flag = lo_flags ? (unsigned*)lo_flags + 1 : nullptr; // the lower neighbour's "from my upper neighbour" word
+    pr.hi_flag = hi_flags ? (unsigned*)hi_flags + 0 : nullptr; // the upper neighbour's "from my lower neighbour" word
+    pr.my_flags = c->p2p_flags.p;
+    pr.base = (unsigned)flag_base;
+    sor_run_p2p_any(c->dev, P, c->bar.ensure(c->dev, 4), c->sp_hp->pe_host.data(), k0, k1, pr);
+}
+#endif
 
 static void run_sor(fr3d_ctx* c, int state_dtype, const HPGeom& hp, int B, int C, const float* f1, const float* f2,
                     int f2f32, const double* Jpre, const double* uvw, const double* whp, double hz, double hy,
@@ -1083,6 +1106,95 @@ int fr3d_level_sweeps_slab(fr3d_ctx* ctx, int level, int q_begin, int q_end, int
     FR3D_REQUIRE(_c->run_level == level, "level %d is not open", level);
     FR3D_REQUIRE(k_end > 0, "empty plane range");
     sor_launch(_c, _c->state_dtype, 0, _c->iterations, q_begin, q_end, k_begin, k_end);
+    FR3D_API_END()
+}
+
+// ---- z-slab solve with the halo exchange inside the kernel (peer memory over NVLink, CUDA IPC) ----------------------
+int fr3d_ipc_export(fr3d_ctx* ctx, int which, void* handle_out)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(handle_out && (which == 0 || which == 1), "bad argument");
+#ifdef FR3D_EMU
+    FR3D_THROW(FR3D_ERR_ARG, "CUDA IPC is not available in the kernel-logic emulator");
+#else
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    void* p = nullptr;
+    if (which == 0) {
+        // reserve the increment array for the largest level once, so that the handle (and the neighbours' mappings
+        // of it) stay valid for the life of the context: the buffer is grow-only and would otherwise move
+        size_t need = 0;
+        for (auto& L : _c->levels) {
+            const size_t n = (size_t)_c->max_batch * L->hp.npad *
+                             (_c->state_dtype == FR3D_F64 ? sizeof(Vec4<double>) : sizeof(Vec4<float>));
+            need = n > need ? n : need;
+        }
+        FR3D_REQUIRE(need > 0, "the context has no plan");
+        if (_c->d.cap < need) {
+            FR3D_REQUIRE(_c->run_level < 0, "export the increment array before a level is opened");
+            _c->d.ensure(_c->dev, need);
+        }
+        p = _c->d.p;
+    } else {
+        if (!_c->p2p_flags.p) {
+            _c->p2p_flags.ensure(_c->dev, 16);
+            _c->dev.zero(_c->p2p_flags.p, 16 * sizeof(unsigned));
+            FR3D_CUDA(cudaStreamSynchronize(_c->dev.stream));
+        }
+        p = _c->p2p_flags.p;
+    }
+    cudaIpcMemHandle_t h;
+    FR3D_CUDA(cudaIpcGetMemHandle(&h, p));
+    memcpy(handle_out, &h, sizeof(h));
+#endif
+    FR3D_API_END()
+}
+
+int fr3d_ipc_open(fr3d_ctx* ctx, const void* handle, void** ptr_out)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(handle && ptr_out, "bad argument");
+#ifdef FR3D_EMU
+    FR3D_THROW(FR3D_ERR_ARG, "CUDA IPC is not available in the kernel-logic emulator");
+#else
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    FR3D_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *ptr_out = p;
+#endif
+    FR3D_API_END()
+}
+
+int fr3d_ipc_close(fr3d_ctx* ctx, void* ptr)
+{
+    FR3D_API_BEGIN(ctx)
+#ifdef FR3D_EMU
+    (void)ptr;
+    FR3D_THROW(FR3D_ERR_ARG, "CUDA IPC is not available in the kernel-logic emulator");
+#else
+    if (ptr) {
+        FR3D_CUDA(cudaStreamSynchronize(_c->dev.stream));
+        FR3D_CUDA(cudaIpcCloseMemHandle(ptr));
+    }
+#endif
+    FR3D_API_END()
+}
+
+int fr3d_level_sweeps_slab_p2p(fr3d_ctx* ctx, int level, int k_begin, int k_end, void* lo_d, void* hi_d, void* lo_flags,
+                               void* hi_flags, int64_t flag_base)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(_c->run_level == level, "level %d is not open", level);
+#ifdef FR3D_EMU
+    (void)k_begin, (void)k_end, (void)lo_d, (void)hi_d, (void)lo_flags, (void)hi_flags, (void)flag_base;
+    FR3D_THROW(FR3D_ERR_ARG, "the peer-memory halo exchange needs CUDA devices");
+#else
+    FR3D_REQUIRE(_c->sp_hp != nullptr, "no level solve has been prepared");
+    if (_c->state_dtype == FR3D_F64)
+        sor_launch_p2p_t<double>(_c, k_begin, k_end, lo_d, hi_d, lo_flags, hi_flags, flag_base);
+    else
+        sor_launch_p2p_t<float>(_c, k_begin, k_end, lo_d, hi_d, lo_flags, hi_flags, flag_base);
+#endif
     FR3D_API_END()
 }
 

@@ -47,15 +47,24 @@ namespace fr3d {
 // Neighbour loads through L1 are safe because (i) a wave only writes hyperplanes of its own parity
 // while neighbours live on hyperplanes of the other parity, (ii) the voxel's own value bypasses L1,
 // and (iii) every CTA executes a gpu-scope fence (which invalidates its SM's L1) at the wave barrier.
+#ifndef FR3D_SOR_F32_MINB
+#define FR3D_SOR_F32_MINB 3
+#endif
+#ifndef FR3D_SOR_F64_MINB
+#define FR3D_SOR_F64_MINB 2
+#endif
+#ifndef FR3D_SOR_F64_PAIR
+#define FR3D_SOR_F64_PAIR 1
+#endif
 template <class ST>
 struct SorTune;
 template <>
 struct SorTune<double> {
-    static constexpr int kPair = 1, kMinBlocks = 2, kNbrCa = 1;
+    static constexpr int kPair = FR3D_SOR_F64_PAIR, kMinBlocks = FR3D_SOR_F64_MINB, kNbrCa = 1;
 };
 template <>
 struct SorTune<float> {
-    static constexpr int kPair = 0, kMinBlocks = 3, kNbrCa = 0;
+    static constexpr int kPair = 0, kMinBlocks = FR3D_SOR_F32_MINB, kNbrCa = 0;
 };
 
 template <class ST>
@@ -308,16 +317,45 @@ FR3D_HD void sor_load(const SorParams<ST>& P, const SorLoc& L, int b, bool with_
     }
 }
 
+// Device-side halo exchange of the z-slab solve (one process per GPU, peer memory over NVLink): the increment arrays
+// and the flag words of the two z-neighbours, opened through CUDA IPC.  A voxel on the slab's lowest / highest plane
+// is stored to the neighbour's copy of the level as well; flags carry "waves completed" (monotonic over launches).
+template <class ST>
+struct SorPeers {
+    Vec4<ST>* lo_d = nullptr;     // increments of the rank that owns the planes below k_begin (nullptr: none)
+    Vec4<ST>* hi_d = nullptr;     // ... above k_end - 1
+    unsigned* lo_flag = nullptr;  // lower neighbour's "my upper neighbour has finished wave" word
+    unsigned* hi_flag = nullptr;  // upper neighbour's "my lower neighbour has finished wave" word
+    unsigned* my_flags = nullptr; // [0]: written by my lower neighbour, [1]: by my upper neighbour
+    unsigned base = 0;            // flag value before this launch's first wave
+};
+
+template <class ST, bool SLAB>
+FR3D_HD void sor_store(const SorParams<ST>& P, int b, int64_t a, const Vec4<ST>& v, int k, int kb, int ke,
+                       const SorPeers<ST>* pr)
+{
+    const int64_t at = (int64_t)b * P.g.npad + a;
+    st4_cg(P.d + at, v);
+    if (SLAB && pr) {
+        if (k == kb && pr->lo_d)
+            st4_cg(pr->lo_d + at, v);
+        if (k == ke - 1 && pr->hi_d)
+            st4_cg(pr->hi_d + at, v);
+    }
+}
+
 // Update the lane's voxel in every frame of the item.
 // SLAB (z-slab multi-GPU solve): only voxels of the planes kb <= k < ke are updated.  It is a separate
 // instantiation (and the plane range travels outside SorParams) so that the full solve's kernel is untouched.
 template <class ST, int C, bool SLAB = false>
-FR3D_HD void sor_process(const SorParams<ST>& P, const SorLoc& L, int kb = 0, int ke = 0)
+FR3D_HD void sor_process(const SorParams<ST>& P, const SorLoc& L, int kb = 0, int ke = 0,
+                         const SorPeers<ST>* pr = nullptr)
 {
     if (L.n0 < 0)
         return; // pad slot
+    int k = 0;
     if (SLAB) {
-        const int k = P.g.perm[L.a] / (P.g.m * P.g.n); // perm = natural index (k*m + j)*n + i
+        k = P.g.perm[L.a] / (P.g.m * P.g.n); // perm = natural index (k*m + j)*n + i
         if (k < kb || k >= ke)
             return; // another rank's plane
     }
@@ -340,7 +378,7 @@ FR3D_HD void sor_process(const SorParams<ST>& P, const SorLoc& L, int kb = 0, in
 #pragma unroll
             for (int e = 0; e < 9; ++e)
                 FR3D_STCG(AB + e * 32, r.A[e]);
-            st4_cg(P.d + (int64_t)b * np + a, sor_update(P, r));
+            sor_store<ST, SLAB>(P, b, a, sor_update(P, r), k, kb, ke, pr);
         }
         return;
     }
@@ -353,12 +391,12 @@ FR3D_HD void sor_process(const SorParams<ST>& P, const SorLoc& L, int kb = 0, in
             sor_load(P, L, b + e, true, r[e]);
 #pragma unroll
         for (int e = 0; e < 2; ++e)
-            st4_cg(P.d + (int64_t)(b + e) * np + a, sor_update(P, r[e]));
+            sor_store<ST, SLAB>(P, b + e, a, sor_update(P, r[e]), k, kb, ke, pr);
     }
     for (; b < L.b1; ++b) {
         SorIn<ST> r;
         sor_load(P, L, b, true, r);
-        st4_cg(P.d + (int64_t)b * np + a, sor_update(P, r));
+        sor_store<ST, SLAB>(P, b, a, sor_update(P, r), k, kb, ke, pr);
     }
 }
 
@@ -706,6 +744,46 @@ __device__ __forceinline__ void fr3d_grid_barrier(unsigned* ctr, unsigned target
     __syncthreads();
 }
 
+// L2 prefetch of the streamed inputs of a located item (the warp's NEXT item, while the current one is processed):
+// the pre-combined system (chunk-major: 2304 contiguous bytes per frame) and the voxels' own increments, or, for a
+// psi-refresh item, the 10C motion-tensor planes and the Laplacian term.  prefetch.global.L2 holds no register and no
+// scoreboard entry, so the bytes in flight per SM are no longer bounded by the register file; the demand loads of
+// the next item then find their lines in L2.  Neighbour increments were written one wave ago and are not prefetched.
+// MEASURED AND REJECTED (B200, config 2, B = 25, results/r02_sor_experiments.md): 55.3 vs 53.2 ms (float64 state),
+// 50.1 vs 44.6 ms (float32 state) -- more bytes in flight make the kernel slower, i.e. it is not waiting for
+// latency that a deeper queue could hide.  Kept off by default as a build option.
+#ifndef FR3D_SOR_PREFETCH
+#define FR3D_SOR_PREFETCH 0
+#endif
+template <class ST, int C>
+__device__ __forceinline__ void sor_prefetch_item(const SorParams<ST>& P, const SorLoc& L, int lane)
+{
+#if FR3D_SOR_PREFETCH
+    const int64_t np = P.g.npad;
+    const int64_t a0 = L.a - lane; // first slot of the chunk
+    for (int b = L.b0; b < L.b1; ++b) {
+        const char* own = reinterpret_cast<const char*>(P.d + (int64_t)b * np + a0);
+        constexpr int kOwnLines = 32 * (int)sizeof(Vec4<ST>) / 128;
+        if (!L.refresh) {
+            const char* ab = reinterpret_cast<const char*>(P.AB + sor_ab_at(P, b, a0, 0));
+            if (lane < 18)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ab + lane * 128));
+            else if (lane < 18 + kOwnLines)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(own + (lane - 18) * 128));
+        } else {
+            const double* Jb = P.J + (int64_t)b * C * 10 * np + a0;
+            for (int li = lane; li < C * 10 * 2; li += 32)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(Jb + (int64_t)(li >> 1) * np) + (li & 1) * 128));
+            const char* Lp = reinterpret_cast<const char*>(P.L + (int64_t)b * np + a0);
+            if (lane < kOwnLines)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(own + lane * 128));
+            else if (lane < 2 * kOwnLines)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(Lp + (lane - kOwnLines) * 128));
+        }
+    }
+#endif
+}
+
 // Persistent cooperative kernel: all waves of one level solve, one grid barrier per wave.
 // Dynamic shared memory: copies of the pe / start tables (tabs_in_smem) so that locating an item
 // costs shared-memory latency only.
@@ -742,8 +820,10 @@ fr3d_sor_wavefront(const SorParams<ST> P, unsigned* bar, int tabs_in_smem)
                 const int next = item + stride;
                 const bool more = next < w.items;
                 SorLoc nxt;
-                if (more)
+                if (more) {
                     nxt = sor_locate(P, tb, q, w, next, lane); // neighbour-table loads fly during the update below
+                    sor_prefetch_item<ST, C>(P, nxt, lane);
+                }
                 sor_process<ST, C, SLAB>(P, cur, kb, ke);
                 if (!more)
                     break;
@@ -753,6 +833,145 @@ fr3d_sor_wavefront(const SorParams<ST> P, unsigned* bar, int tabs_in_smem)
         }
         ++gen;
         fr3d_grid_barrier(bar, gen * gridDim.x);
+    }
+}
+
+// z-slab solve with the halo exchange INSIDE the persistent kernel: every rank sweeps its own planes wave by wave;
+// a boundary-plane voxel is written to the z-neighbour's memory as it is produced (peer store over NVLink), and after
+// every wave the ranks hand each other a "wave q done" flag.  One launch per level instead of one launch, two pack
+// kernels, a host synchronisation and an NCCL message pair per wave.
+//   wave end:  all stores of the CTA -> __syncthreads -> thread 0: system-scope fence, arrive on the local counter,
+//              wait for all CTAs;  block 0 then publishes base + q + 1 in both neighbours' flag words;
+//   wave start: thread 0 of every CTA waits until both of its own flag words have reached base + q (the neighbours'
+//              boundary values of wave q - 1 are then in this GPU's memory), fences, releases the CTA.
+__device__ __forceinline__ void sor_p2p_wait(volatile unsigned* flag, unsigned target)
+{
+    long long t0 = 0;
+    while ((int)(*flag - target) < 0) {
+        if (t0 == 0)
+            t0 = clock64();
+        else if (clock64() - t0 > 40000000000LL)
+            __trap(); // ~20 s: a neighbour died or the ranks disagree on the schedule -- fail instead of hanging
+    }
+}
+template <class ST, int C>
+__global__ void __launch_bounds__(FR3D_SOR_THREADS, SorTune<ST>::kMinBlocks)
+fr3d_sor_wavefront_p2p(const SorParams<ST> P, unsigned* bar, int tabs_in_smem, int kb, int ke, const SorPeers<ST> pr)
+{
+    extern __shared__ int32_t fr3d_sor_smem[];
+    SorTabs tb{P.g.pe, P.g.start};
+    if (tabs_in_smem) {
+        const int S = P.g.S;
+        for (int i = threadIdx.x; i < S; i += blockDim.x)
+            fr3d_sor_smem[i] = P.g.pe[i];
+        for (int i = threadIdx.x; i <= S; i += blockDim.x)
+            fr3d_sor_smem[S + i] = P.g.start[i];
+        __syncthreads();
+        tb.pe = fr3d_sor_smem;
+        tb.start = fr3d_sor_smem + S;
+    }
+    const int wpb = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int stride = gridDim.x * wpb;
+    unsigned gen = 0;
+    for (int q = P.q_begin; q < P.q_end; ++q) {
+        if (q > P.q_begin) {
+            // the neighbours' boundary values of wave q - 1
+            if (threadIdx.x == 0) {
+                const unsigned target = pr.base + (unsigned)(q - P.q_begin);
+                if (pr.lo_d)
+                    sor_p2p_wait(pr.my_flags + 0, target);
+                if (pr.hi_d)
+                    sor_p2p_wait(pr.my_flags + 1, target);
+                __threadfence_system();
+            }
+            __syncthreads();
+        }
+        const SorWave w = sor_wave(P, tb, q);
+        int item = blockIdx.x * wpb + warp;
+        if (item < w.items) {
+            SorLoc cur = sor_locate(P, tb, q, w, item, lane);
+            for (;;) {
+                const int next = item + stride;
+                const bool more = next < w.items;
+                SorLoc nxt;
+                if (more)
+                    nxt = sor_locate(P, tb, q, w, next, lane);
+                sor_process<ST, C, true>(P, cur, kb, ke, &pr);
+                if (!more)
+                    break;
+                cur = nxt;
+                item = next;
+            }
+        }
+        ++gen;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();                  // this CTA's local and peer stores, before it counts as arrived
+            atomicAdd(bar, 1u);
+            while (*((volatile unsigned*)bar) < gen * gridDim.x) {
+            }
+            __threadfence();
+            if (blockIdx.x == 0) {
+                const unsigned done = pr.base + (unsigned)(q - P.q_begin) + 1u;
+                __threadfence_system();
+                if (pr.lo_flag)
+                    *((volatile unsigned*)pr.lo_flag) = done;
+                if (pr.hi_flag)
+                    *((volatile unsigned*)pr.hi_flag) = done;
+            }
+        }
+        __syncthreads();
+    }
+    // do not leave while a neighbour may still be storing its last wave into this GPU's arrays
+    if (threadIdx.x == 0 && P.q_end > P.q_begin) {
+        const unsigned target = pr.base + (unsigned)(P.q_end - P.q_begin);
+        if (pr.lo_d)
+            sor_p2p_wait(pr.my_flags + 0, target);
+        if (pr.hi_d)
+            sor_p2p_wait(pr.my_flags + 1, target);
+        __threadfence_system();
+    }
+}
+
+template <class ST, int C>
+inline void sor_run_p2p(Device& dev, const SorParams<ST>& P, unsigned* bar, int peak_items, int kb, int ke,
+                        const SorPeers<ST>& pr)
+{
+    const size_t smem = (size_t)(2 * P.g.S + 1) * sizeof(int32_t);
+    const int tabs_in_smem = smem <= 40 * 1024;
+    const size_t dyn = tabs_in_smem ? smem : 0;
+    int per_sm = 0;
+    FR3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fr3d_sor_wavefront_p2p<ST, C>, FR3D_SOR_THREADS, dyn));
+    FR3D_REQUIRE(per_sm >= 1, "the z-slab solver kernel does not fit on an SM");
+    const int wpb = FR3D_SOR_THREADS / 32;
+    int64_t want = ((int64_t)peak_items + wpb - 1) / wpb;
+    int grid = dev.sm_count * per_sm;
+    if (want < grid)
+        grid = (int)(want < 1 ? 1 : want);
+    FR3D_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), dev.stream));
+    SorParams<ST> Pc = P;
+    SorPeers<ST> prc = pr;
+    int tis = tabs_in_smem;
+    void* args[] = {(void*)&Pc, (void*)&bar, (void*)&tis, (void*)&kb, (void*)&ke, (void*)&prc};
+    dev.span_begin("fr3d_sor_wavefront_p2p");
+    FR3D_CUDA(cudaLaunchCooperativeKernel((void*)fr3d_sor_wavefront_p2p<ST, C>, dim3(grid), dim3(FR3D_SOR_THREADS), args,
+                                          dyn, dev.stream));
+    dev.span_end();
+    dev.launches++;
+}
+
+template <class ST>
+inline void sor_run_p2p_any(Device& dev, const SorParams<ST>& P, unsigned* bar, const int32_t* pe_host, int kb, int ke,
+                            const SorPeers<ST>& pr)
+{
+    const int peak = sor_peak_items(P.g.S, P.T, P.B, P.fg, pe_host, 0);
+    switch (P.C) {
+    case 1: sor_run_p2p<ST, 1>(dev, P, bar, peak, kb, ke, pr); break;
+    case 2: sor_run_p2p<ST, 2>(dev, P, bar, peak, kb, ke, pr); break;
+    case 3: sor_run_p2p<ST, 3>(dev, P, bar, peak, kb, ke, pr); break;
+    case 4: sor_run_p2p<ST, 4>(dev, P, bar, peak, kb, ke, pr); break;
+    default: FR3D_THROW(FR3D_ERR_ARG, "unsupported channel count %d", P.C);
     }
 }
 

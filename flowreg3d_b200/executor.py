@@ -70,11 +70,17 @@ def flow_params_from_dict(d: dict) -> Tuple[FlowParams, object]:
 class B200Executor3D(_Base):
     """GPU batch executor (one process per GPU; frames of a batch run concurrently)."""
 
-    def __init__(self, n_workers: Optional[int] = None, max_batch: int = 16, device: Optional[torch.device] = None):
+    def __init__(self, n_workers: Optional[int] = None, max_batch: int = 16, device: Optional[torch.device] = None,
+                 state_dtype=np.float64):
+        """state_dtype: storage of the solver increments.  float64 by default HERE (the package default is "auto"):
+        an executor whose name ends in "3d" is held to the reference's cross-executor consistency test
+        (tests/motion_correction/test_parallelization.py:152-198, rtol 1e-5 against sequential3d), which float32
+        increments do not meet."""
         super().__init__(n_workers=1)
         self.name = "b2003d"
         self.max_batch = int(max_batch)
         self.device = device
+        self.state_dtype = state_dtype
         self._reg: Optional[Registration] = None
         self._key = None
         self._ref_token = None
@@ -140,6 +146,10 @@ class B200Executor3D(_Base):
         RuntimeContext.register_parallelization_executor("b2003d", cls)
         return True
 
+    def invalidate_reference(self):
+        """Forget the cached fixed volume: the next process_batch uploads it and rebuilds its pyramid."""
+        self._ref_token = None
+
     # -- internals ------------------------------------------------------------------------
     def _registration(self, shape, Cn, fp: FlowParams, interpolation_method) -> Registration:
         meth = str(getattr(interpolation_method, "value", interpolation_method)).lower()
@@ -148,7 +158,7 @@ class B200Executor3D(_Base):
         if self._reg is None or key != self._key:
             self.cleanup()
             self._reg = Registration(shape, Cn, fp, max_batch=self.max_batch, interpolation_method=meth,
-                                     device=self.device)
+                                     device=self.device, state_dtype=self.state_dtype)
             self._key = key
         return self._reg
 
@@ -156,9 +166,17 @@ class B200Executor3D(_Base):
         rp = np.asarray(reference_proc)
         rr = np.asarray(reference_raw)
         w = None if weight is None else np.asarray(weight)
-        token = (rp.__array_interface__["data"][0], rp.shape, float(rp.reshape(-1)[:: max(1, rp.size // 4096)].sum()),
-                 rr.__array_interface__["data"][0],
-                 None if w is None else (w.shape, float(w.reshape(-1)[:: max(1, w.size // 4096)].sum())))
+        # content tokens: the full sum (one pass over the array, ~10 ms per 100 MB) plus a strided sample -- an
+        # in-place edit of the reference, or a new array that numpy placed at a freed address, changes them; callers
+        # that rewrite the reference in a way sums cannot see can call invalidate_reference()
+
+        def tok(a):
+            if a is None:
+                return None
+            f = a.reshape(-1)
+            return (a.shape, str(a.dtype), float(f.sum(dtype=np.float64)),
+                    float(f[:: max(1, f.size // 65536)].sum(dtype=np.float64)))
+        token = (tok(rp), tok(rr), tok(w))
         if token != self._ref_token:
             if rp.ndim == 3:
                 rp = rp[..., None]

@@ -97,12 +97,21 @@ def _level_info(reg: Registration, li: int):
     return tuple(size), int(S.value), int(nslots.value), start
 
 
+def _require_ctx_stream(reg: Registration):
+    """The NCCL calls below are ordered against the library's kernels by STREAM ORDER: both must run on the stream the
+    Registration was created under."""
+    if reg.device.type == "cuda" and torch.cuda.current_stream(reg.device).cuda_stream != reg.ctx.stream_handle:
+        raise RuntimeError("call the multi-GPU solves under the CUDA stream the Registration was created on "
+                           "(torch.cuda.current_stream() differs from the context's stream)")
+
+
 def get_displacement_pipelined(reg: Registration, moving_proc, uvw=None, group=None, out_dtype=np.float32,
                                min_slots: int = 1 << 21, n_chunks: int = 8,
                                out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """get_displacement for B frames with the level solves pipelined over the ranks of `group`.
     Every rank must call with identical arguments; every rank returns the full result.
     min_slots: levels with fewer solver slots (x frames) are solved redundantly without communication."""
+    _require_ctx_stream(reg)
     lib, h = reg.ctx.lib, reg.ctx.h
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -192,9 +201,11 @@ _PAIR_GROUPS: dict = {}
 
 
 def _pair_group(group, world: int, a: int, b: int):
-    """Process group of the neighbouring ranks (a, b).  new_group is collective over the parent group, so the
-    groups of ALL neighbouring pairs are created together, once, in the same order on every rank."""
-    key = (id(group), world)
+    """Process group of the neighbouring ranks (a, b).  torch.distributed.new_group is collective over the DEFAULT
+    group: the groups of ALL neighbouring pairs are created together, once, in the same order, and EVERY rank of the
+    default group must make the first call for a given `group` (a proper subgroup used by only some ranks would hang
+    there -- create the Registration's pair groups from all ranks first).  Cached per set of member ranks."""
+    key = tuple(_global_rank(group, r) for r in range(world))
     if key not in _PAIR_GROUPS:
         pairs = {}
         for r in range(world - 1):
@@ -217,8 +228,53 @@ def _global_rank(group, r: int) -> int:
 # ------------------------------------------------------------------------------------------------------------------
 # z-slab decomposition with halo exchange (the decomposition SURVEY.md 8(e) / the north star names).
 # ------------------------------------------------------------------------------------------------------------------
+class _SlabPeers:
+    """CUDA-IPC plumbing of the device-side halo exchange, set up once per Registration: this rank's increment array
+    (reserved for the largest level, so that it never moves) and its flag words are exported, the handles all-gathered,
+    and the two z-neighbours' buffers mapped (peer access over NVLink).  The mappings live as long as the
+    Registration."""
+
+    def __init__(self, reg: Registration, group):
+        self.reg, self.group = reg, group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.flag_base = 0
+        self.flags = self._exchange(1)            # neighbour rank -> mapped pointer
+        self.incr = self._exchange(0)
+        self._token = torch.zeros(1, dtype=torch.int32, device=reg.device)
+
+    def _exchange(self, which: int) -> dict:
+        """Export this rank's buffer `which`, all-gather the handles, map the two z-neighbours'."""
+        lib, h = self.reg.ctx.lib, self.reg.ctx.h
+        mine = (C.c_ubyte * 64)()
+        _check(h, lib.fr3d_ipc_export(h, which, mine))
+        t = torch.tensor(list(mine), dtype=torch.uint8, device=self.reg.device)
+        allh = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(allh, t, group=self.group)
+        out = {}
+        for r in (self.rank - 1, self.rank + 1):
+            if 0 <= r < self.world:
+                raw = (C.c_ubyte * 64)(*allh[r].cpu().tolist())
+                ptr = C.c_void_p()
+                _check(h, lib.fr3d_ipc_open(h, raw, C.byref(ptr)))
+                out[r] = ptr.value
+        return out
+
+    def stream_rendezvous(self):
+        """Stream-ordered rendezvous (no host synchronisation): kernels enqueued after it start only when every
+        rank's stream has passed this point, i.e. when every rank has finished preparing (zeroing) its arrays."""
+        dist.all_reduce(self._token, group=self.group)
+
+    def close(self):
+        lib, h = self.reg.ctx.lib, self.reg.ctx.h
+        for p in list(self.flags.values()) + list(self.incr.values()):
+            lib.fr3d_ipc_close(h, C.c_void_p(p))
+        self.flags, self.incr = {}, {}
+
+
 def get_displacement_zslab(reg: Registration, moving_proc, uvw=None, group=None, out_dtype=np.float32,
-                           min_slots: int = 1 << 21, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                           min_slots: int = 1 << 21, out: Optional[torch.Tensor] = None,
+                           p2p: Optional[bool] = None, stats: Optional[dict] = None) -> torch.Tensor:
     """get_displacement for B frames with every large level solved on z-slabs: rank r owns the planes
     [z_r, z_{r+1}) of the level and runs, wave by wave, the sweeps of its planes only
     (`fr3d_level_sweeps_slab`).  A voxel of wave q = (k+j+i) + 2t reads nothing newer than wave q-1, so after every
@@ -231,7 +287,24 @@ def get_displacement_zslab(reg: Registration, moving_proc, uvw=None, group=None,
     This is the straightforward version (host-driven: one kernel launch and one message pair per wave); it exists for
     levels whose state does not fit one GPU and as the baseline for a fused exchange.  For volumes that do fit,
     `get_displacement_pipelined` needs ~8 messages per level instead of ~2 400 and is the faster choice today
-    (DESIGN.md section 6).  Every rank must call with identical arguments; every rank returns the full result."""
+    (DESIGN.md section 6).  Every rank must call with identical arguments; every rank returns the full result.
+
+    p2p (default: on CUDA devices): the halo exchange runs INSIDE the persistent solver kernel -- the ranks map each
+    other's increment arrays through CUDA IPC, a boundary-plane voxel is stored into the z-neighbour's memory as it
+    is produced (NVLink peer store) and one flag word per neighbour and wave replaces the message pair
+    (`fr3d_level_sweeps_slab_p2p`): one launch per level.  p2p=False is the host-driven exchange described above
+    (the only one the CPU emulator / gloo tests can run).
+    stats: optional dict that receives wall-clock milliseconds per phase (begin = pyramid level, warp, assembly --
+    replicated on every rank; sweeps; gather = slabs of the increments to every rank; end = median on own planes +
+    flow slabs); measuring synchronises after every phase."""
+    _require_ctx_stream(reg)
+    import time as _time
+
+    def _mark(name, t0):
+        if stats is not None:
+            reg.sync()
+            stats[name] = stats.get(name, 0.0) + (_time.perf_counter() - t0) * 1e3
+        return _time.perf_counter()
     lib, h = reg.ctx.lib, reg.ctx.h
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -247,12 +320,23 @@ def get_displacement_zslab(reg: Registration, moving_proc, uvw=None, group=None,
     slabbable = reg.plan.plan.sweep == 0 and float(reg.plan.plan.a_smooth) == 1.0
     nl = lib.fr3d_level_count(h)
     keep = []
+    if p2p is None:
+        p2p = reg.device.type == "cuda"
+    peers = None
+    if p2p and world > 1 and slabbable:
+        peers = getattr(reg, "_slab_peers", None)
+        if peers is None or peers.group is not group:
+            peers = reg._slab_peers = _SlabPeers(reg, group)
     for li in range(nl):
+        tm = _time.perf_counter()
         _check(h, lib.fr3d_level_begin(h, li, dev.ptr(mv), dev.ptr(uv), B))
         (pz, py, px), S, nslots, _ = _level_info(reg, li)
+        tm = _mark("begin", tm)
         if world == 1 or not slabbable or pz < world or nslots * B < min_slots:
             _check(h, lib.fr3d_level_sweeps(h, li, -1, -1, -1, -1))      # redundant on every rank, no exchange
+            tm = _mark("sweeps_replicated", tm)
             _check(h, lib.fr3d_level_end(h, li))
+            tm = _mark("end_replicated", tm)
             continue
         bounds = [_split(pz, world, r) for r in range(world)]
         z0, z1 = bounds[rank]
@@ -261,7 +345,7 @@ def get_displacement_zslab(reg: Registration, moving_proc, uvw=None, group=None,
         def planes_out(k0, k1):
             buf = dev.empty((B, (k1 - k0) * plane, 4), state_dt, reg.device)
             _check(h, lib.fr3d_level_planes(h, li, 0, dev.ptr(buf), k0, k1))
-            reg.sync()                                       # the buffer leaves through torch.distributed
+            reg.ctx.order_with_torch()                       # the buffer leaves through torch.distributed
             return buf
 
         def planes_in(buf, k0, k1):
@@ -270,12 +354,20 @@ def get_displacement_zslab(reg: Registration, moving_proc, uvw=None, group=None,
         def cells_out(k, q):
             buf = torch.zeros((B, T * py, 4), dtype=dev.torch_dtype(state_dt), device=reg.device)
             _check(h, lib.fr3d_level_wave_cells(h, li, 0, dev.ptr(buf), k, q))
-            reg.sync()                                       # the buffer leaves through torch.distributed
+            reg.ctx.order_with_torch()                       # the buffer leaves through torch.distributed
             return buf
 
         lo = _global_rank(group, rank - 1) if rank > 0 else None
         hi = _global_rank(group, rank + 1) if rank + 1 < world else None
-        for q in range(S + 2 * (T - 1)):
+        if peers is not None:
+            # device-side exchange: one launch for all waves of the level
+            vp = C.c_void_p
+            peers.stream_rendezvous()
+            _check(h, lib.fr3d_level_sweeps_slab_p2p(
+                h, li, z0, z1, vp(peers.incr.get(rank - 1)), vp(peers.incr.get(rank + 1)),
+                vp(peers.flags.get(rank - 1)), vp(peers.flags.get(rank + 1)), peers.flag_base))
+            peers.flag_base += S + 2 * (T - 1)
+        for q in range(S + 2 * (T - 1) if peers is None else 0):
             _check(h, lib.fr3d_level_sweeps_slab(h, li, q, q + 1, z0, z1))
             # halo: only the cells of the boundary planes that this wave updated (one anti-diagonal per sweep in
             # flight: <= T*py cells instead of py*px)
@@ -297,6 +389,7 @@ def get_displacement_zslab(reg: Registration, moving_proc, uvw=None, group=None,
             for rb, k in recvs:
                 _check(h, lib.fr3d_level_wave_cells(h, li, 1, dev.ptr(rb), k, q))
             keep = keep[-8:]
+        tm = _mark("sweeps_slab", tm)
         # gather the slabs of the finished increments: every rank needs them around its planes for the median
         for r, (a, b) in enumerate(bounds):
             buf = planes_out(a, b) if r == rank else dev.empty((B, (b - a) * plane, 4), state_dt, reg.device)
@@ -304,16 +397,20 @@ def get_displacement_zslab(reg: Registration, moving_proc, uvw=None, group=None,
             if r != rank:
                 planes_in(buf, a, b)
             keep.append(buf)
+        tm = _mark("gather", tm)
         _check(h, lib.fr3d_level_end_range(h, li, z0, z1))
         for r, (a, b) in enumerate(bounds):
             slab = dev.empty((B, 3, b - a, py, px), np.float64, reg.device)
             if r == rank:
                 _check(h, lib.fr3d_flow_slab(h, li, 0, dev.ptr(slab), a, b))
-                reg.sync()
+                reg.ctx.order_with_torch()
             dist.broadcast(slab, src=_global_rank(group, r), group=group)
             if r != rank:
                 _check(h, lib.fr3d_flow_slab(h, li, 1, dev.ptr(slab), a, b))
             keep.append(slab)
+        tm = _mark("end_slab", tm)
+    tm = _time.perf_counter()
     _check(h, lib.fr3d_flow_finish(h, dev.ptr(out), reg._code(out)))
+    _mark("finish", tm)
     reg._keep = [mv, uv, keep]
     return out

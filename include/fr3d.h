@@ -203,6 +203,20 @@ int fr3d_level_planes(fr3d_ctx* ctx, int level, int direction, void* ext, int k_
 /* The cells of plane k that wave q updated (one anti-diagonal per sweep in flight) out of (0) / into (1) `ext`
  * (device, B x iterations x py 4-vectors; entries without a cell are not touched): the per-wave halo message. */
 int fr3d_level_wave_cells(fr3d_ctx* ctx, int level, int direction, void* ext, int k, int q);
+/* The same z-slab solve with the halo exchange INSIDE the persistent kernel (one launch per level instead of one
+ * launch + two pack kernels + a host synchronisation + a message pair per wave).  One process per GPU; the increment
+ * array of the open level (which = 0) and a pair of flag words (which = 1) are shared with the z-neighbours through
+ * CUDA IPC: fr3d_ipc_export fills a 64-byte cudaIpcMemHandle_t, fr3d_ipc_open maps a neighbour's handle (peer access
+ * over NVLink), fr3d_ipc_close unmaps it.  fr3d_level_sweeps_slab_p2p runs ALL waves of the level on the planes
+ * [k_begin, k_end): a voxel on plane k_begin / k_end - 1 is also stored into lo_d / hi_d (the neighbours' arrays),
+ * and after every wave the ranks publish flag_base + (waves done) in each other's flag words and wait for their own.
+ * flag_base must be the same on all ranks and grow by the level's wave count from launch to launch (the words are
+ * never reset).  lo_* / hi_* are NULL for the first / last slab.  No reference counterpart. */
+int fr3d_ipc_export(fr3d_ctx* ctx, int which, void* handle_out);
+int fr3d_ipc_open(fr3d_ctx* ctx, const void* handle, void** ptr_out);
+int fr3d_ipc_close(fr3d_ctx* ctx, void* ptr);
+int fr3d_level_sweeps_slab_p2p(fr3d_ctx* ctx, int level, int k_begin, int k_end, void* lo_d, void* hi_d, void* lo_flags,
+                               void* hi_flags, int64_t flag_base);
 int fr3d_level_end(fr3d_ctx* ctx, int level);
 /* fr3d_level_end restricted to the planes z_begin <= z < z_end of the level's flow (the median of a plane needs
  * the increments of two planes on either side, which every rank holds); the other planes of the flow are then

@@ -30,7 +30,9 @@ ap.add_argument("--min-level", type=int, default=0)
 ap.add_argument("--iterations", type=int, default=100)
 ap.add_argument("--chunks", type=int, default=8)
 ap.add_argument("--zslab", action="store_true", help="z-slab decomposition with per-wave halo exchange instead of the "
-                "sweep pipeline (not yet run on GPUs: expect it to be slow, it is host-driven)")
+                "sweep pipeline (device-side exchange over peer memory unless --host-exchange)")
+ap.add_argument("--host-exchange", action="store_true", help="z-slabs with the host-driven NCCL exchange per wave")
+ap.add_argument("--state", default="f64", choices=["f64", "f32"])
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -42,7 +44,8 @@ ref = np.stack([synth_volume(shape, 10 + c) for c in range(C)], -1)
 mov = np.roll(ref, (0, 2, -3), (0, 1, 2)) + 0.01 * np.random.default_rng(0).standard_normal(ref.shape).astype(np.float32)
 fp = F.FlowParams(alpha=(0.25,) * 3, update_lag=5, iterations=args.iterations, min_level=args.min_level, levels=100,
                   eta=0.8, a_smooth=1.0, a_data=0.45)
-reg = F.Registration(shape, C, fp, max_batch=1, device=device)
+reg = F.Registration(shape, C, fp, max_batch=1, device=device,
+                     state_dtype=np.float32 if args.state == "f32" else np.float64)
 reg.set_reference(ref.astype(np.float32))
 mv = torch.from_numpy(mov.astype(np.float32)[None]).to(device)
 
@@ -67,15 +70,19 @@ def timed(fn, reps):
 t1, single = timed(lambda: reg.get_displacement(mv), 2)
 if args.zslab:
     from flowreg3d_b200.multigpu import get_displacement_zslab
-    tn, piped = timed(lambda: get_displacement_zslab(reg, mv), 1)
+    tn, piped = timed(lambda: get_displacement_zslab(reg, mv, p2p=not args.host_exchange), 1 if args.host_exchange else 2)
 else:
     tn, piped = timed(lambda: get_displacement_pipelined(reg, mv, n_chunks=args.chunks), 2)
 same = bool(torch.equal(single, piped))
+stats = {}
+if args.zslab:
+    get_displacement_zslab(reg, mv, p2p=not args.host_exchange, stats=stats)   # one more pass with phase timers
+
 if rank == 0:
     print(json.dumps({"case": f"single volume {shape}x{C}, min_level {args.min_level}, {args.iterations} sweeps",
                       "levels": [list(s) for _, s in reg.plan.sched], "n_gpus": world,
-                      "mode": "zslab" if args.zslab else "sweep-pipelined", "ms_one_gpu": round(t1, 2), "ms_pipelined": round(tn, 2), "speedup": round(t1 / tn, 3),
-                      "bit_identical": same}))
+                      "mode": ("zslab, host-driven exchange" if args.host_exchange else "zslab, device-side exchange (peer stores + flags)") if args.zslab else "sweep-pipelined", "state": args.state, "ms_one_gpu": round(t1, 2), "ms_pipelined": round(tn, 2), "speedup": round(t1 / tn, 3),
+                      "bit_identical": same, "phase_ms_rank0": {k: round(v, 2) for k, v in stats.items()}}))
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()
