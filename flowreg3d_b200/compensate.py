@@ -88,6 +88,9 @@ class SequenceCorrector:
         fp = flow_params_from_options(options)
         mb = int(max_batch or options.buffer_size)
         kw = dict(interpolation_method=getattr(options, "interpolation_method", "cubic"), sigma=options.sigma)
+        cc_wanted = bool(getattr(options, "cc_initialization", False)) and bool(cc_prealign)
+        if cc_wanted or bool(getattr(options, "update_reference", False)):
+            streams = 1     # both couple the frames of a batch through one context: one stream per GPU
         if int(streams) > 1 and mb > 1:
             self.reg = SplitRegistration(self.shape, Cn, fp, max_batch=mb, n_streams=int(streams), device=device, **kw)
         else:
@@ -109,8 +112,6 @@ class SequenceCorrector:
             # full (Z,Y,X,C) weight array with the channel axis)
             raise ValueError("shape-mismatch for sum: cc_initialization supports single-channel recordings only, "
                              "as in the reference")
-        if self.cc and isinstance(self.reg, SplitRegistration):
-            raise NotImplementedError("cc_initialization is implemented for one stream per GPU")
         # weights (compensate_recording_3D.py:211-224)
         wvec = [options.get_weight_at(c, Cn) for c in range(Cn)]
         if all(np.ndim(w) == 0 for w in wvec):
@@ -126,12 +127,8 @@ class SequenceCorrector:
         # the reference normalises the fixed volume against ITS OWN range (normalization_ref=None);
         # that is the same (lo, den) as above
         self.update_reference = bool(getattr(options, "update_reference", False))
-        if self.update_reference and (self.world > 1 or isinstance(self.reg, SplitRegistration)):
-            raise NotImplementedError("update_reference re-averages the fixed volume from all frames of a batch; it "
-                                      "is implemented for one process / one stream only")
-        if self.world > 1 and self.reg.plan.temporal:
-            raise NotImplementedError("a temporal pre-filter (sigma_t >= 0.125) couples the frames of a batch; it is "
-                                      "not implemented for batches sharded over several GPUs")
+        # frames of temporal-filter reach around a shard (sigma_t >= 0.125 couples the frames of a batch)
+        self.temporal_halo = int(max(self.reg.plan.plan.gauss_radius_t[c] for c in range(Cn))) if self.reg.plan.temporal else 0
         self._weight = weight
         self._ref_proc64 = (dev.empty((1, Z, Y, X, Cn), np.float64, self.device)
                             if (self.update_reference or self.cc) else None)
@@ -164,22 +161,38 @@ class SequenceCorrector:
         part = torch.zeros((Z, Y, X, 3), dtype=torch.float32, device=self.device)
         if flows is not None and flows.shape[0] > 0:
             part = self.reg.mean_frames(flows) * float(flows.shape[0])
-            self.reg.sync()
+            if isinstance(self.reg, SplitRegistration):
+                self.reg.sync()
+            else:
+                self.reg.ctx.order_with_torch()      # stream order, no host synchronisation
         torch.distributed.all_reduce(part, op=torch.distributed.ReduceOp.SUM, group=self.group)
         return part / float(count)
 
     # -- one batch ------------------------------------------------------------------------
     def process_batch(self, raw_local, global_size: Optional[int] = None, local_offset: int = 0,
-                      compensate: bool = True):
+                      compensate: bool = True, halo_before=None, halo_after=None):
         """raw_local: this rank's frames (t,Z,Y,X,C) of the current batch (ndarray or device tensor);
         global_size / local_offset place them in the global batch (defaults: single process).
+        halo_before / halo_after: with a temporal pre-filter (sigma_t >= 0.125) and a batch sharded over ranks, the up
+        to `self.temporal_halo` frames of the SAME batch that precede / follow this rank's frames (the filter couples
+        the frames of a batch, image_processing_3D.py:140-156; at the ends of the batch scipy's reflection applies).
         Returns device tensors (registered float32 (t,Z,Y,X,C), flows float32 (t,Z,Y,X,3))."""
         raw = self.reg._as_dev(raw_local, None, None)
         t = raw.shape[0]
         G = t if global_size is None else int(global_size)
-        proc64 = (dev.empty(tuple(raw.shape), np.float64, self.device)
-                  if ((self.update_reference or self.cc) and t > 0) else None)
-        proc = self.reg.preprocess(raw, self.lo, self.den, out64=proc64) if t > 0 else None
+        want64 = (self.update_reference or self.cc) and t > 0
+        nb = 0 if halo_before is None else int(np.shape(halo_before)[0])
+        na = 0 if halo_after is None else int(np.shape(halo_after)[0])
+        if t > 0 and (nb or na):
+            parts = ([self.reg._as_dev(halo_before, None, None)] if nb else []) + [raw] + \
+                    ([self.reg._as_dev(halo_after, None, None)] if na else [])
+            ext = torch.cat([p_.to(raw.dtype) for p_ in parts], 0)
+            e64 = dev.empty(tuple(ext.shape), np.float64, self.device) if want64 else None
+            proc = self.reg.preprocess(ext, self.lo, self.den, out64=e64)[nb:nb + t]
+            proc64 = e64[nb:nb + t] if want64 else None
+        else:
+            proc64 = dev.empty(tuple(raw.shape), np.float64, self.device) if want64 else None
+            proc = self.reg.preprocess(raw, self.lo, self.den, out64=proc64) if t > 0 else None
         if self.w_init is None and self.cc_zero_start:
             # compensate_recording_3D.py:346-356: with cc_initialization the chain starts from a ZERO field and no
             # bootstrap frames are solved (the rigid estimate of every frame replaces the bootstrap)
@@ -210,13 +223,28 @@ class SequenceCorrector:
             for t0 in range(0, t, self.reg.max_batch):
                 outs.append(self.reg.compensate(raw[t0:t0 + self.reg.max_batch], flows[t0:t0 + self.reg.max_batch]))
             reg = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
-        if self.update_reference and t > 0:
+        if self.update_reference and self.world == 1 and t > 0:
             # (compensate_recording_3D.py:395-429) new fixed volume = mean of the last <= 100 pre-processed frames of
             # the batch warped by their flows (float64 frames in, float32 warps, float64 mean); used from the next
             # batch on.  Out-of-volume voxels take the current pre-processed reference.
             n_ref = min(100, t)
             comp = self.reg.compensate(proc64[t - n_ref:], flows[t - n_ref:], ref_raw=self._ref_proc64[0])
             new64 = self.reg.mean_frames_f64(comp)
+            self._ref_proc64 = new64[None]
+            self.reg.set_reference(new64.to(torch.float32), weight=self._weight)
+        elif self.update_reference:
+            # the same over a batch sharded across ranks: every rank warps ITS frames of the global window (the last
+            # <= 100 of the batch), the float64 partial sums are all-reduced
+            n_ref = min(100, G)
+            a, b = max(0, G - n_ref - local_offset), t
+            Z, Y, X = self.shape
+            part = torch.zeros((Z, Y, X, self.C), dtype=torch.float64, device=self.device)
+            if t > 0 and b > a:
+                comp = self.reg.compensate(proc64[a:b], flows[a:b], ref_raw=self._ref_proc64[0])
+                part = self.reg.mean_frames_f64(comp) * float(b - a)
+                self.reg.ctx.order_with_torch()
+            torch.distributed.all_reduce(part, op=torch.distributed.ReduceOp.SUM, group=self.group)
+            new64 = part / float(n_ref)
             self._ref_proc64 = new64[None]
             self.reg.set_reference(new64.to(torch.float32), weight=self._weight)
         return reg, flows
@@ -362,6 +390,10 @@ def compensate_arr_3D(c1: np.ndarray, c_ref: np.ndarray, options=None,
     registered shaped like c1 and flow (T,Z,Y,X,3) float32.  cc_prealign: see SequenceCorrector (not a reference
     argument; False reproduces what the reference pipeline computes for OFOptions.cc_initialization)."""
     c1 = np.asarray(c1)
+    if c_ref is None:
+        # not in the reference's signature (c_ref is required there): the fixed volume the options describe, i.e. the
+        # mean of the frames listed in options.reference_frames (OF_options_3D.py:496-503)
+        c_ref = (OFOptions() if options is None else options).get_reference_frame(c1)
     c_ref = np.asarray(c_ref)
     squeezed = False
     original_shape = c1.shape
@@ -432,7 +464,11 @@ def compensate_arr_3D_sharded(c1: np.ndarray, c_ref: np.ndarray, options=None, g
         for b0 in range(0, T, int(options.buffer_size)):
             b1 = min(T, b0 + int(options.buffer_size))
             lo, hi = shard_bounds(b1 - b0, seq.world, seq.rank)
-            reg, fl = seq.process_batch(c1[b0 + lo:b0 + hi], global_size=b1 - b0, local_offset=lo)
+            hr = seq.temporal_halo
+            before = c1[b0 + max(0, lo - hr):b0 + lo] if (hr and hi > lo and lo > 0) else None
+            after = c1[b0 + hi:min(b1, b0 + hi + hr)] if (hr and hi > lo and hi < b1 - b0) else None
+            reg, fl = seq.process_batch(c1[b0 + lo:b0 + hi], global_size=b1 - b0, local_offset=lo,
+                                        halo_before=before, halo_after=after)
             seq.reg.sync()
             if hi > lo:
                 regs.append(dev.to_host(reg).copy())

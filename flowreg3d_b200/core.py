@@ -128,16 +128,22 @@ class Context:
         return int(self.lib.fr3d_device_bytes(self.h))
 
 
+import threading
+
 _bare: dict = {}
+_CACHE_LOCK = threading.RLock()     # guards _bare and _PAIR_CACHE (the per-pair functions are called from worker threads
+                                    # by the reference's ThreadingExecutor3D, threading_3d.py:211-225)
 
 
 def bare_context(device: Optional[torch.device] = None) -> Context:
-    """Plan-less context serving the stage entry points (one per device)."""
+    """Plan-less context serving the stage entry points: one per (device, calling thread) -- a context is not
+    re-entrant, so threads never share one."""
     device = device if device is not None else dev.default_device()
-    key = str(device)
-    if key not in _bare:
-        _bare[key] = Context(None, device)
-    return _bare[key]
+    key = (str(device), threading.get_ident())
+    with _CACHE_LOCK:
+        if key not in _bare:
+            _bare[key] = Context(None, device)
+        return _bare[key]
 
 
 class Registration:
@@ -548,36 +554,63 @@ def get_displacement(fixed, moving, alpha=(2, 2, 2), update_lag=10, iterations=2
     fp = FlowParams(alpha=tuple(alpha), update_lag=update_lag, iterations=iterations, min_level=min_level,
                     levels=levels, eta=eta, a_smooth=a_smooth, a_data=a_data)
     reg = _pair_registration((Z, Y, X), Cn, fp)
-    reg.set_reference(fixed.astype(np.float32), weight=weight)
+    # the fixed volume's pyramid is rebuilt only when the fixed volume (or the weight) changed since this thread's
+    # previous call with the same shape and parameters -- the reference's executors call once per frame against the
+    # same fixed volume
+    token = (_content_token(fixed), _content_token(weight))
+    if getattr(reg, "_pair_token", None) != token:
+        reg.set_reference(fixed.astype(np.float32), weight=weight)
+        reg._pair_token = token
     uv = None if uvw is None else np.asarray(uvw).astype(np.float32)
     # With min_level > 0 the flow is the output of the final resize, i.e. float32-exact values (the reference's
     # imresize casts to float32 too): fetch 12 B/voxel and widen on the host.  At min_level == 0 it is the
     # float64 accumulation of the level increments.
     odt = np.float32 if reg.plan.min_level > 0 else np.float64
     out = reg.get_displacement(moving.astype(np.float32)[None], uvw=uv, out_dtype=odt)
+    if reg.device.type == "cuda":
+        # pinned staging buffer (kept with the cached context): one asynchronous copy instead of a pageable one
+        stage = getattr(reg, "_pair_stage", None)
+        if stage is None or stage.shape != out.shape or stage.dtype != out.dtype:
+            stage = reg._pair_stage = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+        stage.copy_(out, non_blocking=True)
+        torch.cuda.current_stream(reg.device).synchronize()
+        return stage.numpy()[0].astype(np.float64)
     reg.sync()
     return dev.to_host(out)[0].astype(np.float64)
+
+
+def _content_token(a):
+    """Cheap content fingerprint of an array (None passes through): shape, dtype, full sum and a strided sample."""
+    if a is None:
+        return None
+    a = np.asarray(a)
+    f = a.reshape(-1)
+    return (a.shape, str(a.dtype), float(f.sum(dtype=np.float64)), float(f[:: max(1, f.size // 4096)].sum(dtype=np.float64)))
 
 
 # The reference's executors call get_displacement once per frame with the same shape and parameters
 # (sequential_3d.py:89-173): keep the last few contexts (plan tables, solver geometry, workspaces) alive
 # instead of rebuilding them on every call.
 _PAIR_CACHE: "dict" = {}
-_PAIR_CACHE_MAX = 4
+_PAIR_CACHE_MAX = 4       # per calling thread
 
 
 def _pair_registration(shape, Cn, fp: FlowParams) -> Registration:
+    """The cached Registration of the calling thread for these parameters (contexts are not re-entrant: every
+    thread gets its own; least recently used ones of the thread are closed beyond _PAIR_CACHE_MAX)."""
     device = dev.default_device()
-    key = (shape, Cn, tuple(float(a) for a in fp.alpha), int(fp.update_lag), int(fp.iterations), int(fp.min_level),
+    tid = threading.get_ident()
+    key = (tid, shape, Cn, tuple(float(a) for a in fp.alpha), int(fp.update_lag), int(fp.iterations), int(fp.min_level),
            int(fp.levels), float(fp.eta), float(fp.a_smooth), tuple(np.asarray(fp.a_data, float).ravel().tolist()),
            np.dtype(resolve_state_dtype(None, shape, fp)).str, int(SWEEP), str(device), str(_lib.library_path()))
-    reg = _PAIR_CACHE.pop(key, None)
-    if reg is None or reg.ctx.h is None:
-        reg = Registration(shape, Cn, fp, max_batch=1, device=device)
-    _PAIR_CACHE[key] = reg                      # most recently used last
-    while len(_PAIR_CACHE) > _PAIR_CACHE_MAX:
-        old = _PAIR_CACHE.pop(next(iter(_PAIR_CACHE)))
-        old.ctx.close()
+    with _CACHE_LOCK:
+        reg = _PAIR_CACHE.pop(key, None)
+        if reg is None or reg.ctx.h is None:
+            reg = Registration(shape, Cn, fp, max_batch=1, device=device)
+        _PAIR_CACHE[key] = reg                      # most recently used last
+        mine = [k for k in _PAIR_CACHE if k[0] == tid]
+        for k in mine[:-_PAIR_CACHE_MAX]:
+            _PAIR_CACHE.pop(k).ctx.close()
     return reg
 
 

@@ -129,6 +129,7 @@ struct fr3d_ctx {
     Buf<double> psi_c, psi_r;
     Buf<unsigned> bar;
     Buf<unsigned> p2p_flags; // z-slab halo flags written by the z-neighbours (fr3d_ipc_export which = 1)
+    Buf<int32_t> slab_pe, slab_start; // per-launch item tables of the z-slab solve (chunks of the own planes only)
     DevTable stage_tab[3];
     std::unique_ptr<HPGeom> stage_hp; // geometry cache of fr3d_sor_level
     // level-by-level execution state (fr3d_level_begin / _sweeps / _end / fr3d_flow_finish)
@@ -522,7 +523,40 @@ static void sor_launch_p2p_t(fr3d_ctx* c, int k0, int k1, void* lo_d, void* hi_d
     pr.hi_flag = hi_flags ? (unsigned*)hi_flags + 0 : nullptr; // the upper neighbour's "from my lower neighbour" word
     pr.my_flags = c->p2p_flags.p;
     pr.base = (unsigned)flag_base;
-    sor_run_p2p_any(c->dev, P, c->bar.ensure(c->dev, 4), c->sp_hp->pe_host.data(), k0, k1, pr);
+    // Item tables restricted to the slab: in hyperplane-major storage the voxels of hyperplane s are ordered by plane,
+    // so the planes [k0, k1) are ONE contiguous slot range of every hyperplane; only the 32-slot chunks that touch it
+    // become work items (the kernel still masks the few foreign voxels of the two end chunks).  Without this every
+    // rank would walk all chunks of every wave and skip half of them -- measured: no speed-up at all.
+    const HPGeom& hp = *c->sp_hp;
+    const int S = hp.S, p = hp.p, m = hp.m, n = hp.n;
+    std::vector<int32_t> spe(S), sst((size_t)S + 1);
+    int64_t at = 0;
+    for (int s = 0; s < S; ++s) {
+        int64_t run = 0, lo = 0, hi = 0;
+        for (int k = 0; k < p; ++k) {
+            if (k == k0)
+                lo = run;
+            int jlo = s - k - (n - 1);
+            jlo = jlo < 0 ? 0 : jlo;
+            int jhi = s - k;
+            jhi = jhi > m - 1 ? m - 1 : jhi;
+            if (jhi >= jlo)
+                run += jhi - jlo + 1;
+            if (k == k1 - 1)
+                hi = run;
+        }
+        const int64_t c0 = lo / 32, c1 = hi > lo ? (hi + 31) / 32 : c0;
+        sst[s] = (int32_t)(at + 32 * c0);
+        spe[s] = (int32_t)(c1 - c0) + (s >= 2 ? spe[s - 2] : 0);
+        at += (run + 31) / 32 * 32;
+    }
+    sst[S] = (int32_t)at;
+    c->slab_pe.upload(c->dev, spe.data(), spe.size());
+    c->slab_start.upload(c->dev, sst.data(), sst.size());
+    FR3D_CUDA(cudaStreamSynchronize(c->dev.stream)); // the host vectors go out of scope
+    P.g.pe = c->slab_pe.p;
+    P.g.start = c->slab_start.p;
+    sor_run_p2p_any(c->dev, P, c->bar.ensure(c->dev, 4), spe.data(), k0, k1, pr);
 }
 #endif
 

@@ -44,6 +44,25 @@ class OFOptions(BaseModel):
     model_config = ConfigDict(arbitrary_types_allowed=True, validate_assignment=False, extra="forbid",
                               populate_by_name=True)
 
+    # I/O and bookkeeping fields of the reference (OF_options_3D.py:141-153, 178, 190-199, 222): accepted so that every
+    # keyword the reference's OFOptions takes constructs here too; file readers / writers are out of scope,
+    # the array path ignores them exactly as the reference's ArrayReader3D / ArrayWriter do (bin_size: "not used for
+    # arrays", util/io/_arr_3d.py:25; n_references > 1: the reference repeats ONE reference, :469-476)
+    input_file: Any = Field(None)
+    input_dim_order: str = Field("TZYX")
+    output_path: Any = Field("results")
+    output_format: Any = Field("MAT")
+    output_file_name: Optional[str] = Field(None)
+    channel_idx: Optional[List[int]] = Field(None)
+    bin_size: StrictInt = Field(1, ge=1)
+    n_references: StrictInt = Field(1, ge=1)
+    min_frames_per_reference: StrictInt = Field(20, ge=1)
+    save_meta_info: bool = Field(True)
+    save_w: bool = Field(False)
+    save_valid_mask: bool = Field(False)
+    save_valid_idx: bool = Field(False)
+    naming_convention: Any = Field("default")
+    preproc_funct: Optional[Any] = Field(None, exclude=True)
     # flow parameters (OF_options_3D.py:155-174)
     alpha: Union[float, Tuple[float, float], Tuple[float, float, float]] = Field((0.25, 0.25, 0.25))
     weight: Union[List[float], np.ndarray] = Field([0.5, 0.5])
@@ -59,7 +78,7 @@ class OFOptions(BaseModel):
     sigma: Any = Field([[1.0, 1.0, 1.0, 0.1], [1.0, 1.0, 1.0, 0.1]])
     buffer_size: StrictInt = Field(10, ge=1)
     # reference (:185-192)
-    reference_frames: Union[List[int], np.ndarray] = Field(list(range(50, 500)))
+    reference_frames: Union[List[int], str, Any, np.ndarray] = Field(list(range(50, 500)))
     update_reference: bool = Field(False)
     # processing options (:197-224)
     verbose: bool = Field(False)
@@ -166,6 +185,35 @@ class OFOptions(BaseModel):
         if i >= w.shape[0]:
             return np.ones(w.shape[1:]) / n_channels
         return w[i]
+
+    def get_reference_frame(self, video=None):
+        """The fixed volume the options describe, for array-backed recordings (OF_options_3D.py:466-503): an ndarray is
+        returned as it is; a list of frame indices selects frames of `video` (T,Z,Y,X[,C]) and returns their mean over
+        time -- `video[indices].mean(axis=0)`, numpy's arithmetic, as the reference's 3-D branch (:496-503); indices
+        outside the recording raise IndexError like the reference's reader (util/io/_base_3d.py:141-144).  File paths
+        belong to the reference's readers (out of scope here).  n_references > 1 repeats the single reference, as the
+        reference does (:469-476)."""
+        if self.n_references > 1:
+            import warnings
+            warnings.warn("Multi-reference mode not fully implemented; repeating a single computed reference")
+            one = self.model_copy(update={"n_references": 1})
+            return [one.get_reference_frame(video)] * self.n_references
+        rf = self.reference_frames
+        if isinstance(rf, np.ndarray):
+            return rf
+        if isinstance(rf, (list, tuple)) and video is not None:
+            v = np.asarray(video)
+            idx = [int(i) for i in rf]
+            T = v.shape[0]
+            for i in idx:
+                if i < -T or i >= T:
+                    raise IndexError(f"Index {i} out of range for {T} binned frames")
+            frames = v[idx]
+            return frames.mean(axis=0) if frames.ndim >= 4 else frames
+        if isinstance(rf, (str, bytes)) or hasattr(rf, "__fspath__"):
+            raise NotImplementedError("reference_frames given as a file path needs the reference's readers "
+                                      "(file I/O is outside this package)")
+        return np.asarray(rf)
 
     def copy(self) -> "OFOptions":
         return self.model_copy(deep=True)

@@ -260,3 +260,41 @@ def test_update_reference(backend, golden):
     # and it matters: the second batch differs from a run with a fixed reference
     _, w_fixed = F.compensate_arr_3D(video, ref, F.OFOptions(**{**opts.model_dump(), "update_reference": False}))
     assert np.abs(w[3:] - w_fixed[3:]).max() > 1e-3
+
+
+def test_per_pair_functions_are_thread_safe(backend, golden):
+    """The reference's get_displacement / imregister_wrapper are pure functions that ThreadingExecutor3D calls from
+    worker threads (threading_3d.py:211-225).  Here every thread gets its own context; concurrent calls (different
+    moving volumes, two different fixed volumes, so the cached-pyramid path is exercised too) equal the serial ones."""
+    import threading
+    import flowreg3d_b200 as F
+    g = golden("flow_small")
+    fixed, moving = g["fixed"][:12, :32, :36].astype(np.float32), g["moving"][:12, :32, :36].astype(np.float32)
+    kw = dict(alpha=(0.25, 0.3, 0.2), update_lag=5, iterations=10, min_level=1, levels=100, eta=0.8, a_smooth=1.0,
+              a_data=0.45)
+    jobs = [(fixed, moving), (fixed, np.roll(moving, 1, 2)), (np.roll(fixed, 1, 1), moving), (fixed, np.roll(moving, 2, 1))]
+
+    def run(job):
+        f, m = job
+        flow = F.get_displacement(f, m, **kw)
+        f32 = flow.astype(np.float32)
+        return flow, F.imregister_wrapper(m, f32[..., 0], f32[..., 1], f32[..., 2], f, "cubic")
+
+    serial = [run(j) for j in jobs]
+    out = [None] * len(jobs)
+    errs = []
+
+    def worker(idx):
+        try:
+            for rep in range(2):                 # second round: cached contexts and pyramids
+                for k in range(idx, len(jobs), 2):
+                    out[k] = run(jobs[k])
+        except Exception as e:                   # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    for (fa, ra), (fb, rb) in zip(serial, out):
+        assert np.array_equal(fa, fb) and np.array_equal(ra, rb)

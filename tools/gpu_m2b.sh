@@ -1,0 +1,10 @@
+#!/bin/bash
+# 2-GPU session b: persistent IPC mappings + stream-ordered rendezvous; phase timings of the z-slab solve
+O=gpurun_out/m2b; mkdir -p $O
+timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -x -q > $O/pytest_multi.log 2>&1; echo "pytest multi rc $?" | tee -a $O/rc.txt
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511"
+timeout 400 $TR tools/bench_pipelined.py --shape 128 1024 1024 --channels 1 --min-level 5 --zslab > $O/zslab_p2p_c4_ml5.log 2>&1; echo "zslab c4 ml5 rc $?" | tee -a $O/rc.txt
+timeout 400 $TR tools/bench_pipelined.py --shape 128 1024 1024 --channels 1 --min-level 2 --zslab > $O/zslab_p2p_c4_ml2.log 2>&1; echo "zslab c4 ml2 rc $?" | tee -a $O/rc.txt
+timeout 400 $TR tools/bench_pipelined.py --shape 128 1024 1024 --channels 1 --min-level 2 --zslab --state f32 > $O/zslab_p2p_c4_ml2_f32.log 2>&1; echo "zslab c4 ml2 f32 rc $?" | tee -a $O/rc.txt
+timeout 600 $TR bench.py --gpus 2 --steps 5 --warmup 3 --no-cpu-baseline > $O/bench_g2.log 2> $O/bench_g2.err; echo "bench g2 rc $?" | tee -a $O/rc.txt
+tail -4 $O/pytest_multi.log; for f in zslab_p2p_c4_ml5 zslab_p2p_c4_ml2 zslab_p2p_c4_ml2_f32; do echo "== $f"; tail -1 $O/$f.log | cut -c1-900; done; tail -1 $O/bench_g2.log | cut -c1-1500
