@@ -227,8 +227,8 @@ def measured_traffic(kernel, state, B, level_n):
     f = ROOT / "profiles" / "r02_sor_traffic.json"
     if not f.exists():
         return None, None
-    t = json.loads(f.read_text())
-    if t.get("kernel") != kernel or t.get("state") != state:
+    t = json.loads(f.read_text()).get(state)
+    if not t or t.get("kernel") != kernel:
         return None, None
     return round(t["dram_bytes_per_frame_voxel"] * B * float(np.mean(level_n))), t.get("source")
 
@@ -401,9 +401,11 @@ def run_gpu(args):
         reg_np, w_np = F.compensate_arr_3D(video, ref, F.OFOptions(buffer_size=B))
         dt = time.perf_counter() - t0
         arr_api = {"value": round(video.shape[0] / dt, 3), "unit": "volumes/s", "frames": int(video.shape[0]),
-                   "what": "flowreg3d_b200.compensate_arr_3D(video, reference, OFOptions(buffer_size=B)) with pageable "
-                           "numpy in and out, wall clock of the whole call (context + reference pyramid + w_init "
-                           "bootstrap + internal pinned staging + results copied into fresh numpy arrays)"}
+                   "what": "flowreg3d_b200.compensate_arr_3D(video, reference, OFOptions(buffer_size=B)) -- the reference's "
+                           "one-call signature -- with pageable numpy in and fresh numpy arrays out (registered as "
+                           "float64, the reference's output_typename default): wall clock of the whole call, i.e. "
+                           "context + reference pyramid + w_init bootstrap + page faults of 0.23 GB of fresh result "
+                           "memory per frame + pageable copies"}
         del reg_np, w_np, video
 
     t = torch.tensor([ms, ms_e2e, float(launches), ms_copy], dtype=torch.float64, device=device)
@@ -457,7 +459,7 @@ def run_gpu(args):
             "e2e": {"value": round(frames_total / (ms_e2e * 1e-3), 3), "unit": "volumes/s",
                     "h2d_bytes_per_step": int(B * Z * Y * X * C * 4),
                     "d2h_bytes_per_step": int(B * Z * Y * X * (C + 3) * 4),
-                    "api": "SequenceCorrector.run_pipelined (the streaming call compensate_arr_3D is built on), pinned "
+                    "api": "SequenceCorrector.run_pipelined (the streaming entry point for host-resident recordings): pinned "
                            "host batches in, pinned host results out, copies inside the timed region",
                     "copy_ceiling_volumes_per_s": round(frames_total / (ms_copy * 1e-3), 3),
                     "frac_of_copy_ceiling": round(ms_copy / ms_e2e, 4),
@@ -514,9 +516,10 @@ def main():
     ap.add_argument("--streams", type=int, default=1, help="concurrent half-batch pipelines per GPU")
     ap.add_argument("--sweep", default="lexicographic", choices=["lexicographic", "redblack"],
                     help="solver sweep order; only lexicographic reproduces the reference")
-    ap.add_argument("--state", default="auto", choices=["auto", "f64", "f32"],
-                    help="storage precision of the solver increments: auto (the package default: f32 when min_level "
-                         ">= 2, i.e. here), f64 (reference to float64 rounding), f32")
+    ap.add_argument("--state", default="f64", choices=["f64", "f32", "auto"],
+                    help="storage precision of the solver increments: f64 (the package default: the reference to "
+                         "float64 rounding), f32 (opt-in: 24 %% fewer solver bytes, inside the tolerance on config 2 "
+                         "but not on every workload, see flowreg3d_b200/core.py), auto (f32 when min_level >= 2)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -293,8 +293,16 @@ static void spline_tile_pass(fr3d_ctx* c, double* coef, int N, int64_t nlines, i
     k.elem_stride = elem_stride;
     k.first = first;
     k.line_fast = line_fast;
+    // bulk-copy (TMA) staging when a block's lines are one contiguous 16-byte aligned run: unit element stride, lines
+    // back to back within and across groups, an even number of 8-byte slots per block start
+    k.tma = (!line_fast && elem_stride == 1 && line_stride == L3 &&
+             (nlines <= per_group || group_stride == per_group * line_stride) &&
+             ((int64_t)TL * L3) % 2 == 0 && first % 2 == 0 && c->dev.spline_tma)
+                ? 1
+                : 0;
     int threads = (TL * nseg + 31) / 32 * 32;
-    launch_tiles(c->dev, k, (nlines + TL - 1) / TL, threads, (size_t)TL * (L3 + nseg + FR3D_SPLINE_PAD) * sizeof(double));
+    launch_tiles(c->dev, k, (nlines + TL - 1) / TL, threads,
+                 (size_t)TL * (L3 + nseg + FR3D_SPLINE_PAD) * sizeof(double) + 16);
 }
 
 // Cubic B-spline coefficients of B*C volumes (any dtype / strides) -> c->coef.
@@ -755,6 +763,10 @@ int fr3d_set_option(fr3d_ctx* ctx, int option, int64_t value)
     case FR3D_OPT_SOR_KERNEL:
         FR3D_REQUIRE(value >= 0 && value <= 2, "FR3D_OPT_SOR_KERNEL: %lld", (long long)value);
         _c->dev.sor_kernel = (int)value;
+        break;
+    case FR3D_OPT_SPLINE_TMA:
+        FR3D_REQUIRE(value == 0 || value == 1, "FR3D_OPT_SPLINE_TMA: %lld", (long long)value);
+        _c->dev.spline_tma = (int)value;
         break;
     case FR3D_OPT_SOR_TILE: {
         const int tb = (int)(value & 0xff), tk = (int)((value >> 8) & 0xff), tj = (int)((value >> 16) & 0xff),

@@ -82,6 +82,7 @@ struct Device {
     int sor_kernel = 0;      // FR3D_OPT_SOR_KERNEL: 2 time-blocked tiles (fr3d_sor_tile.h), 1 staged wavefront (TMA bulk
                              // copies + mbarrier ring), 0 direct-load wavefront
     int sor_stages = 0;      // stages per warp of the staged kernel, 0 = default (FR3D_OPT_SOR_STAGES)
+    int spline_tma = 1;      // FR3D_OPT_SPLINE_TMA: bulk-copy (TMA) staging of the spline X pass
     int sor_tile_sweeps = 0, sor_tile_k = 0, sor_tile_j = 0, sor_tile_i = 0; // FR3D_OPT_SOR_TILE (0 = defaults)
     int sor_k0 = 0, sor_k1 = 0; // plane range of a z-slab solver launch (0, 0: all planes); set around the launch
     int cc_block_scans = 1;  // FR3D_OPT_CC_BLOCK_SCANS (block-cooperative scans: 30.1 -> 5.5 ms per 10 frames on a B200)

@@ -581,6 +581,40 @@ struct SplineXK {
 // starts from 0 a warm-up length W = 40 samples early reproduces the sequential result to
 // |z|^40 ~ 1e-23 relative, far below float64 rounding; segments near the line ends use scipy's
 // exact boundary initialisation.  Same recurrences, constants and operation order as spline_line.
+// TMA staging of a tile whose lines are contiguous in memory (the X pass): ONE bulk copy global -> shared
+// (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP) replaces the per-thread load / store staging loops, and one bulk
+// copy shared -> global writes the filtered lines back.  No registers, no LSU instructions, full-line bursts.
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void fr3d_tma_load_tile(double* smem_dst, const double* gsrc, uint32_t bytes, uint64_t* mbar)
+{
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(mbar);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(gsrc), "r"(bytes), "r"(bar)
+                 : "memory");
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(bar), "r"(0u)
+                     : "memory");
+    } while (!ok);
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void fr3d_tma_store_tile(double* gdst, const double* smem_src, uint32_t bytes)
+{
+    const uint32_t src = (uint32_t)__cvta_generic_to_shared(smem_src);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the tile was written through the generic proxy
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(src), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // shared memory may be reused / released
+}
+#endif
+
 struct SplineTileK {
     static constexpr int PHASES = 6;
     double* coef;
@@ -590,6 +624,7 @@ struct SplineTileK {
     // global address of slot p of line l: first + (l / per_group)*group_stride + (l % per_group)*line_stride + p*elem_stride
     int64_t per_group, group_stride, line_stride, elem_stride, first;
     int line_fast;  // 1: consecutive threads load consecutive lines (Y pass), 0: consecutive slots (X pass)
+    int tma;        // 1: the TL lines of a block are contiguous and 16-byte aligned -> bulk-copy (TMA) staging
 
     FR3D_HD int64_t gaddr(int64_t l, int p) const
     {
@@ -606,6 +641,21 @@ struct SplineTileK {
         double* prevs = sm + (size_t)TL * L3;              // [TL][NSEG]
         double* tails = prevs + (size_t)TL * NSEG;         // [TL][PAD]
         if (ph == 0 || ph == 5) {
+#if defined(__CUDA_ARCH__)
+            if (tma) {
+                // lines l0 .. l0+nl-1 are one contiguous, 16-byte aligned run of nl * (N+3) doubles
+                const uint32_t bytes = (uint32_t)((size_t)nl * L3 * sizeof(double));
+                if ((bytes & 15u) == 0) {
+                    if (tid == 0) {
+                        if (ph == 0)
+                            fr3d_tma_load_tile(sm, coef + gaddr(l0, 0), bytes, reinterpret_cast<uint64_t*>(tails + (size_t)TL * FR3D_SPLINE_PAD));
+                        else
+                            fr3d_tma_store_tile(coef + gaddr(l0, 0), sm, bytes);
+                    }
+                    return;
+                }
+            }
+#endif
             // staging copy global <-> shared: no per-element division, eight independent accesses in
             // flight per thread
             if (line_fast) {

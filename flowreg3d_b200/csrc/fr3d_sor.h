@@ -876,7 +876,9 @@ fr3d_sor_wavefront_p2p(const SorParams<ST> P, unsigned* bar, int tabs_in_smem, i
     unsigned gen = 0;
     for (int q = P.q_begin; q < P.q_end; ++q) {
         if (q > P.q_begin) {
-            // the neighbours' boundary values of wave q - 1
+            // the neighbours' boundary values of wave q - 1.  (Measured and rejected on 2 B200: letting every warp
+            // wait only before its first boundary-plane item, so that the flag latency hides behind interior items,
+            // costs a perm load and a vote per item and is SLOWER: 420 vs 379 ms at config 4, min_level 2.)
             if (threadIdx.x == 0) {
                 const unsigned target = pr.base + (unsigned)(q - P.q_begin);
                 if (pr.lo_d)

@@ -72,8 +72,8 @@ class B200Executor3D(_Base):
 
     def __init__(self, n_workers: Optional[int] = None, max_batch: int = 16, device: Optional[torch.device] = None,
                  state_dtype=np.float64):
-        """state_dtype: storage of the solver increments.  float64 by default HERE (the package default is "auto"):
-        an executor whose name ends in "3d" is held to the reference's cross-executor consistency test
+        """state_dtype: storage of the solver increments.  float64 (the package default): an executor whose name ends
+        in "3d" is held to the reference's cross-executor consistency test
         (tests/motion_correction/test_parallelization.py:152-198, rtol 1e-5 against sequential3d), which float32
         increments do not meet."""
         super().__init__(n_workers=1)

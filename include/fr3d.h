@@ -135,6 +135,9 @@ typedef enum {
                                    * per warp); 0 = direct-load wavefront.  Same arithmetic, same update order:
                                    * results are bit-identical */
     FR3D_OPT_SOR_STAGES = 5,      /* shared-memory stages per warp of the staged solver kernel (0 = built-in default) */
+    FR3D_OPT_SPLINE_TMA = 7,      /* B-spline prefilter X pass: 1 (default) = the block's lines are staged with ONE bulk copy
+                                   * global -> shared (cp.async.bulk + mbarrier) and written back with one bulk copy
+                                   * shared -> global; 0 = per-thread staging loops.  Same arithmetic: bit-identical */
     FR3D_OPT_SOR_TILE = 6         /* tile kernel geometry: Tb | K << 8 | J << 16 | I << 24 (sweeps per time block and
                                    * tile extents; a 0 field keeps its default: 5 sweeps, 8 x 8 x 8) */
 } fr3d_option;

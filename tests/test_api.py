@@ -149,3 +149,32 @@ def test_executor_registers_with_reference_runtime_when_present():
     from flowreg3d._runtime import RuntimeContext
     assert F.B200Executor3D.register() is True
     assert RuntimeContext.get_parallelization_executor("b2003d") is F.B200Executor3D
+
+
+def test_options_accept_every_reference_field_and_reference_from_indices(emu_backend):
+    """OFOptions takes every keyword the reference's OFOptions takes (OF_options_3D.py:141-231; file I/O fields are
+    carried and ignored on the array path), still forbids unknown ones, and get_reference_frame reproduces the 3-D
+    branch of the reference (:496-503): the mean over the listed frames, numpy's arithmetic."""
+    import flowreg3d_b200 as F
+    o = F.OFOptions(input_file=None, input_dim_order="TZYXC", output_path="results", output_format="HDF5",
+                    output_file_name=None, channel_idx=None, bin_size=1, n_references=1, min_frames_per_reference=20,
+                    save_meta_info=False, save_w=True, save_valid_mask=False, save_valid_idx=False,
+                    naming_convention="default", preproc_funct=None, reference_frames=[1, 3])
+    with pytest.raises(Exception):
+        F.OFOptions(no_such_option=1)
+    v = np.random.default_rng(0).random((5, 6, 10, 12, 2)).astype(np.float32)
+    r = o.get_reference_frame(v)
+    assert np.array_equal(r, v[[1, 3]].mean(axis=0)) and r.dtype == np.float32
+    with pytest.raises(IndexError):
+        F.OFOptions(reference_frames=[7]).get_reference_frame(v)
+    arr = np.ones((6, 10, 12, 2))
+    assert F.OFOptions(reference_frames=arr).get_reference_frame(v) is not None
+    with pytest.warns(UserWarning):
+        many = F.OFOptions(reference_frames=[0, 1], n_references=3).get_reference_frame(v)
+    assert len(many) == 3 and np.array_equal(many[0], v[[0, 1]].mean(axis=0))
+    # compensate_arr_3D(c_ref=None): the fixed volume the options describe
+    opts = F.OFOptions(reference_frames=[0, 2], min_level=2, iterations=4, update_lag=2, buffer_size=3, weight=[0.5, 0.5])
+    small = v[:3, :, :, :, :]
+    reg_a, w_a = F.compensate_arr_3D(small, None, opts)
+    reg_b, w_b = F.compensate_arr_3D(small, small[[0, 2]].mean(axis=0), opts)
+    assert np.array_equal(reg_a, reg_b) and np.array_equal(w_a, w_b)

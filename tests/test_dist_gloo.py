@@ -18,7 +18,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, emu_path, tmp, cc=False):
+def _worker(rank, world, port, emu_path, tmp, cc=False, coupled=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     sys.path.insert(0, str(ROOT))
@@ -32,6 +32,9 @@ def _worker(rank, world, port, emu_path, tmp, cc=False):
     opts = F.OFOptions(min_level=3, iterations=8, update_lag=4, buffer_size=5, weight=[0.5, 0.5])
     v = g["video"][:, :12, :24, :28]
     r = g["ref"][:12, :24, :28]
+    if coupled:   # options that couple the frames of a batch: temporal pre-filter + update_reference
+        opts = F.OFOptions(min_level=3, iterations=8, update_lag=4, buffer_size=5, weight=[0.5, 0.5],
+                           sigma=[[1.0, 1.0, 1.0, 0.8], [1.0, 1.0, 1.0, 0.8]], update_reference=True)
     if cc:   # rigid cross-correlation pre-alignment: single channel (as in the reference), per-rank estimator
         opts = F.OFOptions(min_level=3, iterations=8, update_lag=4, buffer_size=5, cc_initialization=True,
                            cc_hw=(20, 24), cc_up=10)
@@ -40,6 +43,31 @@ def _worker(rank, world, port, emu_path, tmp, cc=False):
     np.savez(os.path.join(tmp, f"r{rank}.npz"), reg=reg, w=w, idx=idx)
     dist.barrier()
     dist.destroy_process_group()
+
+
+def test_two_rank_sharding_with_frame_coupling_options(emu_backend, tmp_path):
+    """Temporal pre-filter (sigma_t = 0.8: radius 3 frames, so every shard needs halo frames of its batch) and
+    update_reference (the fixed volume re-averaged from ALL frames of a batch: all-reduced float64 partial sums) on a
+    batch sharded over two ranks equal the single-process result."""
+    from emu.build_emu import build
+    import flowreg3d_b200 as F
+    emu = str(build())
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), emu, str(tmp_path), False, True), nprocs=world, join=True)
+    g = np.load(ROOT / "tests" / "golden" / "sequence.npz")
+    opts = F.OFOptions(min_level=3, iterations=8, update_lag=4, buffer_size=5, weight=[0.5, 0.5], output_typename=None,
+                       sigma=[[1.0, 1.0, 1.0, 0.8], [1.0, 1.0, 1.0, 0.8]], update_reference=True)
+    v = g["video"][:, :12, :24, :28]
+    r = g["ref"][:12, :24, :28]
+    reg1, w1 = F.compensate_arr_3D(v, r, opts)
+    seen = []
+    for rank in range(world):
+        d = np.load(tmp_path / f"r{rank}.npz")
+        seen.extend(d["idx"].tolist())
+        e = np.sqrt(((d["w"].astype(np.float64) - w1[d["idx"]]) ** 2).sum(-1))
+        assert e.mean() <= 1e-5 and e.max() <= 1e-3, (rank, e.mean(), e.max())
+        assert np.linalg.norm(d["reg"] - reg1[d["idx"]]) <= 1e-5 * np.linalg.norm(reg1[d["idx"]])
+    assert sorted(seen) == list(range(v.shape[0]))
 
 
 @pytest.mark.parametrize("cc", [False, True])

@@ -32,5 +32,10 @@ res = {"kernel": kern, "state": state, "B": B, "launches": out,
        "dram_bytes_per_frame_voxel": tot / (B * sum(levels)),
        "source": f"ncu --set full of this build, B = {B}, {state} state: dram__bytes_read.sum + dram__bytes_write.sum of the "
                  f"two solver launches of one step ({raw})"}
-Path(__file__).resolve().parent.parent.joinpath("profiles", "r02_sor_traffic.json").write_text(json.dumps(res, indent=1))
+out_file = Path(__file__).resolve().parent.parent.joinpath("profiles", "r02_sor_traffic.json")
+allres = json.loads(out_file.read_text()) if out_file.exists() else {}
+if "kernel" in allres:      # old single-entry layout
+    allres = {}
+allres[state] = res
+out_file.write_text(json.dumps(allres, indent=1))
 print(json.dumps(res)[:600])
