@@ -1613,6 +1613,46 @@ struct Median5PairK {
         }
         return cur;
     }
+    // Fast path of recover(): almost always exactly ONE window sample rounds to the median key, and then it is the
+    // answer whatever the other samples are.  One pass over the window with hoisted row pointers; the test
+    // "(float)v == med" is made in the float64 domain against the closed interval of doubles that can round to med
+    // (two DSETP on the otherwise idle fp64 pipe instead of a conversion and two compares on the ALU pipe that the
+    // selection saturates) and confirmed exactly for the rare candidates.  Ties fall back to recover().
+    FR3D_HD double recover_fast(const double* f, const int* zi, const int* yi, int i, float med) const
+    {
+        int xi[5];
+#pragma unroll
+        for (int d = 0; d < 5; ++d)
+            xi[d] = mirror_idx(i + d - 2, n);
+        // neighbours of med in float32; the doubles that round to med lie between the midpoints (inclusive bound:
+        // a superset, confirmed below)
+        const float up = nextafterf(med, INFINITY), dn = nextafterf(med, -INFINITY);
+        const double hi = 0.5 * ((double)med + (double)up), lo = 0.5 * ((double)med + (double)dn);
+        int eq = 0;
+        double val = 0.0;
+        bool differ = false;
+#pragma unroll 1
+        for (int a = 0; a < 5; ++a) {
+#pragma unroll
+            for (int b = 0; b < 5; ++b) {
+                const double* row = f + ((int64_t)zi[a] * m + yi[b]) * n;
+#pragma unroll
+                for (int c = 0; c < 5; ++c) {
+                    const double v = row[xi[c]];
+                    if (v >= lo && v <= hi) {
+                        if ((float)v == med) {
+                            differ = differ || (eq > 0 && v != val);
+                            val = v;
+                            ++eq;
+                        }
+                    }
+                }
+            }
+        }
+        if (eq >= 1 && !differ)
+            return val;
+        return recover(f, zi, yi, i, med);
+    }
     FR3D_HD void operator()(int64_t item) const
     {
         const int ip = (int)(item % npair);
@@ -1650,7 +1690,7 @@ struct Median5PairK {
                 wa[t] = a[1 + t];
             wa[26] = ms.own<0>(xo);
             const float med = Forget27<27>::run(wa, ms, xo);
-            const double r = recover(f, zi, yi, i0 + o, med);
+            const double r = recover_fast(f, zi, yi, i0 + o, med);
             dst[oA + o] = add ? add[oA + o] + r : r;
         }
     }

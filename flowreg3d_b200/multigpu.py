@@ -284,10 +284,9 @@ def get_displacement_zslab(reg: Registration, moving_proc, uvw=None, group=None,
     the level the slabs are gathered, the 5^3 median runs on the same z-slabs and the flow slabs are exchanged as in
     the sweep-pipelined solve.  The update order is the reference's: the result is bit-identical to one GPU.
 
-    This is the straightforward version (host-driven: one kernel launch and one message pair per wave); it exists for
-    levels whose state does not fit one GPU and as the baseline for a fused exchange.  For volumes that do fit,
-    `get_displacement_pipelined` needs ~8 messages per level instead of ~2 400 and is the faster choice today
-    (DESIGN.md section 6).  Every rank must call with identical arguments; every rank returns the full result.
+    NOTE on memory: every rank still allocates and assembles the WHOLE level (J, system, increments) and gathers all
+    increments before the median -- the decomposition divides the solver's time, not its memory; a slab-sized
+    assembly is not built.  Every rank must call with identical arguments; every rank returns the full result.
 
     p2p (default: on CUDA devices): the halo exchange runs INSIDE the persistent solver kernel -- the ranks map each
     other's increment arrays through CUDA IPC, a boundary-plane voxel is stored into the z-neighbour's memory as it
