@@ -644,15 +644,39 @@ def imregister_wrapper(f2_level, u, v, w, f1_level, interpolation_method="cubic"
             a = a.astype(np.float64)
         return dev.to_device(a, d)
 
-    f2t, f1t = up(f2), up(np.broadcast_to(f1, f2.shape))
-    ut, vt, wt = (up(np.broadcast_to(np.asarray(a), (Z, Y, X)), np.float64) for a in (u, v, w))
+    f2t = up(f2)
+    f1t = f2t if f1 is f2 else up(np.broadcast_to(f1, f2.shape))
     out = dev.empty((Z, Y, X, Cn), np.float32, d)
     code = lambda t: _lib.dtype_code(str(t.dtype).replace("torch.", ""))
-    _check(ctx.h, ctx.lib.fr3d_warp(ctx.h, dev.ptr(f2t), code(f2t), dev.ptr(ut), dev.ptr(vt), dev.ptr(wt),
-                                    dev.ptr(f1t), code(f1t), Z, Y, X, Cn, order, dev.ptr(out)))
+    flow3 = _interleaved_flow(u, v, w, (Z, Y, X))
+    if flow3 is not None:
+        # the usual call of the reference's executors: u, v, w are the three component views flow[..., q] of ONE
+        # float32 (Z,Y,X,3) array (sequential_3d.py:148-160).  Upload that array once (12 B / voxel instead of three
+        # float64 planes) and take the per-frame-flow entry point: the coordinates are float32 sums either way.
+        ft = up(flow3)
+        _check(ctx.h, ctx.lib.fr3d_warp_flow(ctx.h, dev.ptr(f2t), code(f2t), dev.ptr(ft), dev.ptr(f1t), code(f1t), 1, Z, Y,
+                                             X, Cn, order, dev.ptr(out)))
+    else:
+        ut, vt, wt = (up(np.broadcast_to(np.asarray(a), (Z, Y, X)), np.float64) for a in (u, v, w))
+        _check(ctx.h, ctx.lib.fr3d_warp(ctx.h, dev.ptr(f2t), code(f2t), dev.ptr(ut), dev.ptr(vt), dev.ptr(wt),
+                                        dev.ptr(f1t), code(f1t), Z, Y, X, Cn, order, dev.ptr(out)))
     ctx.sync()
     res = dev.to_host(out).copy()
     return res[..., 0] if Cn == 1 else res
+
+
+def _interleaved_flow(u, v, w, shape):
+    """The float32 (Z,Y,X,3) array that u, v, w are the component views of, or None."""
+    if not all(isinstance(a, np.ndarray) and a.dtype == np.float32 and a.shape == tuple(shape) for a in (u, v, w)):
+        return None
+    Z, Y, X = shape
+    want = (Y * X * 12, X * 12, 12)
+    if not all(a.strides == want for a in (u, v, w)):
+        return None
+    p0, p1, p2 = (a.__array_interface__["data"][0] for a in (u, v, w))
+    if p1 != p0 + 4 or p2 != p0 + 8:
+        return None
+    return np.lib.stride_tricks.as_strided(u, shape=(Z, Y, X, 3), strides=want + (4,), writeable=False)
 
 
 # --------------------------------------------------------------------------------------------

@@ -342,3 +342,21 @@ def test_slab_restricted_sweeps(backend, golden):
         _check(h, lib.fr3d_level_begin(h, li, dev.ptr(mvd), None, B))
         _check(h, lib.fr3d_level_sweeps(h, li, -1, -1, -1, -1))
         _check(h, lib.fr3d_level_end(h, li))
+
+
+def test_imregister_interleaved_flow_views_equal_separate_planes(backend):
+    """imregister_wrapper called with the three component views of ONE float32 (Z,Y,X,3) flow array (what the
+    reference's executors pass, sequential_3d.py:148-160) takes a single-upload path; it must equal the call with
+    three separate planes bit for bit, for both interpolations, and equal the oracle like the plain path does."""
+    import flowreg3d_b200 as F
+    from tests_inputs import smooth_flow
+    rng = np.random.default_rng(4)
+    shp = (7, 30, 44)
+    f2, f1 = rng.random(shp + (2,)).astype(np.float32), rng.random(shp + (2,)).astype(np.float32)
+    flow = (smooth_flow(shp, 6, 2.5, 4.0) * np.array([1.0, -1.5, 0.7])).astype(np.float32)
+    for meth in ("cubic", "linear"):
+        a = F.imregister_wrapper(f2, flow[..., 0], flow[..., 1], flow[..., 2], f1, meth)
+        b = F.imregister_wrapper(f2, flow[..., 0].copy(), flow[..., 1].copy(), flow[..., 2].copy(), f1, meth)
+        assert np.array_equal(a, b), meth
+        o = O.imregister_wrapper(f2, flow[..., 0], flow[..., 1], flow[..., 2], f1, meth)
+        assert ulp_diff(a, o).max() <= 1
