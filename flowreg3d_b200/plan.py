@@ -173,7 +173,7 @@ class PlanHolder:
     """Owns the ctypes fr3d_plan and every host buffer it points to."""
 
     def __init__(self, shape, C_: int, fp: FlowParams, max_batch: int = 1, interp: int = 3,
-                 sigma=None, sweep: int = SWEEP_LEXICOGRAPHIC, state_dtype=np.float32):
+                 sigma=None, sweep: int = SWEEP_LEXICOGRAPHIC, state_dtype=np.float64):
         Z, Y, X = (int(s) for s in shape)
         self.shape = (Z, Y, X)
         self.C = int(C_)

@@ -91,9 +91,11 @@ typedef struct {
                                    * recomputed every sweep (level_solver_3d.py:262-311); lexicographic sweep only */
     int32_t sweep;                /* fr3d_sweep */
     int32_t interp;               /* compensation warp: 3 = cubic B-spline, 1 = trilinear */
-    int32_t state_dtype;          /* solver state storage (du,dv,dw and the constant Laplacian term):
-                                   * FR3D_F32 (default; SURVEY 7.3-D: far inside the tolerance) or
-                                   * FR3D_F64 (strict).  The system matrix and all arithmetic are float64. */
+    int32_t state_dtype;          /* solver state storage (du,dv,dw and the constant Laplacian term): FR3D_F64 (what the
+                                   * Python host passes by default: the reference to float64 rounding) or FR3D_F32
+                                   * (24 % fewer solver bytes; inside the 0.01 / 0.05 voxel tolerance on configs 2 and
+                                   * 4, outside on one measured workload -- DESIGN.md 4.1).  The system matrix and all
+                                   * arithmetic are float64 either way. */
     /* pre-filter (util/image_processing_3D.py:95-162): normalised Gaussian half-kernels
      * w[0..r] (w[0] = centre) per channel and axis (z, y, x); r = 0 means identity.  HOST. */
     int32_t gauss_radius[FR3D_MAX_CHANNELS][3];

@@ -40,7 +40,23 @@ device = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=device)
 shape, C = tuple(args.shape), args.channels
-ref = np.stack([synth_volume(shape, 10 + c) for c in range(C)], -1)
+
+
+def cached_volume(shape, seed):
+    """synth_volume with a per-box file cache (the 128x1024x1024 volume costs a minute of scipy per rank otherwise);
+    rank 0 generates, the others wait for the file."""
+    import time
+    path = Path("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp") / f"fr3d_synth_{'x'.join(map(str, shape))}_{seed}.npy"
+    if rank == 0 and not path.exists():
+        tmp = path.with_suffix(".tmp.npy")
+        np.save(tmp, synth_volume(shape, seed))
+        os.replace(tmp, path)
+    while not path.exists():
+        time.sleep(0.2)
+    return np.load(path)
+
+
+ref = np.stack([cached_volume(shape, 10 + c) for c in range(C)], -1)
 mov = np.roll(ref, (0, 2, -3), (0, 1, 2)) + 0.01 * np.random.default_rng(0).standard_normal(ref.shape).astype(np.float32)
 fp = F.FlowParams(alpha=(0.25,) * 3, update_lag=5, iterations=args.iterations, min_level=args.min_level, levels=100,
                   eta=0.8, a_smooth=1.0, a_data=0.45)
