@@ -367,6 +367,39 @@ class SequenceCorrector:
         drain(K - 1)
         return out_reg, out_flow
 
+    def run_stream(self, batches, sink: Callable, lookahead: int = 1):
+        """Streaming form of run_pipelined for recordings that do not fit in host memory: `batches` is any iterable
+        of host batches (t,Z,Y,X,C) -- e.g. a generator around the reference's reader,
+        `(b for b in iter_batches(reader))` with `while reader.has_batch(): yield reader.read_batch()`
+        (util/io/_base_3d.py:230-256); a `None` item ends the stream -- and `sink(k, registered, flows)` receives the
+        host tensors of batch k in order as soon as they have arrived (e.g. `writer.write_frames(registered.numpy())`,
+        `:339-345`).  Batches are pulled `lookahead` ahead of the one being computed; the copy / compute / copy overlap
+        is that of run_pipelined, which is called on a sliding window of the stream."""
+        it = iter(batches)
+        window, k0 = [], 0
+
+        def pull():
+            try:
+                b = next(it)
+            except StopIteration:
+                return False
+            if b is None:
+                return False
+            window.append(b)
+            return True
+
+        while len(window) < 1 + lookahead and pull():
+            pass
+        while window:
+            # process everything pulled so far as one pipelined run (H2D of the later batches overlaps the compute of
+            # the earlier ones), then refill the window
+            chunk, window = window, []
+            base = k0
+            self.run_pipelined(chunk, sink=lambda k, r, f, base=base: sink(base + k, r, f))
+            k0 += len(chunk)
+            while len(window) < 1 + lookahead and pull():
+                pass
+
     def statistics(self) -> dict:
         """The per-frame lists BatchMotionCorrector keeps (compensate_recording_3D.py:488-508) for this rank's
         frames so far: mean_disp, max_disp, mean_div, mean_translation (computed on the device from the flows)."""

@@ -298,3 +298,40 @@ def test_per_pair_functions_are_thread_safe(backend, golden):
     assert not errs, errs
     for (fa, ra), (fb, rb) in zip(serial, out):
         assert np.array_equal(fa, fb) and np.array_equal(ra, rb)
+
+
+def test_run_stream_from_a_reader_like_iterator(backend, golden):
+    """SequenceCorrector.run_stream: batches pulled from an iterator (the reference's reader.read_batch() pattern,
+    util/io/_base_3d.py:230-251) and handed to a sink in order (writer.write_frames) give exactly what the in-memory
+    entry point gives."""
+    import flowreg3d_b200 as F
+    g = golden("sequence")
+    v, r = g["video"][:, :12, :24, :28], g["ref"][:12, :24, :28]
+    opts = F.OFOptions(min_level=3, iterations=6, update_lag=3, buffer_size=3, weight=[0.5, 0.5], output_typename=None)
+    reg1, w1 = F.compensate_arr_3D(v, r, opts)
+
+    class Reader:                      # the reference's reader protocol: read_batch() -> array or None
+        def __init__(self, arr, bs):
+            self.arr, self.bs, self.at = arr, bs, 0
+
+        def read_batch(self):
+            if self.at >= self.arr.shape[0]:
+                return None
+            b = self.arr[self.at:self.at + self.bs]
+            self.at += self.bs
+            return b
+
+    got_reg, got_w, order = [], [], []
+    seq = F.SequenceCorrector(r, opts)
+    try:
+        rd = Reader(v, 3)
+
+        def batches():                 # `while reader.has_batch(): yield reader.read_batch()`; None ends the stream
+            while True:
+                yield rd.read_batch()
+        seq.run_stream(batches(),
+                       sink=lambda k, reg, fl: (order.append(k), got_reg.append(reg.numpy().copy()), got_w.append(fl.numpy().copy())))
+    finally:
+        seq.close()
+    assert order == list(range(len(order))) and len(order) == 3
+    assert np.array_equal(np.concatenate(got_w, 0), w1) and np.array_equal(np.concatenate(got_reg, 0), reg1)
