@@ -538,6 +538,41 @@ FR3D_HD size_t dtype_size(int dt)
     return 0;
 }
 
+// The same read split in two: the raw bits now (a load whose result nobody waits for yet), the conversion later.
+FR3D_HD uint64_t load_raw_bits(const void* base, int dt, int64_t i)
+{
+    switch (dt) {
+    case FR3D_F32: return (uint64_t)((const uint32_t*)base)[i];
+    case FR3D_F64: return ((const uint64_t*)base)[i];
+    case FR3D_U8: return (uint64_t)((const uint8_t*)base)[i];
+    case FR3D_U16: return (uint64_t)((const uint16_t*)base)[i];
+    case FR3D_I16: return (uint64_t)(uint16_t)((const int16_t*)base)[i];
+    case FR3D_I32: return (uint64_t)(uint32_t)((const int32_t*)base)[i];
+    }
+    return 0;
+}
+FR3D_HD double raw_bits_as_double(uint64_t bits, int dt)
+{
+    switch (dt) {
+    case FR3D_F32: {
+        const uint32_t b32 = (uint32_t)bits;
+        float f;
+        memcpy(&f, &b32, 4);
+        return (double)f;
+    }
+    case FR3D_F64: {
+        double d;
+        memcpy(&d, &bits, 8);
+        return d;
+    }
+    case FR3D_U8: return (double)(uint8_t)bits;
+    case FR3D_U16: return (double)(uint16_t)bits;
+    case FR3D_I16: return (double)(int16_t)(uint16_t)bits;
+    case FR3D_I32: return (double)(int32_t)(uint32_t)bits;
+    }
+    return 0.0;
+}
+
 // Read one element of a dtype-tagged array as double (exact for every supported dtype).
 FR3D_HD double load_as_double(const void* base, int dt, int64_t i)
 {

@@ -222,6 +222,14 @@ struct PreZWinK {
             win[j] = (load_as_double(raw, dt, base + (int64_t)reflect_idx(j - R, Z) * zs) - lo) / den;
         double* o = out + (((int64_t)b * C + c) * Z * Y + y) * X + x;
         const int64_t os = (int64_t)Y * X;
+        // the column's next samples are requested LA planes ahead as RAW bits (the conversion and the division wait
+        // until the sample enters the window): with one load per iteration consumed by the next one, the kernel sat
+        // on the plane-strided loads (ncu, round 2: 50 % of the stall samples on the conversion after the load)
+        constexpr int LA = 6;
+        uint64_t q[LA];
+#pragma unroll
+        for (int a = 0; a < LA; ++a)
+            q[a] = load_raw_bits(raw, dt, base + (int64_t)reflect_idx(R + 1 + a, Z) * zs);
         for (int z = 0; z < Z; ++z) {
             double t = win[R] * w[0];
 #pragma unroll
@@ -231,8 +239,11 @@ struct PreZWinK {
 #pragma unroll
             for (int j = 0; j < 2 * R; ++j)
                 win[j] = win[j + 1];
-            if (z + 1 < Z)
-                win[2 * R] = (load_as_double(raw, dt, base + (int64_t)reflect_idx(z + 1 + R, Z) * zs) - lo) / den;
+            win[2 * R] = (raw_bits_as_double(q[0], dt) - lo) / den;       // sample z + 1 + R (unused after the last plane)
+#pragma unroll
+            for (int a = 0; a + 1 < LA; ++a)
+                q[a] = q[a + 1];
+            q[LA - 1] = load_raw_bits(raw, dt, base + (int64_t)reflect_idx(z + 2 + R + LA - 1, Z) * zs);
         }
     }
 };
@@ -409,10 +420,34 @@ struct PreYXWinK {
         if (sub == 0) {
             const double* plane = in + (((int64_t)b * C + c) * Z + z) * Y * X;
             const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
-            for (int yy = warp; yy < IH; yy += nwarps) {
-                const double* row = plane + (int64_t)reflect_idx(y0 - R + yy, Y) * X;
-                for (int xx = lane; xx < IW; xx += 32)
-                    tin[yy * IW + xx] = row[reflect_idx(x0 - R + xx, X)];
+            // all loads of a thread are issued before its first store to shared memory: a store waits for its load,
+            // and the warp issues in order, so the plain load/store loop serialised up to 9 DRAM latencies per
+            // thread (ncu, round 2: 44 % of the kernel's stall samples on that STS)
+            constexpr int XR = (IW + 31) / 32;
+            for (int yy = warp; yy < IH; yy += 2 * nwarps) {
+                double v[2][XR];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int y2 = yy + u * nwarps;
+                    const double* row = plane + (int64_t)reflect_idx(y0 - R + (y2 < IH ? y2 : yy), Y) * X;
+#pragma unroll
+                    for (int k = 0; k < XR; ++k) {
+                        const int xx = lane + 32 * k;
+                        v[u][k] = row[reflect_idx(x0 - R + (xx < IW ? xx : lane), X)];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int y2 = yy + u * nwarps;
+                    if (y2 < IH) {
+#pragma unroll
+                        for (int k = 0; k < XR; ++k) {
+                            const int xx = lane + 32 * k;
+                            if (xx < IW)
+                                tin[y2 * IW + xx] = v[u][k];
+                        }
+                    }
+                }
             }
         } else if (sub == 1) {
             // task = (column xx, run of 8 rows)
