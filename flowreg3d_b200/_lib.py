@@ -24,6 +24,7 @@ OPT_SOR_KERNEL = 4
 OPT_SOR_STAGES = 5
 OPT_SOR_TILE = 6
 OPT_SPLINE_TMA = 7
+OPT_RESIZE_X_ROWS = 8
 _DTYPES = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.uint8): U8,
            np.dtype(np.uint16): U16, np.dtype(np.int16): I16, np.dtype(np.int32): I32}
 

@@ -179,6 +179,26 @@ static void resize_pass(fr3d_ctx* c, const SrcT* src, const int64_t ss[5], DstT*
             launch(c->dev, k, nb * n[1] * n[2] * runs * 32);
             continue;
         }
+        if (r == 3 && n[2] >= 8 && c->dev.resize_x_rows) {
+            // X pass: 4 rows per thread share the tap look-ups of their output position
+            constexpr int RY = 4;
+            ResizeXRowsK<SrcT, DstT, RY> k;
+            const int64_t groups = (n[2] + RY - 1) / RY;
+            k.src = src + b0 * ss[0];
+            k.dst = dst + b0 * ds[0];
+            for (int q = 0; q < 5; ++q) {
+                k.ss[q] = ss[q];
+                k.ds[q] = ds[q];
+                k.fd[q] = FastDiv((uint32_t)(q == 2 ? groups : n[q]));
+            }
+            k.P = t.P;
+            k.n4 = (int)n[4];
+            k.n2 = (int)n[2];
+            k.idx = t.idx.p;
+            k.wt = t.wt.p;
+            launch(c->dev, k, nb * n[1] * groups * n[3]);
+            continue;
+        }
         ResizePassK<SrcT, DstT> k;
         k.src = src + b0 * ss[0];
         k.dst = dst + b0 * ds[0];
@@ -763,6 +783,10 @@ int fr3d_set_option(fr3d_ctx* ctx, int option, int64_t value)
     case FR3D_OPT_SOR_KERNEL:
         FR3D_REQUIRE(value >= 0 && value <= 2, "FR3D_OPT_SOR_KERNEL: %lld", (long long)value);
         _c->dev.sor_kernel = (int)value;
+        break;
+    case FR3D_OPT_RESIZE_X_ROWS:
+        FR3D_REQUIRE(value == 0 || value == 1, "FR3D_OPT_RESIZE_X_ROWS: %lld", (long long)value);
+        _c->dev.resize_x_rows = (int)value;
         break;
     case FR3D_OPT_SPLINE_TMA:
         FR3D_REQUIRE(value == 0 || value == 1, "FR3D_OPT_SPLINE_TMA: %lld", (long long)value);

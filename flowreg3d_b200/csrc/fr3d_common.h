@@ -82,6 +82,7 @@ struct Device {
     int sor_kernel = 0;      // FR3D_OPT_SOR_KERNEL: 2 time-blocked tiles (fr3d_sor_tile.h), 1 staged wavefront (TMA bulk
                              // copies + mbarrier ring), 0 direct-load wavefront
     int sor_stages = 0;      // stages per warp of the staged kernel, 0 = default (FR3D_OPT_SOR_STAGES)
+    int resize_x_rows = 1;   // FR3D_OPT_RESIZE_X_ROWS: X resampling pass with 4 rows per thread sharing the tap look-ups
     int spline_tma = 1;      // FR3D_OPT_SPLINE_TMA: bulk-copy (TMA) staging of the spline X pass
     int sor_tile_sweeps = 0, sor_tile_k = 0, sor_tile_j = 0, sor_tile_i = 0; // FR3D_OPT_SOR_TILE (0 = defaults)
     int sor_k0 = 0, sor_k1 = 0; // plane range of a z-slab solver launch (0, 0: all planes); set around the launch

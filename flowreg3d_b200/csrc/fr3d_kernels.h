@@ -118,6 +118,61 @@ struct ResizePassK {
     }
 };
 
+// Resampling along the FASTEST axis (axis 3, the X pass): a thread produces the outputs of RY consecutive rows
+// (axis 2) at one output position, so the tap indices and weights of that position are looked up once for RY rows
+// (and all interleaved channels) instead of once per output -- the X pass is bound by load instructions (ncu, round 2:
+// 24 % of its stall samples are LSU-queue throttling, 42 table + sample loads per output).  Lanes stay on consecutive
+// output positions, as in ResizePassK; per output the products are formed and accumulated in the same order.
+template <class SrcT, class DstT, int RY>
+struct ResizeXRowsK {
+    const SrcT* src;
+    DstT* dst;
+    int64_t ss[5], ds[5];
+    FastDiv fd[5]; // fd[2]: row groups (ceil(n2 / RY)); fd[1], fd[3] as in ResizePassK
+    int P, n4, n2;
+    const int32_t* idx;
+    const float* wt;
+    FR3D_HD void operator()(int64_t item) const
+    {
+        uint32_t i[4];
+        uint32_t e = (uint32_t)item;
+        fd[3].divmod(e, e, i[3]);
+        fd[2].divmod(e, e, i[2]);
+        fd[1].divmod(e, i[0], i[1]);
+        const int y0 = (int)i[2] * RY;
+        const int64_t so = (int64_t)i[0] * ss[0] + (int64_t)i[1] * ss[1] + (int64_t)y0 * ss[2];
+        const int64_t dof = (int64_t)i[0] * ds[0] + (int64_t)i[1] * ds[1] + (int64_t)y0 * ds[2] + (int64_t)i[3] * ds[3];
+        const int32_t* ix = idx + (int64_t)i[3] * P;
+        const float* w = wt + (int64_t)i[3] * P;
+        const int64_t sr = ss[3];
+        int nrow = n2 - y0;
+        nrow = nrow > RY ? RY : nrow;
+        for (int q = 0; q < n4; ++q) {
+            const SrcT* sp = src + so + q * ss[4];
+            double acc[RY];
+#pragma unroll
+            for (int u = 0; u < RY; ++u)
+                acc[u] = 0.0;
+            for (int p = 0; p < P; ++p) {
+                const SrcT* tp = sp + (int64_t)ix[p] * sr;
+                const float wp = w[p];
+#pragma unroll
+                for (int u = 0; u < RY; ++u) {
+                    if (u < nrow) {
+                        const float a = (float)tp[(int64_t)u * ss[2]];
+                        const float prod = a * wp;
+                        acc[u] += (double)prod;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < RY; ++u)
+                if (u < nrow)
+                    dst[dof + (int64_t)u * ds[2] + q * ds[4]] = (DstT)(float)acc[u];
+        }
+    }
+};
+
 // ------------------------------------------------------------------------------------------
 // Pre-processing (util/image_processing_3D.py:12-162): (x - lo)/den then a separable Gaussian,
 // scipy correlate1d symmetric form  t = x[l]*w0 + sum_{j=r..1} (x[l-j] + x[l+j])*w[j]  in float64,

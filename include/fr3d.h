@@ -140,6 +140,8 @@ typedef enum {
     FR3D_OPT_SPLINE_TMA = 7,      /* B-spline prefilter X pass: 1 (default) = the block's lines are staged with ONE bulk copy
                                    * global -> shared (cp.async.bulk + mbarrier) and written back with one bulk copy
                                    * shared -> global; 0 = per-thread staging loops.  Same arithmetic: bit-identical */
+    FR3D_OPT_RESIZE_X_ROWS = 8,   /* pyramid X pass: 1 (default) = a thread resamples 4 rows at one output position and
+                                   * looks the taps up once; 0 = one output per thread.  Bit-identical */
     FR3D_OPT_SOR_TILE = 6         /* tile kernel geometry: Tb | K << 8 | J << 16 | I << 24 (sweeps per time block and
                                    * tile extents; a 0 field keeps its default: 5 sweeps, 8 x 8 x 8) */
 } fr3d_option;
