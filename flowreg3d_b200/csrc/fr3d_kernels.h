@@ -277,14 +277,9 @@ struct PreZWinK {
             win[j] = (load_as_double(raw, dt, base + (int64_t)reflect_idx(j - R, Z) * zs) - lo) / den;
         double* o = out + (((int64_t)b * C + c) * Z * Y + y) * X + x;
         const int64_t os = (int64_t)Y * X;
-        // the column's next samples are requested LA planes ahead as RAW bits (the conversion and the division wait
-        // until the sample enters the window): with one load per iteration consumed by the next one, the kernel sat
-        // on the plane-strided loads (ncu, round 2: 50 % of the stall samples on the conversion after the load)
-        constexpr int LA = 6;
-        uint64_t q[LA];
-#pragma unroll
-        for (int a = 0; a < LA; ++a)
-            q[a] = load_raw_bits(raw, dt, base + (int64_t)reflect_idx(R + 1 + a, Z) * zs);
+        // (Measured and rejected, round 2: requesting the column's samples six planes ahead as raw bits -- the ncu
+        // source view puts half of this kernel's stall samples on the conversion behind its one load per plane --
+        // made the kernel slower, 3.4 vs 2.8 ms per 25-frame step: more registers, same latency chain.)
         for (int z = 0; z < Z; ++z) {
             double t = win[R] * w[0];
 #pragma unroll
@@ -294,11 +289,8 @@ struct PreZWinK {
 #pragma unroll
             for (int j = 0; j < 2 * R; ++j)
                 win[j] = win[j + 1];
-            win[2 * R] = (raw_bits_as_double(q[0], dt) - lo) / den;       // sample z + 1 + R (unused after the last plane)
-#pragma unroll
-            for (int a = 0; a + 1 < LA; ++a)
-                q[a] = q[a + 1];
-            q[LA - 1] = load_raw_bits(raw, dt, base + (int64_t)reflect_idx(z + 2 + R + LA - 1, Z) * zs);
+            if (z + 1 < Z)
+                win[2 * R] = (load_as_double(raw, dt, base + (int64_t)reflect_idx(z + 1 + R, Z) * zs) - lo) / den;
         }
     }
 };

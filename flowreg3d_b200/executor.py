@@ -116,7 +116,7 @@ class B200Executor3D(_Base):
                 mv = np.asarray(batch_proc[t0:t1]).astype(np.float32)
                 flow = reg.get_displacement(mv, uvw=uvt)
             out = reg.compensate(batch[t0:t1], flow)
-            reg.sync()
+            reg.ctx.order_with_torch()            # the device -> host copies below are ordered by the stream
             flows[t0:t1] = dev.to_host(flow)
             registered[t0:t1] = dev.to_host(out)  # numpy cast to the batch dtype, as sequential_3d.py:163-169
             if progress_callback is not None:
