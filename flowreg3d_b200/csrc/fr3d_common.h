@@ -394,11 +394,21 @@ void launch(Device& dev, const K& k, int64_t n)
     dev.launches++;
 }
 
-// {x,y,z,w} vector with natural 4-element alignment: float -> one 16-byte access, double -> two.
+// Solver state vector {du, dv, dw}.  float: padded to four components (one 16-byte access per voxel).  double: THREE
+// components, 24 bytes per voxel (round 2: the fourth word was 8 of the 32 + 32 bytes the float64 state moves per
+// voxel and sweep for its own value, and of every 32-byte neighbour gather; the accesses become three 8-byte ones,
+// still contiguous across a warp).  The name is kept from the padded layout; `set_pad` clears the fourth component
+// where there is one.
 template <class T>
-struct alignas(4 * sizeof(T) > 16 ? 16 : 4 * sizeof(T)) Vec4 {
+struct alignas(16) Vec4 {
     T x, y, z, w;
 };
+template <>
+struct alignas(8) Vec4<double> {
+    double x, y, z;
+};
+FR3D_HD void set_pad(Vec4<float>& v) { v.w = 0.0f; }
+FR3D_HD void set_pad(Vec4<double>&) {}
 
 // L2-only (cache-global) vector load / store: data written by other SMs in the previous wave
 FR3D_HD Vec4<float> ld4_cg(const Vec4<float>* p)
@@ -418,13 +428,11 @@ FR3D_HD Vec4<float> ld4_cg(const Vec4<float>* p)
 FR3D_HD Vec4<double> ld4_cg(const Vec4<double>* p)
 {
 #ifdef __CUDA_ARCH__
-    const double2 a = __ldcg(reinterpret_cast<const double2*>(p));
-    const double2 b = __ldcg(reinterpret_cast<const double2*>(p) + 1);
+    const double* q = reinterpret_cast<const double*>(p);
     Vec4<double> r;
-    r.x = a.x;
-    r.y = a.y;
-    r.z = b.x;
-    r.w = b.y;
+    r.x = __ldcg(q);
+    r.y = __ldcg(q + 1);
+    r.z = __ldcg(q + 2);
     return r;
 #else
     return *p;
@@ -446,21 +454,7 @@ FR3D_HD Vec4<float> ld4_ca(const Vec4<float>* p)
     return *p;
 #endif
 }
-FR3D_HD Vec4<double> ld4_ca(const Vec4<double>* p)
-{
-#ifdef __CUDA_ARCH__
-    const double2 a = *reinterpret_cast<const double2*>(p);
-    const double2 b = *(reinterpret_cast<const double2*>(p) + 1);
-    Vec4<double> r;
-    r.x = a.x;
-    r.y = a.y;
-    r.z = b.x;
-    r.w = b.y;
-    return r;
-#else
-    return *p;
-#endif
-}
+FR3D_HD Vec4<double> ld4_ca(const Vec4<double>* p) { return *p; }
 FR3D_HD void st4_cg(Vec4<float>* p, const Vec4<float>& v)
 {
 #ifdef __CUDA_ARCH__
@@ -472,8 +466,10 @@ FR3D_HD void st4_cg(Vec4<float>* p, const Vec4<float>& v)
 FR3D_HD void st4_cg(Vec4<double>* p, const Vec4<double>& v)
 {
 #ifdef __CUDA_ARCH__
-    __stcg(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
-    __stcg(reinterpret_cast<double2*>(p) + 1, make_double2(v.z, v.w));
+    double* q = reinterpret_cast<double*>(p);
+    __stcg(q, v.x);
+    __stcg(q + 1, v.y);
+    __stcg(q + 2, v.z);
 #else
     *p = v;
 #endif

@@ -1420,14 +1420,14 @@ struct AssembleK {
         Lv.x = (ST)Lq[0];
         Lv.y = (ST)Lq[1];
         Lv.z = (ST)Lq[2];
-        Lv.w = (ST)0;
+        set_pad(Lv);
         L[(int64_t)b * np + a] = Lv;
         if (U) {
             Vec4<ST> Uv;
             Uv.x = (ST)Uq[0];
             Uv.y = (ST)Uq[1];
             Uv.z = (ST)Uq[2];
-            Uv.w = (ST)0;
+            set_pad(Uv);
             U[(int64_t)b * np + a] = Uv;
         }
     }

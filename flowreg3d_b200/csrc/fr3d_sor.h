@@ -180,7 +180,7 @@ FR3D_HD Vec4<ST> sor_update(const SorParams<ST>& P, const SorIn<ST>& r)
     o.x = (ST)du_n;
     o.y = (ST)dv_n;
     o.z = (ST)dw_n;
-    o.w = (ST)0;
+    set_pad(o);
     return o;
 }
 
@@ -307,7 +307,7 @@ FR3D_HD void sor_load(const SorParams<ST>& P, const SorLoc& L, int b, bool with_
     }
     if (with_ab) {
         // plain sweep: the constant Laplacian term was folded into b1..b3 at the last refresh
-        r.L.x = r.L.y = r.L.z = r.L.w = (ST)0;
+        r.L.x = r.L.y = r.L.z = (ST)0;
         const double* AB = P.AB + sor_ab_at(P, b, L.a, 0);
 #pragma unroll
         for (int k = 0; k < 9; ++k)
@@ -587,7 +587,7 @@ FR3D_HD void sor_nl_update(const SorParams<ST>& P, int64_t a, int b, int t)
     o.x = (ST)du_n;
     o.y = (ST)dv_n;
     o.z = (ST)dw_n;
-    o.w = (ST)0;
+    set_pad(o);
     st4_cg(P.dold + (int64_t)b * np + a, own);
     st4_cg(d + a, o);
 }
@@ -1238,7 +1238,7 @@ fr3d_sor_staged(const SorParams<ST> P, unsigned* bar, int tabs_in_smem, int NS)
                 for (int k = 0; k < 9; ++k)
                     FR3D_STCG(AB + k * 32, r.A[k]);
             } else {
-                r.L.x = r.L.y = r.L.z = r.L.w = (ST)0;
+                r.L.x = r.L.y = r.L.z = (ST)0;
                 const double* A = reinterpret_cast<const double*>(fr) + lane;
 #pragma unroll
                 for (int k = 0; k < 9; ++k)

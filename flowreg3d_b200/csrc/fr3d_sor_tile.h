@@ -449,7 +449,7 @@ FR3D_HD void sor_tile_task(const SorParams<ST>& P, const SorTileGeom& G, const S
             in.yp.x = su[cyp], in.yp.y = sv[cyp], in.yp.z = sw[cyp];
             in.zm.x = su[czm], in.zm.y = sv[czm], in.zm.z = sw[czm];
             in.zp.x = su[czp], in.zp.y = sv[czp], in.zp.z = sw[czp];
-            in.L.x = in.L.y = in.L.z = in.L.w = (ST)0;
+            in.L.x = in.L.y = in.L.z = (ST)0;
             if (refresh) {
                 // general geometry (lag % Tb != 0): the refresh rides inside the wave, as in the wavefront kernel
                 const Vec4<ST> L = ld4_cg(P.L + (int64_t)frame * np + a);
@@ -486,7 +486,7 @@ FR3D_HD void sor_tile_task(const SorParams<ST>& P, const SorTileGeom& G, const S
             v.x = su[c];
             v.y = sv[c];
             v.z = sw[c];
-            v.w = (ST)0;
+            set_pad(v);
             st4_cg(dg + FR3D_TILE_SLOT(k, j, i), v);
         }
     }

@@ -124,6 +124,7 @@ def get_displacement_pipelined(reg: Registration, moving_proc, uvw=None, group=N
         out = dev.empty((B,) + reg.shape + (3,), out_dtype, reg.device)
     T, lag = int(reg.plan.plan.iterations), int(reg.plan.plan.update_lag)
     state_dt = np.float64 if reg.plan.plan.state_dtype == _lib.F64 else np.float32
+    vlen = 3 if state_dt == np.float64 else 4      # components per state vector (float32 vectors are padded to 16 bytes)
     pipelinable = reg.plan.plan.sweep == 0 and float(reg.plan.plan.a_smooth) == 1.0
     nl = lib.fr3d_level_count(h)
     keep = []
@@ -152,7 +153,7 @@ def get_displacement_pipelined(reg: Registration, moving_proc, uvw=None, group=N
                 for rcv, _, _, _ in sched[rank]:
                     if rcv is not None:
                         a, b = int(start[rcv[0]]), int(start[rcv[1]])
-                        buf = dev.empty((B, b - a, 4), state_dt, reg.device)
+                        buf = dev.empty((B, b - a, vlen), state_dt, reg.device)
                         pending.append((buf, dist.irecv(buf, src=_global_rank(group, src), group=g_in)))
                         keep.append(buf)
                 for rcv, q0, q1, snd in sched[rank]:
@@ -164,11 +165,11 @@ def get_displacement_pipelined(reg: Registration, moving_proc, uvw=None, group=N
                     _check(h, lib.fr3d_level_sweeps(h, li, t0, t1, q0, q1))
                     if snd is not None:
                         a, b = int(start[snd[0]]), int(start[snd[1]])
-                        buf = dev.empty((B, b - a, 4), state_dt, reg.device)
+                        buf = dev.empty((B, b - a, vlen), state_dt, reg.device)
                         _check(h, lib.fr3d_level_state(h, li, 0, dev.ptr(buf), a, b))
                         keep.append((buf, dist.isend(buf, dst=_global_rank(group, dst), group=g_out)))
             # the last active rank holds the finished increments: hand them to everybody
-            full = dev.empty((B, nslots, 4), state_dt, reg.device)
+            full = dev.empty((B, nslots, vlen), state_dt, reg.device)
             if rank == active[-1]:
                 _check(h, lib.fr3d_level_state(h, li, 0, dev.ptr(full), 0, nslots))
             dist.broadcast(full, src=_global_rank(group, active[-1]), group=group)
@@ -316,6 +317,7 @@ def get_displacement_zslab(reg: Registration, moving_proc, uvw=None, group=None,
         out = dev.empty((B,) + reg.shape + (3,), out_dtype, reg.device)
     T = int(reg.plan.plan.iterations)
     state_dt = np.float64 if reg.plan.plan.state_dtype == _lib.F64 else np.float32
+    vlen = 3 if state_dt == np.float64 else 4      # components per state vector (float32 vectors are padded to 16 bytes)
     slabbable = reg.plan.plan.sweep == 0 and float(reg.plan.plan.a_smooth) == 1.0
     nl = lib.fr3d_level_count(h)
     keep = []
@@ -342,7 +344,7 @@ def get_displacement_zslab(reg: Registration, moving_proc, uvw=None, group=None,
         plane = py * px
 
         def planes_out(k0, k1):
-            buf = dev.empty((B, (k1 - k0) * plane, 4), state_dt, reg.device)
+            buf = dev.empty((B, (k1 - k0) * plane, vlen), state_dt, reg.device)
             _check(h, lib.fr3d_level_planes(h, li, 0, dev.ptr(buf), k0, k1))
             reg.ctx.order_with_torch()                       # the buffer leaves through torch.distributed
             return buf
@@ -351,7 +353,7 @@ def get_displacement_zslab(reg: Registration, moving_proc, uvw=None, group=None,
             _check(h, lib.fr3d_level_planes(h, li, 1, dev.ptr(buf), k0, k1))
 
         def cells_out(k, q):
-            buf = torch.zeros((B, T * py, 4), dtype=dev.torch_dtype(state_dt), device=reg.device)
+            buf = torch.zeros((B, T * py, vlen), dtype=dev.torch_dtype(state_dt), device=reg.device)
             _check(h, lib.fr3d_level_wave_cells(h, li, 0, dev.ptr(buf), k, q))
             reg.ctx.order_with_torch()                       # the buffer leaves through torch.distributed
             return buf
@@ -373,13 +375,13 @@ def get_displacement_zslab(reg: Registration, moving_proc, uvw=None, group=None,
             ops, recvs = [], []
             if lo is not None:
                 sb = cells_out(z0, q)
-                rb = dev.empty((B, T * py, 4), state_dt, reg.device)
+                rb = dev.empty((B, T * py, vlen), state_dt, reg.device)
                 ops += [dist.P2POp(dist.isend, sb, lo, group), dist.P2POp(dist.irecv, rb, lo, group)]
                 recvs.append((rb, z0 - 1))
                 keep.append(sb)
             if hi is not None:
                 sb = cells_out(z1 - 1, q)
-                rb = dev.empty((B, T * py, 4), state_dt, reg.device)
+                rb = dev.empty((B, T * py, vlen), state_dt, reg.device)
                 ops += [dist.P2POp(dist.isend, sb, hi, group), dist.P2POp(dist.irecv, rb, hi, group)]
                 recvs.append((rb, z1))
                 keep.append(sb)
@@ -391,7 +393,7 @@ def get_displacement_zslab(reg: Registration, moving_proc, uvw=None, group=None,
         tm = _mark("sweeps_slab", tm)
         # gather the slabs of the finished increments: every rank needs them around its planes for the median
         for r, (a, b) in enumerate(bounds):
-            buf = planes_out(a, b) if r == rank else dev.empty((B, (b - a) * plane, 4), state_dt, reg.device)
+            buf = planes_out(a, b) if r == rank else dev.empty((B, (b - a) * plane, vlen), state_dt, reg.device)
             dist.broadcast(buf, src=_global_rank(group, r), group=group)
             if r != rank:
                 planes_in(buf, a, b)

@@ -183,7 +183,7 @@ int fr3d_get_displacement(fr3d_ctx* ctx, const float* moving_proc, const float* 
  *                      multiple of update_lag.  Lexicographic sweep, a_smooth == 1 only for partial ranges.
  *   fr3d_level_state   copy the increments of solver-storage slots [slot_begin, slot_end) of all B frames
  *                      out of (direction 0) or into (direction 1) `ext` (device, B x (slot_end-slot_begin)
- *                      4-vectors {du,dv,dw,-} of the state dtype).  Hyperplane s = k+j+i occupies the slots
+ *                      state vectors: {du,dv,dw,-} float32 (16 bytes) or {du,dv,dw} float64 (24 bytes)).  Hyperplane s = k+j+i occupies the slots
  *                      hyperplane_start[s] .. hyperplane_start[s+1] reported by fr3d_level_info, so a range of
  *                      hyperplanes is one contiguous block per frame.
  *   fr3d_level_end     increments -> 5^3 median -> accumulate into the flow
@@ -204,11 +204,11 @@ int fr3d_level_state(fr3d_ctx* ctx, int level, int direction, void* ext, int64_t
  * of the level.  fr3d_level_sweeps_slab runs the waves [q_begin, q_end) of ALL sweeps restricted to those planes
  * (a voxel of wave q reads nothing newer than wave q-1, so the ranks exchange, after every wave, the boundary planes
  * they own); fr3d_level_planes copies whole planes of the increments out of (direction 0) or into (1) `ext`
- * (device, B x (k_end-k_begin) x py x px 4-vectors {du,dv,dw,-} of the state dtype). */
+ * (device, B x (k_end-k_begin) x py x px state vectors: 4 float32 or 3 float64 components). */
 int fr3d_level_sweeps_slab(fr3d_ctx* ctx, int level, int q_begin, int q_end, int k_begin, int k_end);
 int fr3d_level_planes(fr3d_ctx* ctx, int level, int direction, void* ext, int k_begin, int k_end);
 /* The cells of plane k that wave q updated (one anti-diagonal per sweep in flight) out of (0) / into (1) `ext`
- * (device, B x iterations x py 4-vectors; entries without a cell are not touched): the per-wave halo message. */
+ * (device, B x iterations x py state vectors; entries without a cell are not touched): the per-wave halo message. */
 int fr3d_level_wave_cells(fr3d_ctx* ctx, int level, int direction, void* ext, int k, int q);
 /* The same z-slab solve with the halo exchange INSIDE the persistent kernel (one launch per level instead of one
  * launch + two pack kernels + a host synchronisation + a message pair per wave).  One process per GPU; the increment

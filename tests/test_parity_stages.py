@@ -318,10 +318,10 @@ def test_slab_restricted_sweeps(backend, golden):
                     _check(h, lib.fr3d_level_sweeps_slab(h, li, q, q + 1, a, b))
                 if q == 0 and a == 0 and pz >= 3 and not checked_mask:
                     # after the first slab's wave 0 only plane 0 .. cuts[1]-1 may be non-zero
-                    buf = dev.empty((B, pz * py * px, 4), np.float64, reg.device)
+                    buf = dev.empty((B, pz * py * px, 3), np.float64, reg.device)   # float64 state: {du, dv, dw}
                     _check(h, lib.fr3d_level_planes(h, li, 0, dev.ptr(buf), 0, pz))
                     reg.sync()
-                    st = dev.to_host(buf).reshape(B, pz, py, px, 4)
+                    st = dev.to_host(buf).reshape(B, pz, py, px, 3)
                     assert np.abs(st[:, 0, 0, 0, :3]).sum() > 0 and not np.abs(st[:, cuts[1]:]).any()
                     checked_mask = True
         _check(h, lib.fr3d_level_end(h, li))
@@ -332,7 +332,7 @@ def test_slab_restricted_sweeps(backend, golden):
     _check(h, lib.fr3d_level_begin(h, 0, dev.ptr(mvd), None, B))
     (pz, py, px), S, _, _ = _level_info(reg, 0)
     _check(h, lib.fr3d_level_sweeps_slab(h, 0, 0, 1, pz // 2, pz))
-    buf = dev.empty((B, pz * py * px, 4), np.float64, reg.device)
+    buf = dev.empty((B, pz * py * px, 3), np.float64, reg.device)
     _check(h, lib.fr3d_level_planes(h, 0, 0, dev.ptr(buf), 0, pz))
     reg.sync()
     assert not np.abs(dev.to_host(buf)).any()        # wave 0 is voxel (0,0,0): not in [pz/2, pz)
