@@ -82,6 +82,12 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
+            for fn in getattr(self, "_on_close", []):     # e.g. unmap the z-neighbours' buffers (multigpu._SlabPeers)
+                try:
+                    fn()
+                except Exception:
+                    pass
+            self._on_close = []
             self.lib.fr3d_destroy(self.h)
             self.h = None
 

@@ -243,6 +243,8 @@ class _SlabPeers:
         self.flags = self._exchange(1)            # neighbour rank -> mapped pointer
         self.incr = self._exchange(0)
         self._token = torch.zeros(1, dtype=torch.int32, device=reg.device)
+        # the mappings are released when the context is closed (before the library frees this rank's own buffers)
+        reg.ctx.__dict__.setdefault("_on_close", []).append(self.close)
 
     def _exchange(self, which: int) -> dict:
         """Export this rank's buffer `which`, all-gather the handles, map the two z-neighbours'."""
