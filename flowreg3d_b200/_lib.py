@@ -116,6 +116,7 @@ def load():
         "fr3d_resize3d": (ci, [vp, vp, ci, ci, ci, ci, C.POINTER(AxisTable), vp]),
         "fr3d_warp": (ci, [vp, vp, ci, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]),
         "fr3d_motion_tensor": (ci, [vp, vp, vp, ci, ci, ci, cd, cd, cd, ci, vp]),
+        "fr3d_motion_tensor_alt": (ci, [vp, ci, vp, vp, ci, ci, ci, cd, cd, cd, vp]),
         "fr3d_sor_level": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, vp, cd, cd, cd, ci, ci, vp, cd, ci, ci, vp]),
         "fr3d_median5": (ci, [vp, vp, ci, ci, ci, ci, vp]),
         "fr3d_mean_frames": (ci, [vp, vp, ci, i64, vp]),
@@ -156,7 +157,7 @@ EXPORTED_SYMBOLS = [
     "fr3d_warp_flow", "fr3d_cc_project", "fr3d_cc_window", "fr3d_cc_cgemm", "fr3d_cc_cross_power",
     "fr3d_cc_abs_argmax", "fr3d_cc_wrap_shift", "fr3d_cc_tile_sums", "fr3d_rigid_flow", "fr3d_add_flow",
     "fr3d_level_sweeps_slab", "fr3d_level_planes", "fr3d_level_wave_cells",
-    "fr3d_ipc_export", "fr3d_ipc_open", "fr3d_ipc_close", "fr3d_level_sweeps_slab_p2p",
+    "fr3d_ipc_export", "fr3d_ipc_open", "fr3d_ipc_close", "fr3d_level_sweeps_slab_p2p", "fr3d_motion_tensor_alt",
 ]
 
 

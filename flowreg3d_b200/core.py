@@ -708,10 +708,24 @@ def resize(img, size):
     return np.ascontiguousarray(y).astype(img.dtype if np.issubdtype(img.dtype, np.floating) else np.float32)
 
 
-def motion_tensor(f1, f2, hz, hy, hx):
-    """get_motion_tensor_gc (core/optical_flow_3d.py:92-152) without its zero ring: (10,p,m,n)."""
+def motion_tensor(f1, f2, hz, hy, hx, kind: str = "gc"):
+    """get_motion_tensor_gc (core/optical_flow_3d.py:92-152) without its zero ring: (10,p,m,n).
+    kind "gray" / "cs": get_motion_tensor_gray (:218-259) / get_motion_tensor_cs (:155-215) for float64 images --
+    stage functions only; like the reference's driver, get_displacement always uses "gc"."""
     f1 = np.asarray(f1)
     f2 = np.asarray(f2)
+    if kind != "gc":
+        if kind not in ("gray", "cs"):
+            raise ValueError("kind must be 'gc', 'gray' or 'cs'")
+        p, m, n = f1.shape
+        ctx = bare_context()
+        a = dev.to_device(f1.astype(np.float64), ctx.device)
+        b = dev.to_device(f2.astype(np.float64), ctx.device)
+        J = dev.empty((10, p, m, n), np.float64, ctx.device)
+        _check(ctx.h, ctx.lib.fr3d_motion_tensor_alt(ctx.h, 1 if kind == "gray" else 2, dev.ptr(a), dev.ptr(b), p, m, n,
+                                                     float(hz), float(hy), float(hx), dev.ptr(J)))
+        ctx.sync()
+        return dev.to_host(J).copy()
     f2f32 = 1 if f2.dtype == np.float32 else 0
     p, m, n = f1.shape
     ctx = bare_context()

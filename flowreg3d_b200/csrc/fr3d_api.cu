@@ -1448,6 +1448,17 @@ int fr3d_motion_tensor(fr3d_ctx* ctx, const float* f1, const float* f2, int p, i
     FR3D_API_END()
 }
 
+int fr3d_motion_tensor_alt(fr3d_ctx* ctx, int kind, const double* f1, const double* f2, int p, int m, int n, double hz,
+                           double hy, double hx, double* J)
+{
+    FR3D_API_BEGIN(ctx)
+    FR3D_REQUIRE(f1 && f2 && J && p > 0 && m > 0 && n > 0, "bad argument");
+    FR3D_REQUIRE(kind == 1 || kind == 2, "kind must be 1 (gray) or 2 (cs), got %d", kind);
+    MotionTensorAltK k{f1, f2, J, p, m, n, kind, hz, hy, hx};
+    launch(_c->dev, k, (int64_t)p * m * n);
+    FR3D_API_END()
+}
+
 int fr3d_sor_level(fr3d_ctx* ctx, const double* J, const double* weight, const double* uvw, int p, int m, int n,
                    int C, const double* alpha, double hz, double hy, double hx, int iterations, int update_lag,
                    const double* a_data, double a_smooth, int sweep, int state_dtype, double* d)

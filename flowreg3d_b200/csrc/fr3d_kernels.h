@@ -1451,6 +1451,97 @@ struct MotionTensorK {
     }
 };
 
+// The two other constancy assumptions of the reference, get_motion_tensor_gray (core/optical_flow_3d.py:218-259) and
+// get_motion_tensor_cs (:155-215).  Neither is reachable through the reference's driver (get_displacement hard-wires
+// the gradient-constancy tensor, :457); they are stage functions here as there, for float64 images, one channel.
+//   gray: fx = (d/dx f1 + d/dx f2) / 2 with central differences over the replicate-padded images (numpy.gradient with
+//         spacings h at interior points of the padded array), ft = f2 - f1;  J = (fx,fy,fz,ft)(fx,fy,fz,ft)^T.
+//   cs:   mean over the 26 neighbours d of  wgt_d * (del_d g)(del_d g)^T  with g = (gx,gy,gz,It), the UNIT-spacing
+//         central differences of the replicate-padded f2 and It = f2 - f1, both replicate-extended again,
+//         del_d a = a(v + d) - a(v),  wgt_d = eps^4 / (4 (eps^2 + (del_d f2)^2)^3),  eps = 80; neighbours are summed in
+//         the reference's order (dz, dy, dx ascending, centre skipped) with its operation order.
+struct MotionTensorAltK {
+    const double* f1;
+    const double* f2;
+    double* J;          // (10, N)
+    int p, m, n, kind;  // kind 1: gray, 2: cs
+    double hz, hy, hx;
+    FR3D_HD double at(const double* f, int k, int j, int i) const
+    {
+        return f[((int64_t)clampi(k, 0, p - 1) * m + clampi(j, 0, m - 1)) * n + clampi(i, 0, n - 1)];
+    }
+    // central difference of f along ax at a clamped voxel, divided by 2*h
+    FR3D_HD double grad(const double* f, int k, int j, int i, int ax, double h) const
+    {
+        k = clampi(k, 0, p - 1);
+        j = clampi(j, 0, m - 1);
+        i = clampi(i, 0, n - 1);
+        const int dk = ax == 0, dj = ax == 1, di = ax == 2;
+        return (at(f, k + dk, j + dj, i + di) - at(f, k - dk, j - dj, i - di)) / (2.0 * h);
+    }
+    FR3D_HD void operator()(int64_t item) const
+    {
+        const int i = (int)(item % n);
+        const int64_t q = item / n;
+        const int j = (int)(q % m);
+        const int k = (int)(q / m);
+        const int64_t N = (int64_t)p * m * n;
+        double Jv[10];
+        if (kind == 1) {
+            const double fx = 0.5 * (grad(f1, k, j, i, 2, hx) + grad(f2, k, j, i, 2, hx));
+            const double fy = 0.5 * (grad(f1, k, j, i, 1, hy) + grad(f2, k, j, i, 1, hy));
+            const double fz = 0.5 * (grad(f1, k, j, i, 0, hz) + grad(f2, k, j, i, 0, hz));
+            const double ft = at(f2, k, j, i) - at(f1, k, j, i);
+            Jv[0] = fx * fx;
+            Jv[1] = fy * fy;
+            Jv[2] = fz * fz;
+            Jv[3] = ft * ft;
+            Jv[4] = fx * fy;
+            Jv[5] = fx * fz;
+            Jv[6] = fy * fz;
+            Jv[7] = fx * ft;
+            Jv[8] = fy * ft;
+            Jv[9] = fz * ft;
+        } else {
+            const double eps2 = 80.0 * 80.0, eps4 = eps2 * eps2;
+            for (int t = 0; t < 10; ++t)
+                Jv[t] = 0.0;
+            const double c0 = at(f2, k, j, i);
+            const double gx0 = grad(f2, k, j, i, 2, 1.0), gy0 = grad(f2, k, j, i, 1, 1.0), gz0 = grad(f2, k, j, i, 0, 1.0);
+            const double it0 = c0 - at(f1, k, j, i);
+            for (int dz = -1; dz <= 1; ++dz)
+                for (int dy = -1; dy <= 1; ++dy)
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        if (dz == 0 && dy == 0 && dx == 0)
+                            continue;
+                        const int kk = k + dz, jj = j + dy, ii = i + dx;
+                        const double dIm = at(f2, kk, jj, ii) - c0;
+                        const double den = eps2 + dIm * dIm;
+                        const double wgt = eps4 / (4.0 * den * den * den);
+                        const double dIx = grad(f2, kk, jj, ii, 2, 1.0) - gx0;
+                        const double dIy = grad(f2, kk, jj, ii, 1, 1.0) - gy0;
+                        const double dIz = grad(f2, kk, jj, ii, 0, 1.0) - gz0;
+                        const double dIt = (at(f2, kk, jj, ii) - at(f1, kk, jj, ii)) - it0;
+                        Jv[0] += wgt * dIx * dIx;
+                        Jv[1] += wgt * dIy * dIy;
+                        Jv[2] += wgt * dIz * dIz;
+                        Jv[3] += wgt * dIt * dIt;
+                        Jv[4] += wgt * dIx * dIy;
+                        Jv[5] += wgt * dIx * dIz;
+                        Jv[6] += wgt * dIy * dIz;
+                        Jv[7] += wgt * dIx * dIt;
+                        Jv[8] += wgt * dIy * dIt;
+                        Jv[9] += wgt * dIz * dIt;
+                    }
+            const double invN = 1.0 / 26.0;
+            for (int t = 0; t < 10; ++t)
+                Jv[t] *= invN;
+        }
+        for (int t = 0; t < 10; ++t)
+            J[t * N + item] = Jv[t];
+    }
+};
+
 // natural (nvol, N) -> solver storage (nvol, npad), pad slots zero; item = (vol, slot)
 template <class SrcT>
 struct ToHPK {

@@ -260,6 +260,12 @@ int fr3d_warp(fr3d_ctx* ctx, const void* vol, int vol_dtype, const double* u, co
 int fr3d_motion_tensor(fr3d_ctx* ctx, const float* f1, const float* f2, int p, int m, int n,
                        double hz, double hy, double hx, int f2_f32_math, double* J);
 
+/* get_motion_tensor_gray (core/optical_flow_3d.py:218-259; kind = 1) and get_motion_tensor_cs (:155-215; kind = 2)
+ * for one channel of float64 images f1, f2 (p,m,n); J as above.  Stage functions only: like in the reference, the
+ * driver never calls them (get_displacement hard-wires the gradient-constancy tensor, :457). */
+int fr3d_motion_tensor_alt(fr3d_ctx* ctx, int kind, const double* f1, const double* f2, int p, int m, int n,
+                           double hz, double hy, double hx, double* J);
+
 /* compute_flow_3d (core/level_solver_3d.py:314-546) on interior arrays (no ring):
  * J (C,10,p,m,n) float64; weight (C,p,m,n) float64; uvw (3,p,m,n) float64; alpha (x,y,z) host;
  * a_data host C doubles; state_dtype FR3D_F32|FR3D_F64 (see fr3d_plan); out d (3,p,m,n) float64 =

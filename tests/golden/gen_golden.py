@@ -123,6 +123,17 @@ def gen_motion_tensor():
     save("motion_tensor", **d)
 
 
+def gen_motion_tensor_alt():
+    """The two constancy variants the reference's driver never calls: get_motion_tensor_gray and get_motion_tensor_cs
+    (core/optical_flow_3d.py:155-259) on a small pair, intensities scaled to 0..255 (cs uses eps = 80)."""
+    fixed, moving, _ = small_pair()
+    f1 = (fixed[..., 0].astype(np.float64)[:11, :18, :20]) * 255.0
+    f2 = (moving[..., 1].astype(np.float64)[:11, :18, :20]) * 255.0
+    h = (1.25, 1.1, 1.3)
+    save("motion_tensor_alt", f1=f1, f2=f2, h=np.array(h), J_gray=np.stack(R.get_motion_tensor_gray(f1, f2, *h), 0),
+         J_cs=np.stack(R.get_motion_tensor_cs(f1, f2, *h), 0))
+
+
 def gen_solver():
     rng = np.random.default_rng(5)
     fixed, moving, _ = small_pair()
@@ -463,7 +474,7 @@ def gen_xcorr():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["tables", "resize", "warp", "motion_tensor", "solver", "flow_small",
+    which = sys.argv[1:] or ["tables", "resize", "warp", "motion_tensor", "motion_tensor_alt", "solver", "flow_small",
                              "preprocess", "preprocess_t", "sequence", "sequence_update_ref", "config1", "config2", "schedule", "xcorr", "xcorr_sequence"]
     for w in which:
         globals()[f"gen_{w}"]()

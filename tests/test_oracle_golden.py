@@ -154,3 +154,10 @@ def test_flow_nonlinear_smoothness(golden):
     kw = dict(alpha=(0.5,) * 3, update_lag=10, iterations=15, min_level=1, levels=100, eta=0.8, a_smooth=0.5, a_data=0.45)
     mean, mx = epe_stats(O.get_displacement(g["fixed"], g["moving"], **kw), g["flow_ml1s"])
     assert mean <= 1e-4 and mx <= 5e-3, (mean, mx)
+
+
+def test_oracle_motion_tensor_gray_and_cs(golden):
+    """The oracle's restatements of the two unused constancy variants equal the live reference bit for bit."""
+    g = golden("motion_tensor_alt")
+    assert np.array_equal(np.stack(O.get_motion_tensor_gray(g["f1"], g["f2"], *g["h"]), 0), g["J_gray"])
+    assert np.array_equal(np.stack(O.get_motion_tensor_cs(g["f1"], g["f2"], *g["h"]), 0), g["J_cs"])

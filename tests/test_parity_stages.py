@@ -360,3 +360,19 @@ def test_imregister_interleaved_flow_views_equal_separate_planes(backend):
         assert np.array_equal(a, b), meth
         o = O.imregister_wrapper(f2, flow[..., 0], flow[..., 1], flow[..., 2], f1, meth)
         assert ulp_diff(a, o).max() <= 1
+
+
+@pytest.mark.parametrize("kind", ["gray", "cs"])
+def test_motion_tensor_gray_and_cs_variants(backend, golden, kind):
+    """get_motion_tensor_gray / get_motion_tensor_cs (core/optical_flow_3d.py:155-259; never called by the reference's
+    driver, stage functions here too) against the live reference's golden: bit-equal (same operations, same order; the
+    library is built without FMA contraction)."""
+    from flowreg3d_b200 import core
+    g = golden("motion_tensor_alt")
+    J = core.motion_tensor(g["f1"], g["f2"], *g["h"], kind=kind)
+    ref = g["J_" + kind]
+    assert not ref[:, 0].any() and not ref[:, :, :, -1].any()              # the reference's zero ring
+    inner = ref[:, 1:-1, 1:-1, 1:-1]
+    assert np.abs(J - inner).max() <= 1e-12 * np.abs(inner).max()
+    with pytest.raises(ValueError):
+        core.motion_tensor(g["f1"], g["f2"], *g["h"], kind="nope")
