@@ -22,6 +22,7 @@ OPT_CC_BLOCK_SCANS = 2
 OPT_WARP_FACTORED = 3
 OPT_SOR_KERNEL = 4
 OPT_SOR_STAGES = 5
+OPT_SOR_SCHED = 9
 OPT_SOR_TILE = 6
 OPT_SPLINE_TMA = 7
 OPT_RESIZE_X_ROWS = 8

@@ -38,12 +38,28 @@ struct HPGeom {
     int32_t npad = 0;
     std::vector<int32_t> pe_host;
     Buf<int32_t> rowbase, start, pe, pe4, nbr, perm;
+    mutable Buf<int32_t> peR; // chunk prefix over hyperplanes s, s - 2 lag, ... (kind-balanced dealing), built on first use
+    mutable int peR_lag = 0;
     HPView view() const
     {
         return HPView{p, m, n, S, npad, rowbase.p, start.p, pe.p, nbr.p, perm.p};
     }
+    const int32_t* refresh_prefix(Device& dev, int lag) const
+    {
+        if (lag < 1 || S == 0 || pe_host.empty())
+            return nullptr;
+        if (peR_lag != lag) {
+            std::vector<int32_t> t(S);
+            for (int s = 0; s < S; ++s)
+                t[s] = pe_host[s] - (s >= 2 ? pe_host[s - 2] : 0) + (s >= 2 * lag ? t[s - 2 * lag] : 0);
+            peR.upload(dev, t.data(), t.size());
+            peR_lag = lag;
+        }
+        return peR.p;
+    }
     void build(Device& dev, int p_, int m_, int n_)
     {
+        peR_lag = 0;
         p = p_;
         m = m_;
         n = n_;
@@ -420,6 +436,9 @@ static void sor_prepare_t(fr3d_ctx* c, const HPGeom& hp, int B, int C, const flo
     P.lag = lag;
     P.fg = sor_frame_group(B);
     P.redblack = sweep == FR3D_SWEEP_REDBLACK;
+    // default: a fifth of each wave by ticket for the float64 state (-3.4 % on a B200), round-robin for float32 (tickets
+    // cost that kernel registers: +3 %)
+    P.sched = c->dev.sor_sched >= 0 ? c->dev.sor_sched : (sizeof(ST) == 8 ? 20 : 0);
     P.t_begin = 0;
     P.t_end = T;
     P.q_begin = 0;
@@ -442,6 +461,7 @@ static void sor_prepare_t(fr3d_ctx* c, const HPGeom& hp, int B, int C, const flo
     P.hy = hy;
     P.hz = hz;
     P.pe4 = hp.pe4.p;
+    P.peR = (P.sched & 128) ? hp.refresh_prefix(dev, lag) : nullptr;
     P.U = nullptr;
     P.dold = nullptr;
     P.psi_c = nullptr;
@@ -515,7 +535,7 @@ static void sor_launch_t(fr3d_ctx* c, int t0, int t1, int q0, int q1, int k0 = 0
     c->dev.sor_k0 = k0;
     c->dev.sor_k1 = k1 > 0 ? k1 : 0;
     try {
-        sor_run(c->dev, P, c->bar.ensure(c->dev, 4), c->sp_hp->pe_host.data());
+        sor_run(c->dev, P, c->bar.ensure(c->dev, FR3D_SOR_BAR_WORDS), c->sp_hp->pe_host.data());
     } catch (...) {
         c->dev.sor_k0 = c->dev.sor_k1 = 0;
         throw;
@@ -584,7 +604,7 @@ static void sor_launch_p2p_t(fr3d_ctx* c, int k0, int k1, void* lo_d, void* hi_d
     FR3D_CUDA(cudaStreamSynchronize(c->dev.stream)); // the host vectors go out of scope
     P.g.pe = c->slab_pe.p;
     P.g.start = c->slab_start.p;
-    sor_run_p2p_any(c->dev, P, c->bar.ensure(c->dev, 4), spe.data(), k0, k1, pr);
+    sor_run_p2p_any(c->dev, P, c->bar.ensure(c->dev, FR3D_SOR_BAR_WORDS), spe.data(), k0, k1, pr);
 }
 #endif
 
@@ -804,6 +824,11 @@ int fr3d_set_option(fr3d_ctx* ctx, int option, int64_t value)
         _c->dev.sor_tile_i = ti;
         break;
     }
+    case FR3D_OPT_SOR_SCHED:
+        FR3D_REQUIRE(value >= -1 && (value < 0 || ((value & 127) <= 100 && (value >> 11) == 0)), "FR3D_OPT_SOR_SCHED: %lld",
+                     (long long)value);
+        _c->dev.sor_sched = (int)value;
+        break;
     case FR3D_OPT_SOR_STAGES:
         FR3D_REQUIRE(value >= 0 && value <= 16 && value != 1, "FR3D_OPT_SOR_STAGES: %lld", (long long)value);
         _c->dev.sor_stages = (int)value;

@@ -81,6 +81,8 @@ struct Device {
     int sor_ctas_per_sm = 0; // 0 = as many as fit
     int sor_kernel = 0;      // FR3D_OPT_SOR_KERNEL: 2 time-blocked tiles (fr3d_sor_tile.h), 1 staged wavefront (TMA bulk
                              // copies + mbarrier ring), 0 direct-load wavefront
+    int sor_sched = -1;      // wavefront kernel item dealing (FR3D_OPT_SOR_SCHED): -1 = default for the state dtype, else
+                             // percent by ticket | 128 (refresh items first)
     int sor_stages = 0;      // stages per warp of the staged kernel, 0 = default (FR3D_OPT_SOR_STAGES)
     int resize_x_rows = 1;   // FR3D_OPT_RESIZE_X_ROWS: X resampling pass with 4 rows per thread sharing the tap look-ups
     int spline_tma = 1;      // FR3D_OPT_SPLINE_TMA: bulk-copy (TMA) staging of the spline X pass

@@ -72,6 +72,8 @@ struct SorParams {
     HPView g;
     int C, B, T, lag, fg; // fg: frames handled by one warp work item
     int redblack;         // 0: waves q = s + 2t (lexicographic order); 1: waves q = 2t + colour (checkerboard)
+    int sched;            // wavefront kernel (FR3D_OPT_SOR_SCHED): bits 0-6 percent of a wave's items handed out through a
+                          // ticket counter instead of round-robin; bit 7: psi-refresh items dealt before the plain ones
     // partial execution (sweep-pipelined multi-GPU solve): only sweeps t_begin <= t < t_end and waves
     // q_begin <= q < q_end of the global schedule q = s + 2t; the full solve is [0,T) x [0,num_waves)
     int t_begin, t_end, q_begin, q_end;
@@ -87,6 +89,7 @@ struct SorParams {
     // nonlinear smoothness term (a_smooth != 1), see "Nonlinear smoothness" below
     double a_smooth, hx, hy, hz;
     const int32_t* pe4;   // (S): chunks in hyperplanes s, s-4, s-8, ...
+    const int32_t* peR;   // (S): chunks in hyperplanes s, s-2*lag, s-4*lag, ... (kind-balanced dealing; nullptr: not built)
     const Vec4<ST>* U;    // (B, npad): u, v, w
     Vec4<ST>* dold;       // (B, npad): increments before the voxel's latest update
     double* psi_c;        // (B, npad): psi_s at the voxel
@@ -279,6 +282,108 @@ FR3D_HD SorLoc sor_locate(const SorParams<ST>& P, const SorTabs& tb, int q, cons
     L.n4 = nb[128];
     L.n5 = nb[160];
     L.refresh = (t % P.lag) == 0;
+    L.b0 = fgi * P.fg;
+    L.b1 = L.b0 + P.fg < P.B ? L.b0 + P.fg : P.B;
+    return L;
+}
+
+// KIND-BALANCED item order of a wave (FR3D_OPT_SOR_SCHED bit 7).  A psi-refresh item (sweep t % lag == 0: reads 10C
+// planes of J, evaluates the robust weights, writes the system) costs ~2.6 plain items, and one wave mixes both kinds --
+// every lag-th of its hyperplanes is a refresh hyperplane.  Dealt round-robin in hyperplane order, a warp draws 0..5
+// refresh items among its ~9 and the wave lasts as long as its unluckiest warp (measured on a B200, config 2: the wave
+// barriers cost 7 ms at lag 1 or with no refresh at all, 11.7 ms at lag 5).  Here the wave's items are enumerated
+// refresh chunks first, then plain chunks, as ONE index range dealt round-robin: every warp gets the same number of
+// refresh items (+-1) and the heavy items run first.  Refresh hyperplanes of wave q are s = q (mod 2 lag); peR is
+// the chunk prefix over that residue class.
+struct SorKinds {
+    int nR;     // refresh hyperplanes in the wave
+    int s_min;  // the lowest of them
+    int baseR;  // refresh chunks before s_min (same residue class)
+    int Rc, Pc; // refresh / plain chunks of the wave
+    int r_items; // refresh items = Rc * frame groups
+};
+template <class ST>
+FR3D_HD SorKinds sor_wave_kinds(const SorParams<ST>& P, int q, const SorWave& w)
+{
+    SorKinds k{0, 0, 0, 0, w.chunks, 0};
+    if (w.nT <= 0)
+        return k;
+    const int thi = (q - w.s_lo) >> 1, tlo = thi - w.nT + 1;
+    const int t_first = (tlo + P.lag - 1) / P.lag * P.lag, t_last = thi / P.lag * P.lag;
+    if (t_first > t_last)
+        return k;
+    const int L2 = 2 * P.lag;
+    k.nR = (t_last - t_first) / P.lag + 1;
+    k.s_min = q - 2 * t_last;
+    k.baseR = k.s_min >= L2 ? P.peR[k.s_min - L2] : 0;
+    k.Rc = P.peR[q - 2 * t_first] - k.baseR;
+    k.Pc = w.chunks - k.Rc;
+    k.r_items = k.Rc * ((P.B + P.fg - 1) / P.fg);
+    return k;
+}
+
+// refresh chunks of the wave in hyperplanes <= s
+template <class ST>
+FR3D_HD int sor_refresh_through(const SorParams<ST>& P, const SorKinds& k, int s)
+{
+    if (k.nR == 0 || s < k.s_min)
+        return 0;
+    const int L2 = 2 * P.lag;
+    return P.peR[k.s_min + (s - k.s_min) / L2 * L2] - k.baseR;
+}
+
+// Item u of the kind-balanced order: u < r_items is a refresh item, the rest are plain items.
+template <class ST>
+FR3D_HD SorLoc sor_locate_bal(const SorParams<ST>& P, const SorTabs& tb, int q, const SorWave& w, const SorKinds& k,
+                              int u, int lane)
+{
+    const HPView& g = P.g;
+    int s, fgi, in_plane;
+    bool refresh;
+    if (u < k.r_items) {
+        const int L2 = 2 * P.lag;
+        fgi = u / k.Rc;
+        const int f = u - fgi * k.Rc;
+        int lo = 0, hi = k.nR - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (P.peR[k.s_min + L2 * mid] - k.baseR > f)
+                hi = mid;
+            else
+                lo = mid + 1;
+        }
+        s = k.s_min + L2 * lo;
+        in_plane = f - ((s >= L2 ? P.peR[s - L2] : 0) - k.baseR);
+        refresh = true;
+    } else {
+        const int v = u - k.r_items;
+        fgi = v / k.Pc;
+        const int f = v - fgi * k.Pc;
+        // hyperplane holding plain chunk f: smallest r with (chunks - refresh chunks) through s_lo + 2r  >  f
+        int lo = 0, hi = w.nT - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const int sm = w.s_lo + 2 * mid;
+            if (tb.pe[sm] - w.base - sor_refresh_through(P, k, sm) > f)
+                hi = mid;
+            else
+                lo = mid + 1;
+        }
+        s = w.s_lo + 2 * lo;
+        const int before = lo > 0 ? tb.pe[s - 2] - w.base - sor_refresh_through(P, k, s - 2) : 0;
+        in_plane = f - before;
+        refresh = false;
+    }
+    SorLoc L;
+    L.a = (int64_t)tb.start[s] + 32 * in_plane + lane;
+    const int32_t* nb = g.nbr + HPView::nbr_at(0, L.a);
+    L.n0 = nb[0];
+    L.n1 = nb[32];
+    L.n2 = nb[64];
+    L.n3 = nb[96];
+    L.n4 = nb[128];
+    L.n5 = nb[160];
+    L.refresh = refresh;
     L.b0 = fgi * P.fg;
     L.b1 = L.b0 + P.fg < P.B ? L.b0 + P.fg : P.B;
     return L;
@@ -668,6 +773,9 @@ inline SorTileGeom sor_tile_geom_for(const Device& dev, int p, int m, int n, int
     return sor_tile_geom(p, m, n, T, lag, Tb, tk, tj, ti);
 }
 
+// words of the barrier buffer: [0] arrival counter, [32 + wave] item tickets of the wavefront kernel (one per wave)
+#define FR3D_SOR_BAR_WORDS (32 + 16384)
+
 #ifdef FR3D_EMU
 template <class ST, int C>
 inline void sor_run_tiles(Device& dev, const SorParams<ST>& P)
@@ -698,8 +806,18 @@ inline void sor_run_c(Device& dev, const SorParams<ST>& P, unsigned*)
         return;
     }
     const SorTabs tb{P.g.pe, P.g.start};
+    const bool balanced = (P.sched & 128) && P.peR && dev.sor_k1 <= 0 && !P.redblack;
+    if (balanced)
+        dev.emu_count("fr3d_sor_wavefront_balanced");
     for (int q = P.q_begin; q < P.q_end; ++q) {
         const SorWave w = sor_wave(P, tb, q);
+        if (balanced) { // the kind-balanced enumeration of the wave's items (same items, other order)
+            const SorKinds kd = sor_wave_kinds(P, q, w);
+            for (int u = w.items - 1; u >= 0; --u)
+                for (int lane = 0; lane < 32; ++lane)
+                    sor_process<ST, C>(P, sor_locate_bal(P, tb, q, w, kd, u, lane));
+            continue;
+        }
         for (int item = 0; item < w.items; ++item)
             for (int lane = 0; lane < 32; ++lane) {
                 if (dev.sor_k1 > 0)
@@ -711,7 +829,9 @@ inline void sor_run_c(Device& dev, const SorParams<ST>& P, unsigned*)
     dev.launches++;
 }
 #else
+#ifndef FR3D_SOR_THREADS
 #define FR3D_SOR_THREADS 256
+#endif
 
 #ifndef FR3D_BARRIER_VARIANT
 #define FR3D_BARRIER_VARIANT 0
@@ -721,6 +841,10 @@ inline void sor_run_c(Device& dev, const SorParams<ST>& P, unsigned*)
 // (SASS: CCTL.IVALL), which the L1-cached neighbour loads of the next wave rely on.
 __device__ __forceinline__ void fr3d_grid_barrier(unsigned* ctr, unsigned target)
 {
+#ifdef FR3D_SOR_TIMING_NO_BARRIER /* DIAGNOSTIC BUILD ONLY (wrong results): what the waves cost without their barrier */
+    __syncthreads();
+    return;
+#endif
     __syncthreads();
     if (threadIdx.x == 0) {
 #if FR3D_BARRIER_VARIANT == 0
@@ -729,6 +853,17 @@ __device__ __forceinline__ void fr3d_grid_barrier(unsigned* ctr, unsigned target
         while (*((volatile unsigned*)ctr) < target) {
         }
         __threadfence();
+#elif FR3D_BARRIER_VARIANT == 3 /* DIAGNOSTIC (wrong results): the fences of the barrier without its synchronisation */
+        __threadfence();
+        __threadfence();
+        (void)ctr;
+        (void)target;
+#elif FR3D_BARRIER_VARIANT == 4 /* DIAGNOSTIC for .ca neighbour loads (no L1 invalidation): release-arrive, relaxed poll */
+        unsigned v;
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+        do {
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        } while (v < target);
 #else
         unsigned v;
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
@@ -835,6 +970,183 @@ fr3d_sor_wavefront(const SorParams<ST> P, unsigned* bar, int tabs_in_smem)
         fr3d_grid_barrier(bar, gen * gridDim.x);
     }
 }
+
+// The same kernel with two changes to HOW a wave's items reach the warps (FR3D_OPT_SOR_SCHED, full solves only; every
+// item runs the same code on the same inputs, so results are bit-identical):
+//  * BAL: the kind-balanced item order (sor_locate_bal above) -- refresh items first, equally many per warp;
+//  * tickets: the first rounds are dealt round-robin (item = warp + r * stride, no traffic); the last `pct` percent of
+//    the wave's items are handed out through a per-wave ticket counter (bar[32 + wave], zeroed before the launch), so
+//    that warps which drew cheap items (L2 hits) take more of them and the wave ends within one item's time on all
+//    warps.  A ticket is drawn one item ahead of its use (the atomic's latency hides behind the update in between).
+template <class ST, int C, bool BAL>
+__global__ void __launch_bounds__(FR3D_SOR_THREADS, SorTune<ST>::kMinBlocks)
+fr3d_sor_wavefront_dyn(const SorParams<ST> P, unsigned* bar, int tabs_in_smem)
+{
+    extern __shared__ int32_t fr3d_sor_smem[];
+    SorTabs tb{P.g.pe, P.g.start};
+    if (tabs_in_smem) {
+        const int S = P.g.S;
+        for (int i = threadIdx.x; i < S; i += blockDim.x)
+            fr3d_sor_smem[i] = P.g.pe[i];
+        for (int i = threadIdx.x; i <= S; i += blockDim.x)
+            fr3d_sor_smem[S + i] = P.g.start[i];
+        __syncthreads();
+        tb.pe = fr3d_sor_smem;
+        tb.start = fr3d_sor_smem + S;
+    }
+    const int wpb = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int stride = gridDim.x * wpb;
+    const int pct = P.sched & 127;
+    unsigned gen = 0;
+    for (int q = P.q_begin; q < P.q_end; ++q) {
+        const SorWave w = sor_wave(P, tb, q);
+        int item = blockIdx.x * wpb + warp;
+        if (item < w.items) {
+            SorKinds kd;
+            if (BAL)
+                kd = sor_wave_kinds(P, q, w);
+            int dyn_base = 0x3fffffff; // items below are dealt round-robin
+            if (pct) {
+                const int rs = (int)(((int64_t)w.items * (100 - pct)) / (100 * (int64_t)stride));
+                dyn_base = (rs < 1 ? 1 : rs) * stride;
+            }
+            unsigned* ticket = bar + 32 + (q - P.q_begin);
+            SorLoc cur = BAL ? sor_locate_bal(P, tb, q, w, kd, item, lane) : sor_locate(P, tb, q, w, item, lane);
+            bool t_dyn = item + stride >= dyn_base;
+            int t_val = t_dyn ? (lane == 0 ? (int)atomicAdd(ticket, 1u) : 0) : item + stride;
+            for (;;) {
+                const int next = t_dyn ? dyn_base + __shfl_sync(0xffffffffu, t_val, 0) : t_val;
+                const bool more = next < w.items;
+                SorLoc nxt;
+                if (more) {
+                    nxt = BAL ? sor_locate_bal(P, tb, q, w, kd, next, lane) : sor_locate(P, tb, q, w, next, lane);
+                    t_dyn = next + stride >= dyn_base;
+                    t_val = t_dyn ? (lane == 0 ? (int)atomicAdd(ticket, 1u) : 0) : next + stride;
+                }
+                sor_process<ST, C, false>(P, cur, 0, 0);
+                if (!more)
+                    break;
+                cur = nxt;
+            }
+        }
+        ++gen;
+        fr3d_grid_barrier(bar, gen * gridDim.x);
+    }
+}
+
+#ifdef FR3D_SOR_SPLIT_EXPERIMENT
+// SPLIT-PHASE waves (EXPERIMENT, compiled with -DFR3D_SOR_SPLIT_EXPERIMENT only; then FR3D_OPT_SOR_SCHED bit 10 selects
+// it and bits 8-9 its arrival mode).  MEASURED AND REJECTED on a B200 (config 2, 25 frames, results/r02_sor_sched.md):
+// 51.8 - 53.6 ms in its four modes against 50.1 ms for the barrier kernel.  Measured on a B200 (config 2, 25 frames): with the
+// grid barrier compiled out the same waves take 38.4 instead of 50.5 ms -- a quarter of the solve is the barrier's
+// latency plus the drain of each wave's last items and the refill after it, ~12 us on each of ~1000 waves.  The frames
+// of a batch are independent systems, so the kernel splits them into two groups and alternates  A_q, B_q, A_q+1, ...:
+// a warp ARRIVES on group A's counter when its A_q items are stored, goes straight on to its B_q items, and only then
+// WAITS for "all warps have arrived for A_q" -- which by then happened long ago.  No CTA-wide or grid-wide stall is
+// left: arrival and wait are per warp (stores -> fence -> red on the group's counter;  poll -> fence, whose acquire
+// also drops the SM's L1 lines that the .ca neighbour loads of the next wave must not see).  With items enumerated
+// chunk-fastest, a group's items are one contiguous index range of the wave.  Same items, same arithmetic, same order
+// of dependent updates: bit-identical.
+template <class ST, int C>
+__global__ void __launch_bounds__(FR3D_SOR_THREADS, SorTune<ST>::kMinBlocks)
+fr3d_sor_wavefront_split(const SorParams<ST> P, unsigned* bar, int tabs_in_smem)
+{
+    extern __shared__ int32_t fr3d_sor_smem[];
+    SorTabs tb{P.g.pe, P.g.start};
+    if (tabs_in_smem) {
+        const int S = P.g.S;
+        for (int i = threadIdx.x; i < S; i += blockDim.x)
+            fr3d_sor_smem[i] = P.g.pe[i];
+        for (int i = threadIdx.x; i <= S; i += blockDim.x)
+            fr3d_sor_smem[S + i] = P.g.start[i];
+        __syncthreads();
+        tb.pe = fr3d_sor_smem;
+        tb.start = fr3d_sor_smem + S;
+    }
+    const int wpb = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int stride = gridDim.x * wpb;
+    const int gw = blockIdx.x * wpb + warp;
+    const int nfg = (P.B + P.fg - 1) / P.fg;
+    const int nfg0 = (nfg + 1) >> 1; // frame groups of the first half
+    // arrival / wait granularity and primitives (experiment switches, FR3D_OPT_SOR_SCHED bits 8, 9):
+    //   mode 0: per warp, __threadfence both sides;  1: per warp, red.release / ld.acquire;  2: per CTA (thread 0
+    //   arrives after a __syncthreads, thread 32 polls the other group meanwhile);  3: per CTA with release / acquire
+    const int mode = (P.sched >> 8) & 3;
+    const bool per_cta = mode >= 2, relacq = mode & 1;
+    const unsigned members = per_cta ? gridDim.x : (unsigned)stride;
+    unsigned gen = 0;
+    for (int q = P.q_begin; q < P.q_end; ++q, ++gen) {
+        const SorWave w = sor_wave(P, tb, q);
+        const int split = w.chunks * nfg0;
+#pragma unroll 1
+        for (int g = 0; g < 2; ++g) {
+            const int hi = g ? w.items : (split < w.items ? split : w.items);
+            int item = (g ? split : 0) + gw;
+            unsigned* ctr = bar + 32 + 32 * g;
+            // This group's previous wave must be complete everywhere.  EVERY member waits, also one without items in
+            // this phase: a member then arrives for wave q only after it saw all arrivals of wave q - 1, which is what
+            // makes "counter >= gen * members" mean "all members have arrived gen times".
+            if (gen) {
+                const unsigned target = gen * members;
+                if (per_cta ? threadIdx.x == 32 : lane == 0) {
+                    if (relacq) {
+                        unsigned v;
+                        do {
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+                        } while (v < target);
+                    } else {
+                        while (*((volatile unsigned*)ctr) < target) {
+                        }
+                        __threadfence();
+                    }
+                }
+            }
+            if (per_cta)
+                __syncthreads(); // (thread 0 has arrived for the other group, thread 32 has seen this group's arrivals)
+            else
+                __syncwarp();
+            if (item < hi) {
+                SorLoc cur = sor_locate(P, tb, q, w, item, lane);
+                for (;;) {
+                    const int next = item + stride;
+                    const bool more = next < hi;
+                    SorLoc nxt;
+                    if (more)
+                        nxt = sor_locate(P, tb, q, w, next, lane);
+                    sor_process<ST, C, false>(P, cur, 0, 0);
+                    if (!more)
+                        break;
+                    cur = nxt;
+                    item = next;
+                }
+            }
+            if (per_cta) {
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    if (relacq) {
+                        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+                    } else {
+                        __threadfence();
+                        atomicAdd(ctr, 1u);
+                    }
+                }
+            } else {
+                if (!relacq)
+                    __threadfence();
+                __syncwarp();
+                if (lane == 0) {
+                    if (relacq)
+                        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+                    else
+                        atomicAdd(ctr, 1u);
+                }
+            }
+        }
+    }
+}
+#endif
 
 // z-slab solve with the halo exchange INSIDE the persistent kernel: every rank sweeps its own planes wave by wave;
 // a boundary-plane voxel is written to the z-neighbour's memory as it is produced (peer store over NVLink), and after
@@ -1486,8 +1798,32 @@ inline void sor_run_c(Device& dev, const SorParams<ST>& P, unsigned* bar, int pe
     const bool slab = dev.sor_k1 > 0;
     FR3D_REQUIRE(!slab || dev.sor_k1 < 32768, "z-slab solve: more than 32767 planes");
     int per_sm = 0;
+    SorParams<ST> Pc = P;
+    const int nwaves = P.q_end - P.q_begin;
+    if (slab || nwaves < 0 || 32 + nwaves > FR3D_SOR_BAR_WORDS)
+        Pc.sched = 0; // slab solves and solves with more waves than tickets: round-robin only
+#ifdef FR3D_SOR_SPLIT_EXPERIMENT
+    const bool split = (Pc.sched & 1024) != 0;
+#else
+    const bool split = false;
+#endif
+    if (!Pc.peR || Pc.redblack)
+        Pc.sched &= ~128; // no refresh-class prefix table / checkerboard waves are homogeneous
+    const bool bal = !split && (Pc.sched & 128) != 0;
+    const bool tickets = !split && (Pc.sched & 127) != 0;
     if (slab)
         FR3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fr3d_sor_wavefront<ST, C, true>,
+                                                                FR3D_SOR_THREADS, dyn));
+#ifdef FR3D_SOR_SPLIT_EXPERIMENT
+    else if (split)
+        FR3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fr3d_sor_wavefront_split<ST, C>,
+                                                                FR3D_SOR_THREADS, dyn));
+#endif
+    else if (bal)
+        FR3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fr3d_sor_wavefront_dyn<ST, C, true>,
+                                                                FR3D_SOR_THREADS, dyn));
+    else if (tickets)
+        FR3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fr3d_sor_wavefront_dyn<ST, C, false>,
                                                                 FR3D_SOR_THREADS, dyn));
     else
         FR3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fr3d_sor_wavefront<ST, C>,
@@ -1501,13 +1837,23 @@ inline void sor_run_c(Device& dev, const SorParams<ST>& P, unsigned* bar, int pe
     int grid = dev.sm_count * per_sm;
     if (want < grid)
         grid = (int)(want < 1 ? 1 : want);
-    FR3D_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), dev.stream));
-    SorParams<ST> Pc = P;
+    FR3D_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned) * (tickets ? 32 + nwaves : 96), dev.stream));
     int tis = tabs_in_smem | (slab ? ((dev.sor_k0 << 1) | (dev.sor_k1 << 16)) : 0);
     void* args[] = {(void*)&Pc, (void*)&bar, (void*)&tis};
     dev.span_begin("fr3d_sor_wavefront");
     if (slab)
         FR3D_CUDA(cudaLaunchCooperativeKernel((void*)fr3d_sor_wavefront<ST, C, true>, dim3(grid),
+                                              dim3(FR3D_SOR_THREADS), args, dyn, dev.stream));
+#ifdef FR3D_SOR_SPLIT_EXPERIMENT
+    else if (split)
+        FR3D_CUDA(cudaLaunchCooperativeKernel((void*)fr3d_sor_wavefront_split<ST, C>, dim3(grid), dim3(FR3D_SOR_THREADS),
+                                              args, dyn, dev.stream));
+#endif
+    else if (bal)
+        FR3D_CUDA(cudaLaunchCooperativeKernel((void*)fr3d_sor_wavefront_dyn<ST, C, true>, dim3(grid),
+                                              dim3(FR3D_SOR_THREADS), args, dyn, dev.stream));
+    else if (tickets)
+        FR3D_CUDA(cudaLaunchCooperativeKernel((void*)fr3d_sor_wavefront_dyn<ST, C, false>, dim3(grid),
                                               dim3(FR3D_SOR_THREADS), args, dyn, dev.stream));
     else
         FR3D_CUDA(cudaLaunchCooperativeKernel((void*)fr3d_sor_wavefront<ST, C>, dim3(grid), dim3(FR3D_SOR_THREADS),

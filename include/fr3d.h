@@ -132,16 +132,21 @@ typedef enum {
                                    * THE ONE KNOB THAT CAN CHANGE RESULTS (by <= 1 float32 ulp). */
     FR3D_OPT_CC_BLOCK_SCANS = 2,  /* rigid pre-alignment: 1 = block-cooperative plane scans (arg-max, tile sums,
                                    * plane mean: one CTA per plane) instead of one thread per plane (0) */
-    FR3D_OPT_SOR_KERNEL = 4,      /* level solver kernel: 2 (default) = time-blocked skewed tiles, increments resident in
-                                   * shared memory for Tb sweeps; 1 = staged wavefront (cp.async.bulk + mbarrier ring
-                                   * per warp); 0 = direct-load wavefront.  Same arithmetic, same update order:
-                                   * results are bit-identical */
+    FR3D_OPT_SOR_KERNEL = 4,      /* level solver kernel: 0 (default) = direct-load wavefront; 1 = staged wavefront
+                                   * (cp.async.bulk + mbarrier ring per warp); 2 = time-blocked skewed tiles, increments
+                                   * resident in shared memory for Tb sweeps.  Same arithmetic, same update order:
+                                   * results are bit-identical (1 and 2 measured slower on B200) */
     FR3D_OPT_SOR_STAGES = 5,      /* shared-memory stages per warp of the staged solver kernel (0 = built-in default) */
     FR3D_OPT_SPLINE_TMA = 7,      /* B-spline prefilter X pass: 1 (default) = the block's lines are staged with ONE bulk copy
                                    * global -> shared (cp.async.bulk + mbarrier) and written back with one bulk copy
                                    * shared -> global; 0 = per-thread staging loops.  Same arithmetic: bit-identical */
     FR3D_OPT_RESIZE_X_ROWS = 8,   /* pyramid X pass: 1 (default) = a thread resamples 4 rows at one output position and
                                    * looks the taps up once; 0 = one output per thread.  Bit-identical */
+    FR3D_OPT_SOR_SCHED = 9,       /* direct-load wavefront kernel, how a wave's work items reach the warps: bits 0-6 =
+                                   * percent (0..100) of the items handed out through a per-wave ticket counter instead
+                                   * of round-robin; bit 7 = psi-refresh items enumerated first, equally many per warp
+                                   * (measured slower on B200).  -1 (default) = 20 for the float64 state, 0 for float32.
+                                   * Scheduling only: results are bit-identical */
     FR3D_OPT_SOR_TILE = 6         /* tile kernel geometry: Tb | K << 8 | J << 16 | I << 24 (sweeps per time block and
                                    * tile extents; a 0 field keeps its default: 5 sweeps, 8 x 8 x 8) */
 } fr3d_option;

@@ -158,6 +158,48 @@ def test_solver_wavefront_reproduces_lexicographic_order(backend, golden):
         assert np.abs(d - np.moveaxis(o[INNER], -1, 0)).max() <= 1e-10
 
 
+def test_solver_item_scheduling_options_are_bit_identical(backend, golden):
+    """FR3D_OPT_SOR_SCHED only changes which warp runs which work item of a wave (psi-refresh items dealt first and
+    evenly = bit 7; the last percent of a wave through a ticket counter = bits 0-6): same items, same arithmetic."""
+    import flowreg3d_b200 as F
+    from flowreg3d_b200 import _lib, core, device as dev
+    g = golden("solver")
+    J, wgt, uvw, ref, it, lag, _ = _solver_case(g, "c2")
+    ctx = core.bare_context()
+
+    def with_sched(value, fn):
+        core._check(ctx.h, ctx.lib.fr3d_set_option(ctx.h, _lib.OPT_SOR_SCHED, value))
+        try:
+            return fn()
+        finally:
+            core._check(ctx.h, ctx.lib.fr3d_set_option(ctx.h, _lib.OPT_SOR_SCHED, -1))
+
+    for it2, lag2 in ((it, lag), (1, 5), (7, 1), (4, 3), (23, 2), (11, 50)):
+        solve = lambda: core.sor_level(J, wgt, uvw, g["c2_alpha"], g["c2_h"], it2, lag2, g["c2_a_data"])  # noqa: E731
+        base = with_sched(0, solve)
+        for sched in (128, 128 + 20, 20, 100, 128 + 100):
+            assert np.array_equal(with_sched(sched, solve), base), (it2, lag2, sched)
+    # several frames per launch (frame pairs per work item, an odd frame left over), whole pyramid
+    gs = golden("flow_small")
+    fixed, moving = gs["fixed"].astype(np.float32), gs["moving"].astype(np.float32)
+    mv = np.stack([moving, np.roll(moving, 1, 2), np.roll(moving, -2, 1)], 0)
+    fp = F.FlowParams(alpha=(0.25, 0.3, 0.2), update_lag=5, iterations=12, min_level=1, levels=100, eta=0.8,
+                      a_smooth=1.0, a_data=0.45)
+    flows = []
+    for sched in (0, 128 + 20):
+        reg = F.Registration(fixed.shape[:3], fixed.shape[3], fp, max_batch=3)
+        core._check(reg.ctx.h, reg.ctx.lib.fr3d_set_option(reg.ctx.h, _lib.OPT_SOR_SCHED, sched))
+        reg.set_reference(fixed)
+        flows.append(dev.to_host(reg.get_displacement(mv)).copy())
+        reg.sync()
+    assert np.array_equal(flows[0], flows[1])
+    if backend == "emu":            # the emulator reports which code paths ran: the balanced order must have been one
+        ctx.profile(True)
+        with_sched(128, lambda: core.sor_level(J, wgt, uvw, g["c2_alpha"], g["c2_h"], 3, 2, g["c2_a_data"]))
+        assert "fr3d_sor_wavefront_balanced" in ctx.profile_report()
+        ctx.profile(False)
+
+
 def test_solver_redblack_mode_matches_redblack_restatement(backend, golden):
     """The opt-in checkerboard sweep equals a CPU restatement with the same (non-reference) order, and
     differs from the lexicographic result (which is why it is not the default)."""

@@ -32,6 +32,8 @@ ap.add_argument("--iterations", type=int, default=100)
 ap.add_argument("--ctas", type=int, nargs="*", default=[0])
 ap.add_argument("--kernels", type=int, nargs="*", default=[0, 2], help="0 direct wavefront, 1 staged wavefront, 2 tiles")
 ap.add_argument("--tiles", nargs="*", default=["0"], help="FR3D_OPT_SOR_TILE values Tb,K,J,I (e.g. 5,8,8,8) for kernel 2")
+ap.add_argument("--sched", type=int, nargs="*", default=[0], help="FR3D_OPT_SOR_SCHED values for kernel 0")
+ap.add_argument("--lag", type=int, default=5, help="update_lag (psi refresh every lag sweeps)")
 ap.add_argument("--library", default=None, help="a tuning build of libfr3d.so (CUDA) instead of the in-tree one")
 args = ap.parse_args()
 if args.library:
@@ -43,9 +45,9 @@ rng = np.random.default_rng(0)
 frames = np.stack([np.roll(ref, (0, (b % 3) + 1, -(b % 4) - 1), (0, 1, 2)) for b in range(B)], 0)
 frames = (frames + 0.01 * rng.standard_normal(frames.shape)).astype(np.float32)
 dev_frames = torch.from_numpy(frames).cuda()
-fp = F.FlowParams(min_level=args.min_level, a_smooth=1.0, iterations=args.iterations, alpha=(0.25,) * 3, update_lag=5,
+fp = F.FlowParams(min_level=args.min_level, a_smooth=1.0, iterations=args.iterations, alpha=(0.25,) * 3, update_lag=args.lag,
                   levels=100, eta=0.8, a_data=0.45)
-lag = 5
+lag = args.lag
 
 
 def tile_code(spec):
@@ -55,7 +57,7 @@ def tile_code(spec):
     return tb | (k << 8) | (j << 16) | (i << 24)
 
 
-def run(state, kernel, stages, ctas, tile="0"):
+def run(state, kernel, stages, ctas, tile="0", sched=0):
     reg = F.Registration(shape, Cn, fp, max_batch=B, state_dtype=np.float32 if state == "f32" else np.float64)
     reg.set_reference(ref, weight=np.full(Cn, 1.0 / Cn))
     h, lib = reg.ctx.h, reg.ctx.lib
@@ -63,6 +65,7 @@ def run(state, kernel, stages, ctas, tile="0"):
     core._check(h, lib.fr3d_set_option(h, _lib.OPT_SOR_STAGES, stages))
     core._check(h, lib.fr3d_set_option(h, _lib.OPT_SOR_CTAS_PER_SM, ctas))
     core._check(h, lib.fr3d_set_option(h, _lib.OPT_SOR_TILE, tile_code(tile)))
+    core._check(h, lib.fr3d_set_option(h, _lib.OPT_SOR_SCHED, sched))
     flow = reg.get_displacement(dev_frames)
     reg.sync()
     reg.ctx.profile(True)
@@ -85,11 +88,12 @@ def run(state, kernel, stages, ctas, tile="0"):
 base = {}
 for state in args.states:
     for kernel in args.kernels:
-        variants = [(st, "0") for st in args.stages] if kernel == 1 else [(0, tl) for tl in args.tiles] if kernel == 2 else [(0, "0")]
-        for stages, tile in variants:
+        variants = ([(st, "0", 0) for st in args.stages] if kernel == 1 else [(0, tl, 0) for tl in args.tiles] if kernel == 2
+                    else [(0, "0", sc) for sc in args.sched])
+        for stages, tile, sched in variants:
             for ctas in args.ctas:
                 try:
-                    ms, total, gbs, flow, names, level_n = run(state, kernel, stages, ctas, tile)
+                    ms, total, gbs, flow, names, level_n = run(state, kernel, stages, ctas, tile, sched)
                 except Exception as e:  # report and go on: a failing variant must not hide the others
                     print(json.dumps({"state": state, "kernel": kernel, "stages": stages, "ctas": ctas, "tile": tile,
                                       "error": str(e)}), flush=True)
@@ -98,7 +102,7 @@ for state in args.states:
                     base[state] = flow
                 same = bool(np.array_equal(flow, base[state])) if state in base else None
                 dmax = float(np.abs(flow - base[state]).max()) if state in base else None
-                print(json.dumps({"state": state, "kernel": kernel, "stages": stages, "ctas": ctas, "tile": tile,
+                print(json.dumps({"state": state, "kernel": kernel, "stages": stages, "ctas": ctas, "tile": tile, "sched": sched,
                                   "sor_ms": round(ms, 3), "all_kernels_ms": round(total, 3),
                                   "alg_gbs": round(gbs, 1), "frac_of_6453": round(gbs / 6453.1, 4),
                                   "bit_identical_to_direct": same, "max_abs_diff": dmax, "names": names,
