@@ -23,6 +23,8 @@ OPT_WARP_FACTORED = 3
 OPT_SOR_KERNEL = 4
 OPT_SOR_STAGES = 5
 OPT_SOR_SCHED = 9
+OPT_SOR_FRAMES_PER_ITEM = 10
+OPT_WARP_TILE = 11
 OPT_SOR_TILE = 6
 OPT_SPLINE_TMA = 7
 OPT_RESIZE_X_ROWS = 8

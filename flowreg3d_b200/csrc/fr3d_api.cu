@@ -361,25 +361,16 @@ static void spline_prefilter(fr3d_ctx* c, const void* src, int dt, int64_t sb, i
 // resident warps and independent work per thread, not fewer bytes (profiles/r01_sor_variants.txt, gather
 // experiments): cubic warps of 1 or 2 channels run the channel-interleaved kernel with a rolled z loop at 64
 // registers (4 CTAs per SM): 7.6 ms against 10.5 ms for 16 frames of 32x512x512x2; other channel counts run the
-// generic kernel capped to 64 registers (8.7 ms).  Blocks cover 32x8x1 outputs (FR3D_WARP_TILE="tx,ty,tz": A/B aid).
+// generic kernel capped to 64 registers (8.7 ms).  Blocks cover 32x8x1 outputs (FR3D_OPT_WARP_TILE: A/B aid).
 static void launch_gather(fr3d_ctx* c, WarpGatherK g)
 {
-    struct Tile {
-        int tx = 32, ty = 8, tz = 1;
-        Tile()
-        {
-            if (const char* e = getenv("FR3D_WARP_TILE")) {
-                int a = 0, b = 1, d = 1;
-                if (sscanf(e, "%d,%d,%d", &a, &b, &d) == 3 && a > 0 && b > 0 && d > 0 && a * b * d == 256) {
-                    tx = a;
-                    ty = b;
-                    tz = d;
-                }
-            }
-        }
-    };
-    static const Tile tile; // initialised once, thread-safe (contexts may be driven from several host threads)
-    const int tx = tile.tx, ty = tile.ty, tz = tile.tz;
+    // block shape of the gather in outputs (FR3D_OPT_WARP_TILE, an A/B aid; 0 fields keep 32 x 8 x 1)
+    int tx = c->dev.warp_tile & 0xff, ty = (c->dev.warp_tile >> 8) & 0xff, tz = (c->dev.warp_tile >> 16) & 0xff;
+    if (tx <= 0 || ty <= 0 || tz <= 0 || tx * ty * tz != 256) {
+        tx = 32;
+        ty = 8;
+        tz = 1;
+    }
     g.set_tile(tx, ty, tz);
     const int64_t n = g.items();
     if (g.order == 3 && g.C == 2 && c->dev.warp_factored)
@@ -402,11 +393,10 @@ static void check_dtype(int dt)
 }
 
 // Frames per warp work item: enough items to balance the busiest wave over the grid.
-static int sor_frame_group(int B)
+static int sor_frame_group(const Device& dev, int B)
 {
-    static const int fg_env = getenv("FR3D_SOR_FG") ? atoi(getenv("FR3D_SOR_FG")) : 0; // tuning aid
-    if (fg_env > 0)
-        return fg_env < B ? fg_env : B;
+    if (dev.sor_frames_per_item > 0) // FR3D_OPT_SOR_FRAMES_PER_ITEM (tuning aid)
+        return dev.sor_frames_per_item < B ? dev.sor_frames_per_item : B;
     return B >= 2 ? 2 : 1;
 }
 
@@ -434,7 +424,7 @@ static void sor_prepare_t(fr3d_ctx* c, const HPGeom& hp, int B, int C, const flo
     P.B = B;
     P.T = T;
     P.lag = lag;
-    P.fg = sor_frame_group(B);
+    P.fg = sor_frame_group(c->dev, B);
     P.redblack = sweep == FR3D_SWEEP_REDBLACK;
     // default: a fifth of each wave by ticket for the float64 state (-3.4 % on a B200), round-robin for float32 (tickets
     // cost that kernel registers: +3 %)
@@ -822,6 +812,17 @@ int fr3d_set_option(fr3d_ctx* ctx, int option, int64_t value)
         _c->dev.sor_tile_k = tk;
         _c->dev.sor_tile_j = tj;
         _c->dev.sor_tile_i = ti;
+        break;
+    }
+    case FR3D_OPT_SOR_FRAMES_PER_ITEM:
+        FR3D_REQUIRE(value >= 0 && value <= 64, "FR3D_OPT_SOR_FRAMES_PER_ITEM: %lld", (long long)value);
+        _c->dev.sor_frames_per_item = (int)value;
+        break;
+    case FR3D_OPT_WARP_TILE: {
+        const int tx = (int)(value & 0xff), ty = (int)((value >> 8) & 0xff), tz = (int)((value >> 16) & 0xff);
+        FR3D_REQUIRE(value == 0 || ((value >> 24) == 0 && tx * ty * tz == 256), "FR3D_OPT_WARP_TILE: %lld (tx*ty*tz must be 256)",
+                     (long long)value);
+        _c->dev.warp_tile = (int)value;
         break;
     }
     case FR3D_OPT_SOR_SCHED:

@@ -83,6 +83,8 @@ struct Device {
                              // copies + mbarrier ring), 0 direct-load wavefront
     int sor_sched = -1;      // wavefront kernel item dealing (FR3D_OPT_SOR_SCHED): -1 = default for the state dtype, else
                              // percent by ticket | 128 (refresh items first)
+    int sor_frames_per_item = 0; // frames one warp work item of the wavefront kernels covers, 0 = default 2 (FR3D_OPT_SOR_FRAMES_PER_ITEM)
+    int warp_tile = 0;       // gather block shape tx | ty << 8 | tz << 16, 0 = 32 x 8 x 1 (FR3D_OPT_WARP_TILE)
     int sor_stages = 0;      // stages per warp of the staged kernel, 0 = default (FR3D_OPT_SOR_STAGES)
     int resize_x_rows = 1;   // FR3D_OPT_RESIZE_X_ROWS: X resampling pass with 4 rows per thread sharing the tap look-ups
     int spline_tma = 1;      // FR3D_OPT_SPLINE_TMA: bulk-copy (TMA) staging of the spline X pass

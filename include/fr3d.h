@@ -147,6 +147,10 @@ typedef enum {
                                    * of round-robin; bit 7 = psi-refresh items enumerated first, equally many per warp
                                    * (measured slower on B200).  -1 (default) = 20 for the float64 state, 0 for float32.
                                    * Scheduling only: results are bit-identical */
+    FR3D_OPT_SOR_FRAMES_PER_ITEM = 10, /* frames one warp work item of the wavefront kernels covers (0 = default 2; tuning aid,
+                                   * bit-identical) */
+    FR3D_OPT_WARP_TILE = 11,      /* gather block shape in outputs, tx | ty << 8 | tz << 16 with tx*ty*tz == 256 (0 = default
+                                   * 32 x 8 x 1; tuning aid, bit-identical) */
     FR3D_OPT_SOR_TILE = 6         /* tile kernel geometry: Tb | K << 8 | J << 16 | I << 24 (sweeps per time block and
                                    * tile extents; a 0 field keeps its default: 5 sweeps, 8 x 8 x 8) */
 } fr3d_option;

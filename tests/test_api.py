@@ -53,6 +53,9 @@ def test_no_cpu_fallback_without_library(monkeypatch, tmp_path):
     assert _lib.library_path() == ROOT / "flowreg3d_b200" / "libfr3d.so" and not _lib.is_emulator()
     src = (ROOT / "flowreg3d_b200" / "_lib.py").read_text() + (ROOT / "flowreg3d_b200" / "device.py").read_text()
     assert "os.environ" not in src and "getenv" not in src
+    # ... and the CUDA library reads no environment either: every tuning aid is an fr3d_set_option value
+    for f in (ROOT / "flowreg3d_b200" / "csrc").iterdir():
+        assert "getenv" not in f.read_text(), f
 
 
 def test_product_never_imports_oracle():

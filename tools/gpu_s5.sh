@@ -2,7 +2,7 @@
 # GPU session 5 (single GPU): frames-per-item sweep of the wavefront kernel, full test-suite, bench (both arms), ncu
 O=gpurun_out/s5; mkdir -p $O
 for fg in 1 2 3 4 5 8; do
-  FR3D_SOR_FG=$fg timeout 300 python tools/sor_ab.py --states f64 f32 --kernels 0 > $O/fg$fg.log 2>&1; echo "fg $fg rc $?" | tee -a $O/rc.txt
+  timeout 300 python tools/sor_ab.py --frames-per-item $fg --states f64 f32 --kernels 0 > $O/fg$fg.log 2>&1; echo "fg $fg rc $?" | tee -a $O/rc.txt
 done
 timeout 1500 python -m pytest tests -m gpu -x -q > $O/pytest.log 2>&1; echo "pytest rc $?" | tee -a $O/rc.txt
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc $?" | tee -a $O/rc.txt

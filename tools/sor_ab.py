@@ -33,6 +33,7 @@ ap.add_argument("--ctas", type=int, nargs="*", default=[0])
 ap.add_argument("--kernels", type=int, nargs="*", default=[0, 2], help="0 direct wavefront, 1 staged wavefront, 2 tiles")
 ap.add_argument("--tiles", nargs="*", default=["0"], help="FR3D_OPT_SOR_TILE values Tb,K,J,I (e.g. 5,8,8,8) for kernel 2")
 ap.add_argument("--sched", type=int, nargs="*", default=[0], help="FR3D_OPT_SOR_SCHED values for kernel 0")
+ap.add_argument("--frames-per-item", type=int, default=0, help="FR3D_OPT_SOR_FRAMES_PER_ITEM (0 = default 2)")
 ap.add_argument("--lag", type=int, default=5, help="update_lag (psi refresh every lag sweeps)")
 ap.add_argument("--library", default=None, help="a tuning build of libfr3d.so (CUDA) instead of the in-tree one")
 args = ap.parse_args()
@@ -66,6 +67,7 @@ def run(state, kernel, stages, ctas, tile="0", sched=0):
     core._check(h, lib.fr3d_set_option(h, _lib.OPT_SOR_CTAS_PER_SM, ctas))
     core._check(h, lib.fr3d_set_option(h, _lib.OPT_SOR_TILE, tile_code(tile)))
     core._check(h, lib.fr3d_set_option(h, _lib.OPT_SOR_SCHED, sched))
+    core._check(h, lib.fr3d_set_option(h, _lib.OPT_SOR_FRAMES_PER_ITEM, args.frames_per_item))
     flow = reg.get_displacement(dev_frames)
     reg.sync()
     reg.ctx.profile(True)
