@@ -58,13 +58,23 @@ namespace fr3d {
 #endif
 template <class ST>
 struct SorTune;
+//   ticket-dealt kernel, float64 state: ONE CTA of 384 threads per SM (12 warps at 168 registers, no spills) -- with
+//   round-robin dealing fewer warps lose (52.2 vs 50.1 ms), with tickets they win (47.3 vs 48.4 ms; results/r02_sor_sched.md)
+#ifndef FR3D_SOR_F64_DYN_THREADS
+#define FR3D_SOR_F64_DYN_THREADS 384
+#endif
+#ifndef FR3D_SOR_F64_DYN_MINB
+#define FR3D_SOR_F64_DYN_MINB 1
+#endif
 template <>
 struct SorTune<double> {
     static constexpr int kPair = FR3D_SOR_F64_PAIR, kMinBlocks = FR3D_SOR_F64_MINB, kNbrCa = 1;
+    static constexpr int kDynThreads = FR3D_SOR_F64_DYN_THREADS, kDynMinBlocks = FR3D_SOR_F64_DYN_MINB;
 };
 template <>
 struct SorTune<float> {
     static constexpr int kPair = 0, kMinBlocks = FR3D_SOR_F32_MINB, kNbrCa = 0;
+    static constexpr int kDynThreads = 256, kDynMinBlocks = FR3D_SOR_F32_MINB;
 };
 
 template <class ST>
@@ -979,7 +989,7 @@ fr3d_sor_wavefront(const SorParams<ST> P, unsigned* bar, int tabs_in_smem)
 //    that warps which drew cheap items (L2 hits) take more of them and the wave ends within one item's time on all
 //    warps.  A ticket is drawn one item ahead of its use (the atomic's latency hides behind the update in between).
 template <class ST, int C, bool BAL>
-__global__ void __launch_bounds__(FR3D_SOR_THREADS, SorTune<ST>::kMinBlocks)
+__global__ void __launch_bounds__(SorTune<ST>::kDynThreads, SorTune<ST>::kDynMinBlocks)
 fr3d_sor_wavefront_dyn(const SorParams<ST> P, unsigned* bar, int tabs_in_smem)
 {
     extern __shared__ int32_t fr3d_sor_smem[];
@@ -1798,6 +1808,7 @@ inline void sor_run_c(Device& dev, const SorParams<ST>& P, unsigned* bar, int pe
     const bool slab = dev.sor_k1 > 0;
     FR3D_REQUIRE(!slab || dev.sor_k1 < 32768, "z-slab solve: more than 32767 planes");
     int per_sm = 0;
+    int threads = FR3D_SOR_THREADS;
     SorParams<ST> Pc = P;
     const int nwaves = P.q_end - P.q_begin;
     if (slab || nwaves < 0 || 32 + nwaves > FR3D_SOR_BAR_WORDS)
@@ -1819,12 +1830,13 @@ inline void sor_run_c(Device& dev, const SorParams<ST>& P, unsigned* bar, int pe
         FR3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fr3d_sor_wavefront_split<ST, C>,
                                                                 FR3D_SOR_THREADS, dyn));
 #endif
-    else if (bal)
-        FR3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fr3d_sor_wavefront_dyn<ST, C, true>,
-                                                                FR3D_SOR_THREADS, dyn));
-    else if (tickets)
-        FR3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fr3d_sor_wavefront_dyn<ST, C, false>,
-                                                                FR3D_SOR_THREADS, dyn));
+    else if (bal || tickets) {
+        threads = SorTune<ST>::kDynThreads;
+        if (bal)
+            FR3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fr3d_sor_wavefront_dyn<ST, C, true>, threads, dyn));
+        else
+            FR3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fr3d_sor_wavefront_dyn<ST, C, false>, threads, dyn));
+    }
     else
         FR3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fr3d_sor_wavefront<ST, C>,
                                                                 FR3D_SOR_THREADS, dyn));
@@ -1832,7 +1844,7 @@ inline void sor_run_c(Device& dev, const SorParams<ST>& P, unsigned* bar, int pe
     if (dev.sor_ctas_per_sm > 0 && per_sm > dev.sor_ctas_per_sm)
         per_sm = dev.sor_ctas_per_sm;
     // no more CTAs than the busiest wave can use
-    const int wpb = FR3D_SOR_THREADS / 32;
+    const int wpb = threads / 32;
     int64_t want = ((int64_t)peak_items + wpb - 1) / wpb;
     int grid = dev.sm_count * per_sm;
     if (want < grid)
@@ -1850,11 +1862,11 @@ inline void sor_run_c(Device& dev, const SorParams<ST>& P, unsigned* bar, int pe
                                               args, dyn, dev.stream));
 #endif
     else if (bal)
-        FR3D_CUDA(cudaLaunchCooperativeKernel((void*)fr3d_sor_wavefront_dyn<ST, C, true>, dim3(grid),
-                                              dim3(FR3D_SOR_THREADS), args, dyn, dev.stream));
+        FR3D_CUDA(cudaLaunchCooperativeKernel((void*)fr3d_sor_wavefront_dyn<ST, C, true>, dim3(grid), dim3(threads), args,
+                                              dyn, dev.stream));
     else if (tickets)
-        FR3D_CUDA(cudaLaunchCooperativeKernel((void*)fr3d_sor_wavefront_dyn<ST, C, false>, dim3(grid),
-                                              dim3(FR3D_SOR_THREADS), args, dyn, dev.stream));
+        FR3D_CUDA(cudaLaunchCooperativeKernel((void*)fr3d_sor_wavefront_dyn<ST, C, false>, dim3(grid), dim3(threads), args,
+                                              dyn, dev.stream));
     else
         FR3D_CUDA(cudaLaunchCooperativeKernel((void*)fr3d_sor_wavefront<ST, C>, dim3(grid), dim3(FR3D_SOR_THREADS),
                                               args, dyn, dev.stream));

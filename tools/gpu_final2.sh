@@ -1,7 +1,7 @@
 #!/bin/bash
-# final check of the round on one GPU after the ticket-dealt waves became the float64 default: the whole GPU suite,
+# final check of the round on one GPU (ticket-dealt waves at 384 threads x 168 registers as the float64 default): the whole GPU suite,
 # smoke(), the driver's bench invocation (both arms), ncu capture + launch list of the new default solver kernel
-O=gpurun_out/final2; mkdir -p $O
+O=gpurun_out/final3; mkdir -p $O
 timeout 1500 python -m pytest tests -m gpu -x -q > $O/pytest.log 2>&1; echo "pytest rc $?" | tee -a $O/rc.txt
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc $?" | tee -a $O/rc.txt
 timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > $O/bench.log 2> $O/bench.err; echo "bench rc $?" | tee -a $O/rc.txt
