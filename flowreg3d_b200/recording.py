@@ -15,13 +15,12 @@ import os
 import warnings
 from dataclasses import dataclass
 from pathlib import Path
-from typing import Any, Callable, List, Optional, Sequence, Union
+from typing import Any, Callable, List, Optional
 
 import numpy as np
 import torch
 
 from .compensate import SequenceCorrector
-from .options import OFOptions
 
 
 @dataclass
@@ -194,20 +193,31 @@ class BatchMotionCorrector:
         self.video_writer = video_writer
         self.w_writer = w_writer
         self.progress_callbacks: List[Callable[[int, int], None]] = []
+        self._progress_trackers: dict = {}      # task id -> (frames done, total), compensate_recording_3D.py:60-62
+        self._total_frames: Optional[int] = None
         self.device = device
         self.cc_prealign = bool(cc_prealign)
         self.lookahead = int(lookahead)
 
     def register_progress_callback(self, callback: Callable[[int, int], None]) -> None:
-        if callback is not None and callable(callback):
+        # compensate_recording_3D.py:124-135: callback(current_frame, total_frames), a callback registers once
+        if callback not in self.progress_callbacks:
             self.progress_callbacks.append(callback)
 
-    def _notify(self, current: int, total: int):
-        for cb in self.progress_callbacks:
-            try:
-                cb(current, total)
-            except Exception as e:  # compensate_recording_3D.py:158-162
-                warnings.warn(f"Progress callback error: {e}")
+    def _notify_progress(self, frames_completed: int, task_id: str = "main") -> None:
+        # compensate_recording_3D.py:137-162: per-task cumulative counters; only the main task (whose total is the
+        # reader's length) reaches the callbacks, a failing callback warns
+        if task_id not in self._progress_trackers:
+            self._progress_trackers[task_id] = (0, self._total_frames if task_id == "main" else None)
+        current, total = self._progress_trackers[task_id]
+        current += frames_completed
+        self._progress_trackers[task_id] = (current, total)
+        if task_id == "main" and total and self.progress_callbacks:
+            for cb in self.progress_callbacks:
+                try:
+                    cb(current, total)
+                except Exception as e:
+                    warnings.warn(f"Progress callback error: {e}")
 
     # -- I/O (compensate_recording_3D.py:164-196, OF_options_3D.py:405-463) ---------------------------------------
     def _setup_io(self):
@@ -262,11 +272,10 @@ class BatchMotionCorrector:
         self._setup_io()
         self._setup_reference(reference_frame)
         reader, writer, o = self.video_reader, self.video_writer, self.options
-        total = len(reader) if hasattr(reader, "__len__") else None
+        self._total_frames = len(reader) if hasattr(reader, "__len__") else None     # :438-439
         seq = SequenceCorrector(self.reference_raw, o, device=self.device, statistics=True,
                                 cc_prealign=self.cc_prealign)
         dtypes: List[np.dtype] = []
-        done = [0]
 
         def batches():
             while reader.has_batch():
@@ -285,8 +294,7 @@ class BatchMotionCorrector:
             writer.write_frames(reg.astype(dtypes[k], copy=True))
             if getattr(o, "save_w", False) and self.w_writer is not None:
                 self.w_writer.write_frames(np.array(fl))
-            done[0] += reg.shape[0]
-            self._notify(done[0], total if total is not None else done[0])
+            self._notify_progress(reg.shape[0])
 
         try:
             seq.run_stream(batches(), sink, lookahead=self.lookahead)

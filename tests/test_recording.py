@@ -78,6 +78,41 @@ def test_compensate_recording_npy_files_and_reference_indices(emu_backend, golde
                                            reference_frames=[0], **KW))
 
 
+def test_registration_config_and_progress_protocol():
+    """The reference's own unit tests for this surface (tests/motion_correction/test_compensate_recording_3D.py:24-47,
+    435-481, 532-560), on this package's objects."""
+    from unittest.mock import patch
+    import flowreg3d_b200 as F
+    c = F.RegistrationConfig()
+    assert (c.n_jobs, c.batch_size, c.verbose, c.parallelization) == (-1, 10, False, None)
+    c = F.RegistrationConfig(n_jobs=2, batch_size=5, verbose=True, parallelization="threading3d")
+    assert (c.n_jobs, c.batch_size, c.verbose, c.parallelization) == (2, 5, True, "threading3d")
+    opts = F.OFOptions(input_file="dummy.h5", output_path="unused", quality_setting="fast", levels=2, iterations=5)
+    pipe = F.BatchMotionCorrector(opts)
+    calls = []
+    cb = lambda cur, tot: calls.append((cur, tot))  # noqa: E731
+    pipe.register_progress_callback(cb)
+    pipe.register_progress_callback(cb)
+    assert len(pipe.progress_callbacks) == 1
+    pipe._total_frames = 100
+    for n in (10, 15, 20, 25, 30):
+        pipe._notify_progress(n)
+    pipe._notify_progress(7, task_id="other")          # other tasks are tracked, not reported
+    assert calls == [(10, 100), (25, 100), (45, 100), (70, 100), (100, 100)]
+    ref = np.random.rand(4, 16, 16, 2).astype(np.float32)
+    with patch.object(F.BatchMotionCorrector, "run") as run:
+        run.return_value = ref
+        cfg = F.RegistrationConfig(n_jobs=1, batch_size=5, verbose=True, parallelization="sequential3d")
+        assert np.array_equal(F.compensate_recording(opts, ref, cfg), ref)
+        run.assert_called_once_with(ref)
+    with patch.object(F.BatchMotionCorrector, "run") as run:
+        run.return_value = ref
+        assert np.array_equal(F.compensate_recording(opts), ref)
+        run.assert_called_once_with(None)
+    with pytest.raises(NotImplementedError):            # an .h5 path needs the reference's reader object
+        F.BatchMotionCorrector(F.OFOptions(input_file="dummy.h5", output_path="/tmp/fr3d_unused_out"))._setup_io()
+
+
 def test_array_reader_protocol():
     from flowreg3d_b200.recording import ArrayReader3D, ArrayWriter3D, NpyFileWriter3D
     a = np.arange(7 * 2 * 3 * 4 * 1, dtype=np.float32).reshape(7, 2, 3, 4, 1)
