@@ -11,7 +11,6 @@ formats that need nothing but numpy: in-memory arrays (`ArrayReader3D` / `ArrayW
 files through memory maps (`NpyFileReader3D` / `NpyFileWriter3D`), which is what an out-of-core run uses here."""
 from __future__ import annotations
 
-import os
 import warnings
 from dataclasses import dataclass
 from pathlib import Path
@@ -164,10 +163,6 @@ class NpyFileWriter3D:
             self._mm = None
 
 
-def _is_reader(x) -> bool:
-    return hasattr(x, "has_batch") and hasattr(x, "read_batch")
-
-
 def _fmt(x) -> str:
     return str(getattr(x, "value", x)).upper()
 
@@ -188,6 +183,7 @@ class BatchMotionCorrector:
         self.mean_div: List[float] = []
         self.mean_translation: List[float] = []
         self.reference_raw: Optional[np.ndarray] = None
+        self.weight: Optional[np.ndarray] = None
         self.w_init: Optional[np.ndarray] = None
         self.video_reader = None
         self.video_writer = video_writer
@@ -198,6 +194,17 @@ class BatchMotionCorrector:
         self.device = device
         self.cc_prealign = bool(cc_prealign)
         self.lookahead = int(lookahead)
+        # (:64-74) the reference sizes its CPU worker pool here; kept as attributes, the GPU path has one worker
+        if self.config.n_jobs == -1:
+            import os
+            self.n_workers = os.cpu_count() or 4
+        else:
+            self.n_workers = self.config.n_jobs
+        # (:76-121) the executor object of the pipeline: this package's BaseExecutor3D implementation.  run() drives
+        # the same kernels through SequenceCorrector (batches stay on the device between the stages); the executor is
+        # what the reference's own BatchMotionCorrector would call (tests/test_reference_plugin.py).
+        from .executor import B200Executor3D
+        self.executor = B200Executor3D(n_workers=1, device=device)
 
     def register_progress_callback(self, callback: Callable[[int, int], None]) -> None:
         # compensate_recording_3D.py:124-135: callback(current_frame, total_frames), a callback registers once
@@ -224,36 +231,34 @@ class BatchMotionCorrector:
         o = self.options
         out_dir = Path(getattr(o, "output_path", "results"))
         out_dir.mkdir(parents=True, exist_ok=True)
-        src = getattr(o, "input_file", None)
-        bs, bin_size = int(o.buffer_size), int(getattr(o, "bin_size", 1))
-        if _is_reader(src):
-            self.video_reader = src
-        elif isinstance(src, np.ndarray):
-            self.video_reader = ArrayReader3D(src, bs, bin_size)
-        elif isinstance(src, (str, os.PathLike)) and str(src).lower().endswith(".npy"):
-            self.video_reader = NpyFileReader3D(src, bs, bin_size)
-        elif src is None:
-            raise ValueError("options.input_file is not set")
-        else:
-            raise NotImplementedError(
-                f"no reader for {src!r} in this package (arrays and .npy files only): pass a reader object with the "
-                "reference's protocol as options.input_file, e.g. flowreg3d.util.io.factory.get_video_file_reader(...)")
+        if hasattr(o, "get_video_reader"):
+            self.video_reader = o.get_video_reader()
+        else:       # an options object without the getters: the same factory
+            from . import io_factory
+            self.video_reader = io_factory.get_video_file_reader(getattr(o, "input_file", None),
+                                                                 buffer_size=int(o.buffer_size),
+                                                                 bin_size=int(getattr(o, "bin_size", 1)))
         fmt = _fmt(getattr(o, "output_format", "ARRAY"))
         if self.video_writer is None:
-            if fmt == "ARRAY":
-                self.video_writer = ArrayWriter3D()
-            elif fmt == "NPY":
-                name = getattr(o, "output_file_name", None) or str(out_dir / "compensated.npy")
-                self.video_writer = NpyFileWriter3D(name, len(self.video_reader))
+            if hasattr(o, "get_video_writer"):
+                self.video_writer = o.get_video_writer()
             else:
-                raise NotImplementedError(
-                    f"no writer for output_format {fmt} in this package (ARRAY and NPY only): pass video_writer=<object "
-                    "with write_frames / close>, e.g. flowreg3d.util.io.factory.get_video_file_writer(...)")
+                from . import io_factory
+                self.video_writer = io_factory.get_video_file_writer(str(out_dir / f"compensated.{fmt}"), fmt,
+                                                                     frame_count=len(self.video_reader))
         if getattr(o, "save_w", False) and self.w_writer is None:
-            if fmt == "ARRAY":
-                self.w_writer = ArrayWriter3D()
-            else:
-                self.w_writer = NpyFileWriter3D(out_dir / "w.npy", len(self.video_reader))
+            from . import io_factory
+            try:
+                if fmt == "ARRAY":       # (:175-182) flows stay in memory when the frames do
+                    self.w_writer = io_factory.get_video_file_writer(None, "ARRAY")
+                else:                    # (:183-190: w.h5 with datasets u, v, w in the reference; w.npy (T,Z,Y,X,3) here)
+                    n = len(self.video_reader) if hasattr(self.video_reader, "__len__") else 0
+                    self.w_writer = io_factory.get_video_file_writer(str(out_dir / "w.npy"), "NPY", frame_count=n,
+                                                                     dataset_names=["u", "v", "w"])
+            except Exception as e:       # (:191-196)
+                warnings.warn(f"Failed to create displacement writer: {e}. Displacements will not be saved.")
+                self.w_writer = None
+                o.save_w = False
 
     def _setup_reference(self, reference_frame):
         o = self.options
@@ -266,6 +271,12 @@ class BatchMotionCorrector:
             else:
                 reference_frame = o.get_reference_frame(None)
         self.reference_raw = np.asarray(reference_frame).astype(np.float64)
+        # (:207-224) the per-channel data weights as a full (Z,Y,X,C) array
+        Z, Y, X = self.reference_raw.shape[:3]
+        n_channels = self.reference_raw.shape[3] if self.reference_raw.ndim == 4 else 1
+        self.weight = np.ones((Z, Y, X, n_channels), dtype=np.float64)
+        for c in range(n_channels):
+            self.weight[..., c] = o.get_weight_at(c, n_channels)
 
     # -- the pipeline (compensate_recording_3D.py:431-557) -----------------------------------------------------------
     def run(self, reference_frame: Optional[np.ndarray] = None) -> np.ndarray:

@@ -1,0 +1,57 @@
+"""The reference's OWN test files, unmodified, against this package ("run unmodified against the new
+shims to validate the boundary").  tests/ref_shim/fr3d_ref_shim.py aliases the `flowreg3d.*` module names the tests
+import to flowreg3d_b200 modules (kernel-logic emulator as the backend) and pytest runs the files where they lie under
+/root/reference/tests -- nothing is copied.  Every test that is expected NOT to pass is listed below with the reason;
+anything else failing fails this test.  Runs only where the reference tree is present (not on the GPU box)."""
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+REF_TESTS = Path("/root/reference/tests/motion_correction")
+pytestmark = pytest.mark.skipif(not REF_TESTS.is_dir(), reason="reference source tree not present")
+
+WORKER_POOL = "the reference's CPU executor registry / worker-pool selection, which this package does not have"
+EXPECTED_FAILURES = {
+    "test_OF_options_3D.py": {
+        "TestReference3DHandling::test_reference_tiff_file_3d": "needs the tifffile package (absent in this image)",
+        "TestSaveLoad3D::test_save_load_with_3d_reference": "asserts a .tif side file; without tifffile the reference "
+                                                            "volume is stored as reference_frames.npy",
+    },
+    "test_compensate_arr_3D.py": {
+        "TestArrayReaderWriter3DIntegration::test_3d_array_reader_creation":
+            "asserts that compensate_arr_3D goes through the reader factory; here the array entry copies straight "
+            "from / into the caller's arrays (DESIGN 5, host costs)",
+        "TestArrayReaderWriter3DIntegration::test_3d_array_writer_creation": "same, for the writer factory",
+    },
+    "test_compensate_recording_3D.py": {
+        "TestBatchMotionCorrector3D::test_3d_executor_setup_specific_selection": WORKER_POOL,
+        "TestBatchMotionCorrector3D::test_3d_executor_fallback": WORKER_POOL,
+        "TestErrorHandling3D::test_3d_executor_instantiation_error": WORKER_POOL,
+        "TestReferenceSetup3D::test_3d_reference_preprocessing":
+            "mocks flowreg3d.util.image_processing_3D.normalize / apply_gaussian_filter; the pre-filter here is the CUDA "
+            "kernel pair behind fr3d_preprocess",
+        "TestFlowComputation3D::test_3d_batch_processing_parallel":
+            "calls the private _process_batch_parallel with a mocked executor; batches here run through "
+            "SequenceCorrector.process_batch",
+    },
+}
+MIN_PASSED = {"test_OF_options_3D.py": 28, "test_compensate_arr_3D.py": 20, "test_compensate_recording_3D.py": 17}
+
+
+@pytest.mark.parametrize("name", sorted(EXPECTED_FAILURES))
+def test_reference_test_file_passes_against_this_package(emu_backend, name):
+    env = dict(os.environ, PYTHONPATH=str(ROOT / "tests" / "ref_shim"), NUMBA_CACHE_DIR="/tmp/numba_cache")
+    cmd = [sys.executable, "-m", "pytest", str(REF_TESTS / name), "-p", "fr3d_ref_shim",
+           f"--confcutdir={REF_TESTS}", "-p", "no:cacheprovider", "-q", "-rf", "--no-header"]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900, cwd="/tmp").stdout
+    failed = set(re.findall(r"^(?:FAILED|ERROR) \S*?" + re.escape(name) + r"::(\S+)", out, flags=re.M))
+    m = re.search(r"(\d+) passed", out)
+    passed = int(m.group(1)) if m else 0
+    unexpected = failed - set(EXPECTED_FAILURES[name])
+    assert not unexpected, (sorted(unexpected), out[-3000:])
+    assert passed >= MIN_PASSED[name], (passed, out[-3000:])
