@@ -65,6 +65,11 @@ _alias("flowreg3d.motion_correction.OF_options_3D", O)          # the real modul
 _alias("flowreg3d.motion_correction.compensate_arr_3D", C)
 _alias("flowreg3d.motion_correction.compensate_recording_3D", R)
 _mod("flowreg3d.util")
+from flowreg3d_b200 import core as K, xcorr as X  # noqa: E402
+
+_alias("flowreg3d.util.xcorr_prealignment", X)
+_mod("flowreg3d.core")
+_alias("flowreg3d.core.optical_flow_3d", K)
 _mod("flowreg3d.util.io")
 _alias("flowreg3d.util.io.factory", io_factory)
 _alias("flowreg3d.util.io._arr_3d", R)
