@@ -42,9 +42,13 @@ EXPECTED_FAILURES = {
             "SequenceCorrector.process_batch",
     },
 }
+EXPECTED_FAILURES["test_parallelization.py"] = {       # progress callbacks through compensate_arr_3D etc. pass
+    "TestParallelizationExecutors::test_all_executors_available": WORKER_POOL,
+    "TestParallelizationExecutors::test_sequential_executor": WORKER_POOL + " (asserts the executor's class name)",
+}
 EXPECTED_FAILURES["test_xcorr_prealignment.py"] = {}      # the six known-answer tests of the rigid pre-alignment: all pass
 MIN_PASSED = {"test_OF_options_3D.py": 28, "test_compensate_arr_3D.py": 20, "test_compensate_recording_3D.py": 17,
-              "test_xcorr_prealignment.py": 6}
+              "test_xcorr_prealignment.py": 6, "test_parallelization.py": 6}
 
 
 @pytest.mark.parametrize("name", sorted(EXPECTED_FAILURES))
