@@ -1,5 +1,7 @@
 #!/bin/bash
-# Item scheduling of the wavefront kernel (FR3D_OPT_SOR_SCHED): dynamic tickets, early locate, first-item prefetch.
+# Item scheduling of the wavefront kernel (FR3D_OPT_SOR_SCHED = percent of each wave dealt by ticket).  The first run of
+# this script also carried the early-locate / first-item-prefetch switches (values 256 / 768), which were removed
+# after they measured no gain (results/r02_sor_sched.md).
 mkdir -p gpurun_out/sched
 timeout 900 python tools/sor_ab.py --kernels 0 --states f64 f32 --reps 3 \
     --sched 0 10 20 30 40 60 100 > gpurun_out/sched/ab.jsonl 2> gpurun_out/sched/ab.err
