@@ -301,23 +301,29 @@ class SequenceCorrector:
         out_reg = list(out_reg) if out_reg is not None else [None] * K
         out_flow = list(out_flow) if out_flow is not None else [None] * K
         tmax = max([b.shape[0] for b in hb], default=0)
-        cyc_reg, cyc_flow = {}, {}
+        # sink mode: two cycling pinned result buffers per kind, kept on the corrector -- run_stream calls this method once
+        # per window of the stream, and page-locking fresh host memory costs more than the copies it serves
+        # (cudaHostAlloc 2.6 GB/s on the box, results/r02_host_costs.txt)
+        cyc = self.__dict__.setdefault("_cyc_out", {})
+
+        def cycling(kind, slot, last):
+            buf = cyc.get((kind, slot))
+            if buf is None or buf.shape[0] < tmax or tuple(buf.shape[1:]) != (Z, Y, X, last):
+                buf = cyc[(kind, slot)] = torch.empty((tmax, Z, Y, X, last), dtype=torch.float32, pin_memory=True)
+            return buf
+
         for k in range(K):
             t = hb[k].shape[0]
             if out_reg[k] is None:
-                if sink is not None:  # two cycling buffers
-                    if k % 2 not in cyc_reg:
-                        cyc_reg[k % 2] = torch.empty((tmax, Z, Y, X, self.C), dtype=torch.float32).pin_memory()
-                    out_reg[k] = cyc_reg[k % 2]
+                if sink is not None:
+                    out_reg[k] = cycling("reg", k % 2, self.C)
                 else:
-                    out_reg[k] = torch.empty((t, Z, Y, X, self.C), dtype=torch.float32).pin_memory()
+                    out_reg[k] = torch.empty((t, Z, Y, X, self.C), dtype=torch.float32, pin_memory=True)
             if out_flow[k] is None:
                 if sink is not None:
-                    if k % 2 not in cyc_flow:
-                        cyc_flow[k % 2] = torch.empty((tmax, Z, Y, X, 3), dtype=torch.float32).pin_memory()
-                    out_flow[k] = cyc_flow[k % 2]
+                    out_flow[k] = cycling("flow", k % 2, 3)
                 else:
-                    out_flow[k] = torch.empty((t, Z, Y, X, 3), dtype=torch.float32).pin_memory()
+                    out_flow[k] = torch.empty((t, Z, Y, X, 3), dtype=torch.float32, pin_memory=True)
         ev_in, ev_done, ev_out = [None] * K, [None] * K, [None] * K
 
         def drain(k):
@@ -410,6 +416,7 @@ class SequenceCorrector:
                 "mean_translation": a[:, 3].tolist()}
 
     def close(self):
+        self.__dict__.pop("_cyc_out", None)
         if isinstance(self.reg, SplitRegistration):
             self.reg.close()
         else:
