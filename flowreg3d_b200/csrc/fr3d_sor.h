@@ -305,6 +305,8 @@ FR3D_HD SorLoc sor_locate(const SorParams<ST>& P, const SorTabs& tb, int q, cons
 // refresh chunks first, then plain chunks, as ONE index range dealt round-robin: every warp gets the same number of
 // refresh items (+-1) and the heavy items run first.  Refresh hyperplanes of wave q are s = q (mod 2 lag); peR is
 // the chunk prefix over that residue class.
+// MEASURED SLOWER than the mixed order (52.4 vs 50.1 ms, results/r02_sor_sched.md): a wave of two homogeneous phases --
+// all warps streaming J, then all warps sweeping -- overlaps worse than the mix.  Kept as an option (bit 7), not a default.
 struct SorKinds {
     int nR;     // refresh hyperplanes in the wave
     int s_min;  // the lowest of them
